@@ -1,0 +1,235 @@
+/*
+ * b200nerf.h — C-ABI of libb200nerf.so, the B200 (sm_100a) volumetric-rendering core.
+ *
+ * This is the drop-in boundary of SURVEY.md §8(b).  The reference (nerfstudio v1.1.5) has no FFI of its
+ * own: its hot path calls three un-vendored CUDA packages (tiny-cuda-nn, nerfacc, gsplat) or falls back to
+ * PyTorch ops.  Every entry point below replaces one of those call sites; the comment above each group
+ * cites the reference file:line (relative to nerfstudio/) whose arithmetic it reproduces.
+ *
+ * Conventions
+ *   - every function is `extern "C" int f(..., void* stream)`; `stream` is a cudaStream_t (NULL = default).
+ *   - return 0 on success; negative = argument error (B2N_E_*); positive = cudaError_t of the launch.
+ *     b2n_last_error() returns a static string describing the last failure on the calling thread.
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`; tensors are dense row-major fp32
+ *     unless stated; int64 for index tensors that the reference exposes as torch.long.
+ *   - the library allocates nothing persistent; outputs and workspaces are caller-allocated.
+ *   - there is NO CPU fallback anywhere behind this header.
+ */
+#ifndef B200NERF_H
+#define B200NERF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2N_OK 0
+#define B2N_E_ARG (-1)      /* bad argument (null pointer, size out of range) */
+#define B2N_E_UNSUPPORTED (-2) /* configuration outside what the kernels are built for */
+
+#define B2N_MAX_LEVELS 32
+#define B2N_MAX_MLP_LAYERS 10
+
+/* grid addressing mode */
+#define B2N_GRID_TORCH 0 /* nerfstudio torch path: field_components/encodings.py:398-458 */
+#define B2N_GRID_TCNN 1  /* tiny-cuda-nn HashGrid semantics; parity unpinned */
+
+/* activations (field_components/mlp.py:33-58 names) */
+#define B2N_ACT_NONE 0
+#define B2N_ACT_RELU 1
+#define B2N_ACT_SIGMOID 2
+#define B2N_ACT_SOFTPLUS 3
+#define B2N_ACT_TANH 4
+
+/* spacing functions of SpacedSampler subclasses (model_components/ray_samplers.py:131-248) */
+#define B2N_SPACING_UNIFORM 0
+#define B2N_SPACING_PIECEWISE 1 /* UniformLinDispPiecewiseSampler */
+#define B2N_SPACING_LINDISP 2
+#define B2N_SPACING_SQRT 3
+#define B2N_SPACING_LOG 4
+
+/* background handling of RGBRenderer (model_components/renderers.py:71-119) */
+#define B2N_BG_NONE 0        /* "random": nothing blended */
+#define B2N_BG_LAST_SAMPLE 1
+#define B2N_BG_CONSTANT 2    /* white / black / explicit colour: bg[3] */
+
+/* Multiresolution grid description (host struct, passed by pointer, copied into kernel params). */
+typedef struct B2nGrid {
+  int32_t n_levels;
+  int32_t n_features; /* per level: 1, 2, 4 or 8 */
+  int32_t log2_hashmap_size;
+  int32_t mode; /* B2N_GRID_* */
+  float scale[B2N_MAX_LEVELS];     /* torch: encoder.scalings[l]; tcnn: exp2(l*log2(g))*base-1 */
+  uint32_t resolution[B2N_MAX_LEVELS]; /* tcnn: ceil(scale)+1 (dense stride); unused in torch mode */
+  uint32_t offset[B2N_MAX_LEVELS];     /* first table row of the level (torch: l*T) */
+  uint32_t size[B2N_MAX_LEVELS];       /* rows in the level (torch: T) */
+  uint32_t hashed[B2N_MAX_LEVELS];     /* 1 = XOR-prime hash, 0 = dense index */
+} B2nGrid;
+
+/* Tiny MLP description (host struct).  Layer i maps in_i -> out_i with nn.Linear layout W[out_i][in_i]
+ * (+ bias[out_i]; b[i] == NULL means no bias, as tcnn networks have none).  w/b are DEVICE pointers — the
+ * reference keeps one nn.Parameter per layer (`layers.i.weight/bias`), so the boundary takes them as they are.
+ * skip[i] != 0 means the layer input is cat([network_input, previous_hidden]) (mlp.py:172-173). */
+typedef struct B2nMlp {
+  int32_t n_layers;
+  int32_t in_dim;
+  int32_t hidden_act; /* B2N_ACT_* applied after every layer but the last */
+  int32_t out_act;    /* B2N_ACT_* applied after the last layer */
+  int32_t out_dims[B2N_MAX_MLP_LAYERS];
+  int32_t skip[B2N_MAX_MLP_LAYERS];
+  const float* w[B2N_MAX_MLP_LAYERS];
+  const float* b[B2N_MAX_MLP_LAYERS];
+} B2nMlp;
+/* gradient destinations (device pointers, same shapes as w/b); entries may be NULL to skip; ACCUMULATED into */
+typedef struct B2nMlpGrad {
+  float* dw[B2N_MAX_MLP_LAYERS];
+  float* db[B2N_MAX_MLP_LAYERS];
+} B2nMlpGrad;
+
+const char* b2n_version(void);
+const char* b2n_last_error(void);
+/* device properties the host side sizes grids with: fills sm_count, cc_major, cc_minor, max_smem_optin */
+int b2n_device_info(int32_t* out4_host);
+/* launch-geometry knobs (e.g. "hash_levels_per_block_fwd"); returns 1 if the key exists */
+int b2n_tune(const char* key, int value);
+
+/* ---- K1/K2: multiresolution hash grid --------------------------------------------------------------
+ * replaces HashEncoding.pytorch_fwd / tcnn.Encoding("HashGrid")   field_components/encodings.py:362-365,417-463
+ * x [N,3] in [0,1];  table [rows,F] fp32;  y [N, L*F] (row-major, level-major features).
+ * idx_out (optional, may be NULL): int64 [N,L,8] corner rows in the reference's hashed_0..7 order (for parity). */
+int b2n_hashgrid_fwd(const B2nGrid* grid_host, const float* x, const float* table, int64_t n, float* y,
+                     int64_t* idx_out, void* stream);
+/* dtable [rows,F] is ACCUMULATED into (caller zeroes);  dx [N,3] optional (NULL = skip) is overwritten. */
+int b2n_hashgrid_bwd(const B2nGrid* grid_host, const float* x, const float* table, const float* dy, int64_t n,
+                     float* dtable, float* dx, void* stream);
+
+/* ---- K3: tiny fused MLP (fp32 SIMT) -----------------------------------------------------------------
+ * replaces MLP.pytorch_fwd / tcnn.Network   field_components/mlp.py:110-114,160-184
+ * x [N,in] row-major, y [N,out_last].  `hidden` (optional workspace, required for bwd) receives the
+ * post-activation outputs of layers 0..n_layers-2, feature-major: layer i at hidden + hid_off_i,
+ * laid out [out_i][N]; hid_off_i = N * sum_{j<i} out_j.  The whole network must fit in shared memory
+ * (B2N_E_UNSUPPORTED otherwise; all nerfacto / instant-ngp networks do). */
+int b2n_mlp_fwd(const B2nMlp* mlp_host, const float* x, int64_t n, float* y, float* hidden, void* stream);
+/* dx [N,in] optional (NULL = skip), overwritten. */
+int b2n_mlp_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, const float* y,
+                const float* hidden, const float* dy, int64_t n, float* dx, void* stream);
+
+/* ---- K5/K6: direction / frequency encodings ---------------------------------------------------------
+ * SHEncoding (encodings.py:752-799, utils/spherical_harmonics.py:24-81): levels in 1..5, out [N,levels^2].
+ * remap01 != 0 applies d <- (d+1)/2 first (fields/base_field.py:136-142 fused in). */
+int b2n_sh_fwd(const float* dirs, int64_t n, int32_t levels, int32_t remap01, float* out, void* stream);
+/* NeRFEncoding (encodings.py:148-186): out [N, D*F*2 (+D if include_input)], freqs_host[F] = 2^linspace. */
+int b2n_freq_fwd(const float* x, int64_t n, int32_t d, const float* freqs_host, int32_t n_freq,
+                 int32_t include_input, float* out, void* stream);
+int b2n_freq_bwd(const float* x, const float* dout, int64_t n, int32_t d, const float* freqs_host, int32_t n_freq,
+                 int32_t include_input, float* dx, void* stream);
+
+/* ---- a8-a10: sample positions -> unit cube -----------------------------------------------------------
+ * Frustums.get_positions + SceneContraction(inf) + (x+2)/4 | aabb normalise + selector
+ *   cameras/rays.py:50-59; field_components/spatial_distortions.py:66-69; fields/nerfacto_field.py:205-213
+ * Ray form: origins/directions [R,3], starts/ends [R,S] with row stride `bin_stride` (so starts=bins,
+ * ends=bins+1 of an [R,S+1] edge array works).  Point form: pass positions [N,3] with R=N,S=1 and
+ * directions=NULL.  x_out [R*S,3] (already multiplied by the selector), sel_out uint8 [R*S]. */
+int b2n_positions_fwd(const float* origins, const float* directions, const float* starts, const float* ends,
+                      int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,
+                      const float* aabb_host6, float* x_out, uint8_t* sel_out, void* stream);
+
+/* density = avg_init * exp(h) * sel, bwd: dh = g * avg_init * exp(clamp(h,-15,15)) * sel
+ *   field_components/activations.py:28-41; fields/nerfacto_field.py:226-232.  h has row stride h_stride. */
+int b2n_density_act_fwd(const float* h, int64_t h_stride, const uint8_t* sel, int64_t n, float avg_init,
+                        float* density, void* stream);
+int b2n_density_act_bwd(const float* h, int64_t h_stride, const uint8_t* sel, const float* g, int64_t n,
+                        float avg_init, float* dh, int64_t dh_stride, void* stream);
+
+/* ---- a5/a6: samplers --------------------------------------------------------------------------------
+ * SpacedSampler.generate_ray_samples (ray_samplers.py:78-128).  lin [S+1] = linspace(0,1,S+1) computed by the
+ * host with torch (bit-identical bins).  jitter: NULL (eval) | [R] (jitter_stride=0... single) | [R,S+1].
+ * Outputs spacing bins sbins [R,S+1] and euclidean bins ebins [R,S+1]. */
+int b2n_spaced_sample(const float* nears, const float* fars, const float* lin, const float* jitter,
+                      int32_t jitter_per_bin, int64_t n_rays, int32_t n_samples, int32_t spacing,
+                      float* sbins, float* ebins, void* stream);
+/* PDFSampler.generate_ray_samples (ray_samplers.py:276-372), include_original=False.
+ * bins [R,S+1] spacing-domain edges, weights [R,S] (annealing w**anneal fused in: pass anneal=1 for none),
+ * u_base [nb] = linspace(0,1-1/nb,nb) from the host, jitter NULL | [R] | [R,nb].
+ * Outputs new_sbins [R,nb], new_ebins [R,nb]; optional cdf_out [R,S+1], inds_out int64 [R,nb]. */
+int b2n_pdf_sample(const float* bins, const float* weights, const float* u_base, const float* jitter,
+                   int32_t jitter_per_bin, const float* nears, const float* fars, int64_t n_rays, int32_t n_in,
+                   int32_t n_out, float anneal, float histogram_padding, float eps, int32_t spacing,
+                   float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out, void* stream);
+
+/* ---- a21-a23: transmittance weights and compositing ---------------------------------------------------
+ * RaySamples.get_weights (cameras/rays.py:129-152): ebins [R,S+1] euclidean edges, density [R,S] -> w [R,S]. */
+int b2n_weights_fwd(const float* ebins, const float* density, int64_t n_rays, int32_t n_samples, float* weights,
+                    void* stream);
+int b2n_weights_bwd(const float* ebins, const float* density, const float* dweights, int64_t n_rays,
+                    int32_t n_samples, float* ddensity, void* stream);
+/* RGBRenderer + AccumulationRenderer + DepthRenderer(expected|median) (renderers.py:71-119,292-385).
+ * rgb [R,S,3]; outputs rgb_out [R,3], acc [R], depth_exp [R] (unclipped numerator/denominator form; the
+ * global min/max clip of renderers.py:381 is applied by the host with [lo,hi]), depth_med [R], med_idx int64 [R].
+ * Any output pointer may be NULL.  eval_mode: nan_to_num(rgb) before, clamp01 after (renderers.py:225-231). */
+int b2n_composite_fwd(const float* rgb, const float* weights, const float* ebins, int64_t n_rays, int32_t n_samples,
+                      int32_t bg_mode, const float* bg_host3, int32_t eval_mode, float* rgb_out, float* acc,
+                      float* depth_exp, float* depth_med, int64_t* med_idx, void* stream);
+/* grads wrt rgb samples and weights given d_rgb_out [R,3], d_acc [R] (NULL=0), d_depth_exp [R] (NULL=0). */
+int b2n_composite_bwd(const float* rgb, const float* weights, const float* ebins, const float* d_rgb_out,
+                      const float* d_acc, const float* d_depth_exp, int64_t n_rays, int32_t n_samples, int32_t bg_mode,
+                      const float* bg_host3, float* d_rgb, float* d_weights, void* stream);
+
+/* ---- a24: proposal losses (model_components/losses.py:53-155) -------------------------------------------
+ * interlevel term of ONE proposal level: c [R,Sc+1], w [R,Sc] (final level, constants), cp [R,Sp+1], wp [R,Sp].
+ * loss_rows [R] = sum_i clip(w-w_outer,0)^2/(w+1e-7)  (host divides by R*Sc for the mean);
+ * d_wp [R,Sp] = d(sum over the row)/d wp, scaled by `gscale` (NULL = skip). */
+int b2n_interlevel_fwd_bwd(const float* c, const float* w, const float* cp, const float* wp, int64_t n_rays,
+                           int32_t sc, int32_t sp, float gscale, float* loss_rows, float* d_wp, void* stream);
+/* distortion: t [R,S+1], w [R,S] -> loss_rows [R]; d_w [R,S] scaled by gscale (NULL = skip). */
+int b2n_distortion_fwd_bwd(const float* t, const float* w, int64_t n_rays, int32_t s, float gscale, float* loss_rows,
+                           float* d_w, void* stream);
+
+/* ---- a1/a2: ray generation (cameras/cameras.py:599-929; camera_utils.py:318-330,375-478) ---------------
+ * perspective cameras with optional OpenCV distortion (k1,k2,k3,k4,p1,p2), pixel-centre coordinates.
+ * c2w [C,3,4], intr [C,4]=(fx,fy,cx,cy), dist [C,6] or NULL, ray_indices int64 [R,3]=(cam,row,col). */
+int b2n_raygen(const float* c2w, const float* intr, const float* dist, const int64_t* ray_indices, int64_t n_rays,
+               float* origins, float* directions, float* pixel_area, float* directions_norm, int64_t* camera_indices,
+               void* stream);
+/* AABBBoxCollider (model_components/scene_colliders.py:47-108). */
+int b2n_aabb_collide(const float* origins, const float* directions, const float* aabb_host6, float near_plane,
+                     int64_t n_rays, float* nears, float* fars, void* stream);
+
+/* ---- K7-K12: packed (instant-ngp) path; nerfacc 0.5.2 call sites models/instant_ngp.py:120-198 ----------
+ * pack_info: ray_indices int64 [M] sorted -> packed_info int64 [R,2] (start,count). */
+int b2n_pack_info(const int64_t* ray_indices, int64_t m, int64_t n_rays, int64_t* packed_info, void* stream);
+/* render_weight_from_density on packed samples: per-ray exclusive scan of sigma*dt. */
+int b2n_packed_weights_fwd(const float* t_starts, const float* t_ends, const float* sigmas,
+                           const int64_t* packed_info, int64_t n_rays, float* weights, float* trans, float* alphas,
+                           void* stream);
+int b2n_packed_weights_bwd(const float* t_starts, const float* t_ends, const float* sigmas,
+                           const int64_t* packed_info, const float* dweights, int64_t n_rays, float* dsigmas,
+                           void* stream);
+/* accumulate_along_rays: out[r,:] = sum_{i in ray r} w[i]*values[i,:] (values NULL -> D=1, v=1). */
+int b2n_packed_accumulate_fwd(const float* weights, const float* values, int32_t d, const int64_t* packed_info,
+                              int64_t n_rays, float* out, void* stream);
+int b2n_packed_accumulate_bwd(const float* weights, const float* values, int32_t d, const int64_t* packed_info,
+                              const float* dout, int64_t n_rays, float* dweights, float* dvalues, void* stream);
+/* occupancy-grid ray marching, two passes.  binaries uint8 [levels,res,res,res]; roi aabb (xmin..zmax) host.
+ * pass 1 (counts): samples per ray -> counts int32 [R].  Host (or caller) turns counts into offsets [R]
+ * (exclusive scan) and total M; pass 2 writes ray_indices int64 [M], t_starts/t_ends [M] at those offsets. */
+int b2n_occgrid_count(const float* origins, const float* directions, const float* t_min, const float* t_max,
+                      const uint8_t* binaries, int32_t levels, int32_t res, const float* roi_host6, float step,
+                      float cone_angle, float near_plane, float far_plane, const float* jitter, int64_t n_rays,
+                      int32_t* counts, void* stream);
+int b2n_occgrid_fill(const float* origins, const float* directions, const float* t_min, const float* t_max,
+                     const uint8_t* binaries, int32_t levels, int32_t res, const float* roi_host6, float step,
+                     float cone_angle, float near_plane, float far_plane, const float* jitter, int64_t n_rays,
+                     const int64_t* offsets, int64_t* ray_indices, float* t_starts, float* t_ends, void* stream);
+
+/* ---- optimiser step either side of the path: torch.optim.Adam semantics ---------------
+ * p,g,m,v flat fp32 [n]; step is the 1-based step count; grads are multiplied by grad_scale first
+ * (1/world_size after a sum-allreduce, or 1/loss_scale). */
+int b2n_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,
+                  float beta2, float eps, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200NERF_H */

@@ -159,22 +159,26 @@ int b2n_pdf_sample(const float* bins, const float* weights, const float* u_base,
                    float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out, void* stream);
 
 /* ---- a21-a23: transmittance weights and compositing ---------------------------------------------------
- * RaySamples.get_weights (cameras/rays.py:129-152): ebins [R,S+1] euclidean edges, density [R,S] -> w [R,S]. */
-int b2n_weights_fwd(const float* ebins, const float* density, int64_t n_rays, int32_t n_samples, float* weights,
-                    void* stream);
-int b2n_weights_bwd(const float* ebins, const float* density, const float* dweights, int64_t n_rays,
-                    int32_t n_samples, float* ddensity, void* stream);
+ * Sample intervals are given as starts/ends [R,S] with row stride `bin_stride`: for an [R,S+1] edge array
+ * pass starts=edges, ends=edges+1, bin_stride=S+1 (what the reference's samplers produce).
+ * RaySamples.get_weights (cameras/rays.py:129-152): density [R,S] -> w [R,S]. */
+int b2n_weights_fwd(const float* starts, const float* ends, int64_t bin_stride, const float* density, int64_t n_rays,
+                    int32_t n_samples, float* weights, void* stream);
+int b2n_weights_bwd(const float* starts, const float* ends, int64_t bin_stride, const float* density,
+                    const float* dweights, int64_t n_rays, int32_t n_samples, float* ddensity, void* stream);
 /* RGBRenderer + AccumulationRenderer + DepthRenderer(expected|median) (renderers.py:71-119,292-385).
- * rgb [R,S,3]; outputs rgb_out [R,3], acc [R], depth_exp [R] (unclipped numerator/denominator form; the
- * global min/max clip of renderers.py:381 is applied by the host with [lo,hi]), depth_med [R], med_idx int64 [R].
+ * rgb [R,S,3]; outputs rgb_out [R,3], acc [R], depth_exp [R] (sum(w t)/(sum(w)+1e-10); the global min/max clip of
+ * renderers.py:381 is applied by the host), depth_med [R], med_idx int64 [R].
  * Any output pointer may be NULL.  eval_mode: nan_to_num(rgb) before, clamp01 after (renderers.py:225-231). */
-int b2n_composite_fwd(const float* rgb, const float* weights, const float* ebins, int64_t n_rays, int32_t n_samples,
-                      int32_t bg_mode, const float* bg_host3, int32_t eval_mode, float* rgb_out, float* acc,
-                      float* depth_exp, float* depth_med, int64_t* med_idx, void* stream);
+int b2n_composite_fwd(const float* rgb, const float* weights, const float* starts, const float* ends,
+                      int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t bg_mode, const float* bg_host3,
+                      int32_t eval_mode, float* rgb_out, float* acc, float* depth_exp, float* depth_med,
+                      int64_t* med_idx, void* stream);
 /* grads wrt rgb samples and weights given d_rgb_out [R,3], d_acc [R] (NULL=0), d_depth_exp [R] (NULL=0). */
-int b2n_composite_bwd(const float* rgb, const float* weights, const float* ebins, const float* d_rgb_out,
-                      const float* d_acc, const float* d_depth_exp, int64_t n_rays, int32_t n_samples, int32_t bg_mode,
-                      const float* bg_host3, float* d_rgb, float* d_weights, void* stream);
+int b2n_composite_bwd(const float* rgb, const float* weights, const float* starts, const float* ends,
+                      int64_t bin_stride, const float* d_rgb_out, const float* d_acc, const float* d_depth_exp,
+                      int64_t n_rays, int32_t n_samples, int32_t bg_mode, const float* bg_host3, float* d_rgb,
+                      float* d_weights, void* stream);
 
 /* ---- a24: proposal losses (model_components/losses.py:53-155) -------------------------------------------
  * interlevel term of ONE proposal level: c [R,Sc+1], w [R,Sc] (final level, constants), cp [R,Sp+1], wp [R,Sp].

@@ -6,7 +6,8 @@
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr_c,
-                                                   float b1, float b2, float inv_sqrt_bc2, float eps, float gscale) {
+                                                   float b1, float b2, float omb1, float omb2, float inv_sqrt_bc2, float eps,
+                                                   float gscale) {
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -17,8 +18,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float gk = ga[k] * gscale;
-      ma[k] = b1 * ma[k] + (1.f - b1) * gk;
-      va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+      ma[k] = b1 * ma[k] + omb1 * gk;
+      va[k] = b2 * va[k] + omb2 * gk * gk;
       pa[k] -= lr_c * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
     }
     reinterpret_cast<float4*>(p)[i] = pp;
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gk = g[i] * gscale;
-    const float mk = b1 * m[i] + (1.f - b1) * gk, vk = b2 * v[i] + (1.f - b2) * gk * gk;
+    const float mk = b1 * m[i] + omb1 * gk, vk = b2 * v[i] + omb2 * gk * gk;
     m[i] = mk, v[i] = vk;
     p[i] -= lr_c * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
   }
@@ -35,13 +36,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 extern "C" int b2n_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,
                              float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(p && g && m && v, "null pointer");
   B2N_REQUIRE(step >= 1, "step is 1-based");
   B2N_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
   if (n == 0) return B2N_OK;
   const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
   const int grid = (int)min(div_up(n / 4 + 1, 256), (int64_t)b2n_sm_count() * 8);
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2,
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, (float)(1.0 - (double)beta1),
+                                                      (float)(1.0 - (double)beta2),
                                                       (float)(1.0 / sqrt(bc2)), eps, grad_scale);
   B2N_LAUNCH_CHECK();
 }

@@ -58,6 +58,7 @@ __global__ void sh_fwd_kernel(const float* __restrict__ dirs, int64_t n, int rem
 }
 
 extern "C" int b2n_sh_fwd(const float* dirs, int64_t n, int32_t levels, int32_t remap01, float* out, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(dirs && out, "null pointer");
   B2N_REQUIRE(levels >= 1 && levels <= 5, "levels must be in 1..5");
   if (n == 0) return B2N_OK;
@@ -134,6 +135,7 @@ static int fill_freq(FreqParams& fp, int d, const float* freqs_host, int n_freq,
 
 extern "C" int b2n_freq_fwd(const float* x, int64_t n, int32_t d, const float* freqs_host, int32_t n_freq,
                             int32_t include_input, float* out, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(x && out, "null pointer");
   FreqParams fp;
   B2N_REQUIRE(fill_freq(fp, d, freqs_host, n_freq, include_input) == 0, "bad frequency table");
@@ -146,6 +148,7 @@ extern "C" int b2n_freq_fwd(const float* x, int64_t n, int32_t d, const float* f
 
 extern "C" int b2n_freq_bwd(const float* x, const float* dout, int64_t n, int32_t d, const float* freqs_host,
                             int32_t n_freq, int32_t include_input, float* dx, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(x && dout && dx, "null pointer");
   FreqParams fp;
   B2N_REQUIRE(fill_freq(fp, d, freqs_host, n_freq, include_input) == 0, "bad frequency table");
@@ -206,6 +209,7 @@ extern "C" int b2n_positions_fwd(const float* origins, const float* directions, 
                                  const float* ends, int64_t bin_stride, int64_t n_rays, int32_t n_samples,
                                  int32_t contraction, const float* aabb_host6, float* x_out, uint8_t* sel_out,
                                  void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(origins && x_out, "null pointer");
   B2N_REQUIRE(directions == nullptr || (starts && ends), "ray form needs starts/ends");
   B2N_REQUIRE(contraction || aabb_host6, "aabb required without contraction");
@@ -246,6 +250,7 @@ __global__ void density_act_bwd_kernel(const float* __restrict__ h, int64_t h_st
 
 extern "C" int b2n_density_act_fwd(const float* h, int64_t h_stride, const uint8_t* sel, int64_t n, float avg_init,
                                    float* density, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(h && density, "null pointer");
   if (n == 0) return B2N_OK;
   density_act_fwd_kernel<<<(unsigned)div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(h, h_stride, sel, n, avg_init, density);
@@ -254,6 +259,7 @@ extern "C" int b2n_density_act_fwd(const float* h, int64_t h_stride, const uint8
 
 extern "C" int b2n_density_act_bwd(const float* h, int64_t h_stride, const uint8_t* sel, const float* g, int64_t n,
                                    float avg_init, float* dh, int64_t dh_stride, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(h && g && dh, "null pointer");
   if (n == 0) return B2N_OK;
   density_act_bwd_kernel<<<(unsigned)div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(h, h_stride, sel, g, n, avg_init, dh, dh_stride);

@@ -283,6 +283,7 @@ static void launch_bwd(const GridParams& gp, const float* x, const float* table,
 
 extern "C" int b2n_hashgrid_fwd(const B2nGrid* grid_host, const float* x, const float* table, int64_t n, float* y,
                                 int64_t* idx_out, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(grid_host && x && table && y, "null pointer");
   B2N_REQUIRE(n >= 0, "negative n");
   GridParams gp;
@@ -301,6 +302,7 @@ extern "C" int b2n_hashgrid_fwd(const B2nGrid* grid_host, const float* x, const 
 
 extern "C" int b2n_hashgrid_bwd(const B2nGrid* grid_host, const float* x, const float* table, const float* dy,
                                 int64_t n, float* dtable, float* dx, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(grid_host && x && dy && dtable, "null pointer");
   B2N_REQUIRE(dx == nullptr || table != nullptr, "dx needs the table");
   GridParams gp;

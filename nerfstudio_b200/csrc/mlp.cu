@@ -396,6 +396,7 @@ static int smem_limit() {
 }
 
 extern "C" int b2n_mlp_fwd(const B2nMlp* mlp_host, const float* x, int64_t n, float* y, float* hidden, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(mlp_host && x && y, "null pointer");
   MlpParams mp;
   B2N_REQUIRE(build_params(mlp_host, nullptr, mp, true) == 0, "bad mlp description");
@@ -412,6 +413,7 @@ extern "C" int b2n_mlp_fwd(const B2nMlp* mlp_host, const float* x, int64_t n, fl
 
 extern "C" int b2n_mlp_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, const float* y,
                            const float* hidden, const float* dy, int64_t n, float* dx, void* stream) {
+  if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(mlp_host && grad_host && x && y && dy, "null pointer");
   B2N_REQUIRE(mlp_host->n_layers == 1 || hidden != nullptr, "hidden activations required");
   MlpParams mp;

@@ -28,6 +28,7 @@ __global__ void pack_info_kernel(const int64_t* __restrict__ ray_indices, int64_
 }
 
 extern "C" int b2n_pack_info(const int64_t* ray_indices, int64_t m, int64_t n_rays, int64_t* packed_info, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(packed_info && (ray_indices || m == 0), "null pointer");
   if (n_rays == 0) return B2N_OK;
   pack_info_kernel<<<(unsigned)div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(ray_indices, m, n_rays, packed_info);
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(PW * 32) packed_weights_bwd_kernel(const float
 extern "C" int b2n_packed_weights_fwd(const float* t_starts, const float* t_ends, const float* sigmas,
                                       const int64_t* packed_info, int64_t n_rays, float* weights, float* trans,
                                       float* alphas, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(t_starts && t_ends && sigmas && packed_info && weights, "null pointer");
   if (n_rays == 0) return B2N_OK;
   packed_weights_fwd_kernel<<<(unsigned)div_up(n_rays, PW), PW * 32, 0, (cudaStream_t)stream>>>(t_starts, t_ends, sigmas, packed_info, n_rays, weights, trans, alphas);
@@ -104,6 +106,7 @@ extern "C" int b2n_packed_weights_fwd(const float* t_starts, const float* t_ends
 extern "C" int b2n_packed_weights_bwd(const float* t_starts, const float* t_ends, const float* sigmas,
                                       const int64_t* packed_info, const float* dweights, int64_t n_rays, float* dsigmas,
                                       void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(t_starts && t_ends && sigmas && packed_info && dweights && dsigmas, "null pointer");
   if (n_rays == 0) return B2N_OK;
   packed_weights_bwd_kernel<<<(unsigned)div_up(n_rays, PW), PW * 32, 0, (cudaStream_t)stream>>>(t_starts, t_ends, sigmas, packed_info, dweights, n_rays, dsigmas);
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(PW * 32) packed_accum_bwd_kernel(const float* 
 
 extern "C" int b2n_packed_accumulate_fwd(const float* weights, const float* values, int32_t d, const int64_t* packed_info,
                                          int64_t n_rays, float* out, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(weights && packed_info && out && d >= 1, "bad arguments");
   if (n_rays == 0) return B2N_OK;
   packed_accum_fwd_kernel<<<(unsigned)div_up(n_rays, PW), PW * 32, 0, (cudaStream_t)stream>>>(weights, values, d, packed_info, n_rays, out);
@@ -158,6 +162,7 @@ extern "C" int b2n_packed_accumulate_fwd(const float* weights, const float* valu
 
 extern "C" int b2n_packed_accumulate_bwd(const float* weights, const float* values, int32_t d, const int64_t* packed_info,
                                          const float* dout, int64_t n_rays, float* dweights, float* dvalues, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(weights && packed_info && dout && d >= 1, "bad arguments");
   B2N_REQUIRE(!(dvalues && !values), "dvalues without values");
   if (n_rays == 0) return B2N_OK;
@@ -253,6 +258,7 @@ extern "C" int b2n_occgrid_count(const float* origins, const float* directions, 
                                  const uint8_t* binaries, int32_t levels, int32_t res, const float* roi_host6, float step,
                                  float cone_angle, float near_plane, float far_plane, const float* jitter, int64_t n_rays,
                                  int32_t* counts, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(origins && directions && binaries && counts, "null pointer");
   March mp;
   B2N_REQUIRE(fill_march(mp, levels, res, roi_host6, step, cone_angle, near_plane, far_plane) == 0, "bad grid description");
@@ -266,6 +272,7 @@ extern "C" int b2n_occgrid_fill(const float* origins, const float* directions, c
                                 const uint8_t* binaries, int32_t levels, int32_t res, const float* roi_host6, float step,
                                 float cone_angle, float near_plane, float far_plane, const float* jitter, int64_t n_rays,
                                 const int64_t* offsets, int64_t* ray_indices, float* t_starts, float* t_ends, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(origins && directions && binaries && offsets && ray_indices && t_starts && t_ends, "null pointer");
   March mp;
   B2N_REQUIRE(fill_march(mp, levels, res, roi_host6, step, cone_angle, near_plane, far_plane) == 0, "bad grid description");

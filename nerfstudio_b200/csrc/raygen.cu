@@ -84,6 +84,7 @@ __global__ void raygen_kernel(const float* __restrict__ c2w, const float* __rest
 extern "C" int b2n_raygen(const float* c2w, const float* intr, const float* dist, const int64_t* ray_indices,
                           int64_t n_rays, float* origins, float* directions, float* pixel_area, float* directions_norm,
                           int64_t* camera_indices, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(c2w && intr && ray_indices && origins && directions, "null pointer");
   if (n_rays == 0) return B2N_OK;
   raygen_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
@@ -114,6 +115,7 @@ __global__ void aabb_collide_kernel(const __grid_constant__ Box box, const float
 
 extern "C" int b2n_aabb_collide(const float* origins, const float* directions, const float* aabb_host6, float near_plane,
                                 int64_t n_rays, float* nears, float* fars, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(origins && directions && aabb_host6 && nears && fars, "null pointer");
   if (n_rays == 0) return B2N_OK;
   Box box;

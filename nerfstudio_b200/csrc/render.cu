@@ -11,20 +11,22 @@
 // ------------------------------------------------------------------------------------------------
 // get_weights
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RW * 32) weights_fwd_kernel(const float* __restrict__ ebins,
+__global__ void __launch_bounds__(RW * 32) weights_fwd_kernel(const float* __restrict__ starts,
+                                                              const float* __restrict__ ends, int64_t bs,
                                                               const float* __restrict__ density, int64_t n_rays, int S,
                                                               float* __restrict__ weights) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * RW + warp;
   if (r >= n_rays) return;
-  const float* e = ebins + r * (S + 1);
+  const float* st = starts + r * bs;
+  const float* en = ends + r * bs;
   const float* d = density + r * S;
   const int chunk = (S + 31) / 32, i0 = lane * chunk, i1 = min(S, i0 + chunk);
   double local = 0.0;
-  for (int i = i0; i < i1; ++i) local += (double)mul_rn(sub_rn(__ldg(e + i + 1), __ldg(e + i)), __ldg(d + i));
+  for (int i = i0; i < i1; ++i) local += (double)mul_rn(sub_rn(__ldg(en + i), __ldg(st + i)), __ldg(d + i));
   double run = warp_scan_incl_d(local, lane) - local;  // exclusive prefix of this chunk
   for (int i = i0; i < i1; ++i) {
-    const float dd = mul_rn(sub_rn(__ldg(e + i + 1), __ldg(e + i)), __ldg(d + i));
+    const float dd = mul_rn(sub_rn(__ldg(en + i), __ldg(st + i)), __ldg(d + i));
     const float alpha = sub_rn(1.f, expf(-dd));
     const float T = expf(-(float)run);
     weights[r * S + i] = nan_to_num(mul_rn(alpha, T));
@@ -33,24 +35,26 @@ __global__ void __launch_bounds__(RW * 32) weights_fwd_kernel(const float* __res
 }
 
 // dL/d(dd_k) = g_k T_k (1 - a_k) - sum_{i>k} g_i a_i T_i ;  dsigma_k = delta_k * that.
-__global__ void __launch_bounds__(RW * 32) weights_bwd_kernel(const float* __restrict__ ebins,
+__global__ void __launch_bounds__(RW * 32) weights_bwd_kernel(const float* __restrict__ starts,
+                                                              const float* __restrict__ ends, int64_t bs,
                                                               const float* __restrict__ density,
                                                               const float* __restrict__ dweights, int64_t n_rays, int S,
                                                               float* __restrict__ ddensity) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * RW + warp;
   if (r >= n_rays) return;
-  const float* e = ebins + r * (S + 1);
+  const float* st = starts + r * bs;
+  const float* en = ends + r * bs;
   const float* d = density + r * S;
   const float* g = dweights + r * S;
   const int chunk = (S + 31) / 32, i0 = lane * chunk, i1 = min(S, i0 + chunk);
   double local = 0.0;
-  for (int i = i0; i < i1; ++i) local += (double)mul_rn(sub_rn(__ldg(e + i + 1), __ldg(e + i)), __ldg(d + i));
+  for (int i = i0; i < i1; ++i) local += (double)mul_rn(sub_rn(__ldg(en + i), __ldg(st + i)), __ldg(d + i));
   const double excl = warp_scan_incl_d(local, lane) - local;
   // pass A: per-chunk sum of g_i * w_i (finite only), to build the suffix sums
   double run = excl, gw_local = 0.0;
   for (int i = i0; i < i1; ++i) {
-    const float dd = mul_rn(sub_rn(__ldg(e + i + 1), __ldg(e + i)), __ldg(d + i));
+    const float dd = mul_rn(sub_rn(__ldg(en + i), __ldg(st + i)), __ldg(d + i));
     const float w = mul_rn(sub_rn(1.f, expf(-dd)), expf(-(float)run));
     if (isfinite(w)) gw_local += (double)(__ldg(g + i) * w);
     run += (double)dd;
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(RW * 32) weights_bwd_kernel(const float* __res
   // pass B: walk the chunk backwards
   run = excl + local;
   for (int i = i1 - 1; i >= i0; --i) {
-    const float delta = sub_rn(__ldg(e + i + 1), __ldg(e + i));
+    const float delta = sub_rn(__ldg(en + i), __ldg(st + i));
     const float dd = mul_rn(delta, __ldg(d + i));
     run -= (double)dd;  // exclusive prefix at i (up to fp64 rounding)
     const float ea = expf(-dd), T = expf(-(float)run);
@@ -73,21 +77,23 @@ __global__ void __launch_bounds__(RW * 32) weights_bwd_kernel(const float* __res
   }
 }
 
-extern "C" int b2n_weights_fwd(const float* ebins, const float* density, int64_t n_rays, int32_t n_samples,
-                               float* weights, void* stream) {
-  B2N_REQUIRE(ebins && density && weights, "null pointer");
+extern "C" int b2n_weights_fwd(const float* starts, const float* ends, int64_t bin_stride, const float* density,
+                               int64_t n_rays, int32_t n_samples, float* weights, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
+  B2N_REQUIRE(starts && ends && density && weights, "null pointer");
   B2N_REQUIRE(n_samples >= 1, "n_samples");
   if (n_rays == 0) return B2N_OK;
-  weights_fwd_kernel<<<(unsigned)div_up(n_rays, RW), RW * 32, 0, (cudaStream_t)stream>>>(ebins, density, n_rays, n_samples, weights);
+  weights_fwd_kernel<<<(unsigned)div_up(n_rays, RW), RW * 32, 0, (cudaStream_t)stream>>>(starts, ends, bin_stride, density, n_rays, n_samples, weights);
   B2N_LAUNCH_CHECK();
 }
 
-extern "C" int b2n_weights_bwd(const float* ebins, const float* density, const float* dweights, int64_t n_rays,
-                               int32_t n_samples, float* ddensity, void* stream) {
-  B2N_REQUIRE(ebins && density && dweights && ddensity, "null pointer");
+extern "C" int b2n_weights_bwd(const float* starts, const float* ends, int64_t bin_stride, const float* density,
+                               const float* dweights, int64_t n_rays, int32_t n_samples, float* ddensity, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
+  B2N_REQUIRE(starts && ends && density && dweights && ddensity, "null pointer");
   B2N_REQUIRE(n_samples >= 1, "n_samples");
   if (n_rays == 0) return B2N_OK;
-  weights_bwd_kernel<<<(unsigned)div_up(n_rays, RW), RW * 32, 0, (cudaStream_t)stream>>>(ebins, density, dweights, n_rays, n_samples, ddensity);
+  weights_bwd_kernel<<<(unsigned)div_up(n_rays, RW), RW * 32, 0, (cudaStream_t)stream>>>(starts, ends, bin_stride, density, dweights, n_rays, n_samples, ddensity);
   B2N_LAUNCH_CHECK();
 }
 
@@ -102,7 +108,9 @@ struct Bg {
 __global__ void __launch_bounds__(RW * 32) composite_fwd_kernel(const __grid_constant__ Bg bg,
                                                                 const float* __restrict__ rgb,
                                                                 const float* __restrict__ weights,
-                                                                const float* __restrict__ ebins, int64_t n_rays, int S,
+                                                                const float* __restrict__ starts,
+                                                                const float* __restrict__ ends, int64_t bs,
+                                                                int64_t n_rays, int S,
                                                                 float* __restrict__ rgb_out, float* __restrict__ acc_out,
                                                                 float* __restrict__ depth_exp,
                                                                 float* __restrict__ depth_med,
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(RW * 32) composite_fwd_kernel(const __grid_con
       if (bg.eval_mode) a = nan_to_num(a), b = nan_to_num(b), c = nan_to_num(c);
       cr = fmaf(wi, a, cr), cg = fmaf(wi, b, cg), cb = fmaf(wi, c, cb);
     }
-    if (ebins) wt = fmaf(wi, div_rn(add_rn(__ldg(ebins + r * (S + 1) + i), __ldg(ebins + r * (S + 1) + i + 1)), 2.f), wt);
+    if (starts) wt = fmaf(wi, div_rn(add_rn(__ldg(starts + r * bs + i), __ldg(ends + r * bs + i)), 2.f), wt);
   }
   // median: first index whose inclusive cumulative weight >= 0.5 (searchsorted left), clamped to S-1
   if (depth_med || med_idx) {
@@ -138,8 +146,8 @@ __global__ void __launch_bounds__(RW * 32) composite_fwd_kernel(const __grid_con
     const int idx = min(found, S - 1);
     if (lane == 0) {
       if (med_idx) med_idx[r] = idx;
-      if (depth_med && ebins)
-        depth_med[r] = div_rn(add_rn(__ldg(ebins + r * (S + 1) + idx), __ldg(ebins + r * (S + 1) + idx + 1)), 2.f);
+      if (depth_med && starts)
+        depth_med[r] = div_rn(add_rn(__ldg(starts + r * bs + idx), __ldg(ends + r * bs + idx)), 2.f);
     }
   }
   cr = warp_sum(cr), cg = warp_sum(cg), cb = warp_sum(cb), acc = warp_sum(acc), wt = warp_sum(wt);
@@ -167,7 +175,8 @@ __global__ void __launch_bounds__(RW * 32) composite_fwd_kernel(const __grid_con
 __global__ void __launch_bounds__(RW * 32) composite_bwd_kernel(const __grid_constant__ Bg bg,
                                                                 const float* __restrict__ rgb,
                                                                 const float* __restrict__ weights,
-                                                                const float* __restrict__ ebins,
+                                                                const float* __restrict__ starts,
+                                                                const float* __restrict__ ends, int64_t bs,
                                                                 const float* __restrict__ d_rgb_out,
                                                                 const float* __restrict__ d_acc,
                                                                 const float* __restrict__ d_depth, int64_t n_rays, int S,
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(RW * 32) composite_bwd_kernel(const __grid_con
   for (int i = lane; i < S; i += 32) {
     const float wi = __ldg(w + i);
     acc += wi;
-    if (d_depth) wt = fmaf(wi, div_rn(add_rn(__ldg(ebins + r * (S + 1) + i), __ldg(ebins + r * (S + 1) + i + 1)), 2.f), wt);
+    if (d_depth) wt = fmaf(wi, div_rn(add_rn(__ldg(starts + r * bs + i), __ldg(ends + r * bs + i)), 2.f), wt);
   }
   acc = warp_sum(acc), wt = warp_sum(wt);
   const float g0 = d_rgb_out ? __ldg(d_rgb_out + 3 * r) : 0.f, g1 = d_rgb_out ? __ldg(d_rgb_out + 3 * r + 1) : 0.f,
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(RW * 32) composite_bwd_kernel(const __grid_con
     if (d_w) {
       float gw = a * g0 + b * g1 + c * g2 - bgdot + ga;
       if (d_depth) {
-        const float t = div_rn(add_rn(__ldg(ebins + r * (S + 1) + i), __ldg(ebins + r * (S + 1) + i + 1)), 2.f);
+        const float t = div_rn(add_rn(__ldg(starts + r * bs + i), __ldg(ends + r * bs + i)), 2.f);
         gw += gd * (t - D) / denom;
       }
       d_w[r * S + i] = gw;
@@ -215,34 +224,38 @@ static void fill_bg(Bg& bg, int mode, const float* c, int eval_mode) {
   for (int i = 0; i < 3; ++i) bg.c[i] = (mode == B2N_BG_CONSTANT && c) ? c[i] : 0.f;
 }
 
-extern "C" int b2n_composite_fwd(const float* rgb, const float* weights, const float* ebins, int64_t n_rays,
-                                 int32_t n_samples, int32_t bg_mode, const float* bg_host3, int32_t eval_mode,
+extern "C" int b2n_composite_fwd(const float* rgb, const float* weights, const float* starts, const float* ends,
+                                 int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t bg_mode, const float* bg_host3, int32_t eval_mode,
                                  float* rgb_out, float* acc, float* depth_exp, float* depth_med, int64_t* med_idx,
                                  void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(weights, "null weights");
   B2N_REQUIRE(!(rgb_out && !rgb), "rgb_out needs rgb");
-  B2N_REQUIRE(!((depth_exp || depth_med) && !ebins), "depth needs ebins");
+  B2N_REQUIRE(!((depth_exp || depth_med) && !(starts && ends)), "depth needs starts/ends");
+  B2N_REQUIRE((starts == nullptr) == (ends == nullptr), "starts/ends must come together");
   B2N_REQUIRE(n_samples >= 1, "n_samples");
   B2N_REQUIRE(bg_mode != B2N_BG_CONSTANT || bg_host3, "constant background needs a colour");
   if (n_rays == 0) return B2N_OK;
   Bg bg;
   fill_bg(bg, bg_mode, bg_host3, eval_mode);
   composite_fwd_kernel<<<(unsigned)div_up(n_rays, RW), RW * 32, 0, (cudaStream_t)stream>>>(
-      bg, rgb, weights, ebins, n_rays, n_samples, rgb_out, acc, depth_exp, depth_med, med_idx);
+      bg, rgb, weights, starts, ends, bin_stride, n_rays, n_samples, rgb_out, acc, depth_exp, depth_med, med_idx);
   B2N_LAUNCH_CHECK();
 }
 
-extern "C" int b2n_composite_bwd(const float* rgb, const float* weights, const float* ebins, const float* d_rgb_out,
+extern "C" int b2n_composite_bwd(const float* rgb, const float* weights, const float* starts, const float* ends,
+                                 int64_t bin_stride, const float* d_rgb_out,
                                  const float* d_acc, const float* d_depth_exp, int64_t n_rays, int32_t n_samples,
                                  int32_t bg_mode, const float* bg_host3, float* d_rgb, float* d_weights, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(rgb && weights, "null pointer");
-  B2N_REQUIRE(!(d_depth_exp && !ebins), "depth grad needs ebins");
+  B2N_REQUIRE(!(d_depth_exp && !(starts && ends)), "depth grad needs starts/ends");
   B2N_REQUIRE(bg_mode != B2N_BG_CONSTANT || bg_host3, "constant background needs a colour");
   if (n_rays == 0) return B2N_OK;
   Bg bg;
   fill_bg(bg, bg_mode, bg_host3, 0);
   composite_bwd_kernel<<<(unsigned)div_up(n_rays, RW), RW * 32, 0, (cudaStream_t)stream>>>(
-      bg, rgb, weights, ebins, d_rgb_out, d_acc, d_depth_exp, n_rays, n_samples, d_rgb, d_weights);
+      bg, rgb, weights, starts, ends, bin_stride, d_rgb_out, d_acc, d_depth_exp, n_rays, n_samples, d_rgb, d_weights);
   B2N_LAUNCH_CHECK();
 }
 
@@ -318,6 +331,7 @@ __global__ void __launch_bounds__(RW * 32) interlevel_kernel(const float* __rest
 extern "C" int b2n_interlevel_fwd_bwd(const float* c, const float* w, const float* cp, const float* wp, int64_t n_rays,
                                       int32_t sc, int32_t sp, float gscale, float* loss_rows, float* d_wp,
                                       void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(c && w && cp && wp, "null pointer");
   B2N_REQUIRE(sc >= 1 && sp >= 1 && sp <= 4096, "sample counts out of range");
   if (n_rays == 0) return B2N_OK;
@@ -357,6 +371,7 @@ __global__ void __launch_bounds__(RW * 32) distortion_kernel(const float* __rest
 
 extern "C" int b2n_distortion_fwd_bwd(const float* t, const float* w, int64_t n_rays, int32_t s, float gscale,
                                       float* loss_rows, float* d_w, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(t && w, "null pointer");
   B2N_REQUIRE(s >= 1 && s <= 4096, "sample count out of range");
   if (n_rays == 0) return B2N_OK;

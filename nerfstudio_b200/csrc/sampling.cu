@@ -54,6 +54,7 @@ __global__ void spaced_sample_kernel(const float* __restrict__ nears, const floa
 extern "C" int b2n_spaced_sample(const float* nears, const float* fars, const float* lin, const float* jitter,
                                  int32_t jitter_per_bin, int64_t n_rays, int32_t n_samples, int32_t spacing,
                                  float* sbins, float* ebins, void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(nears && fars && lin && sbins && ebins, "null pointer");
   B2N_REQUIRE(n_samples >= 1, "n_samples");
   const int64_t total = n_rays * (n_samples + 1);
@@ -146,6 +147,7 @@ extern "C" int b2n_pdf_sample(const float* bins, const float* weights, const flo
                               int32_t n_in, int32_t n_out, float anneal, float histogram_padding, float eps,
                               int32_t spacing, float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out,
                               void* stream) {
+  if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(bins && weights && u_base && nears && fars && new_sbins, "null pointer");
   B2N_REQUIRE(n_in >= 1 && n_in <= 4096 && n_out >= 1, "sample counts out of range");
   if (n_rays == 0) return B2N_OK;

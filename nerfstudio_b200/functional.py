@@ -1,0 +1,678 @@
+"""Tensor-level API over the C-ABI: thin wrappers + torch.autograd.Functions.
+
+Every function here launches hand-written sm_100a kernels from libb200nerf.so on the current CUDA stream.
+PyTorch is used for device memory, streams and autograd bookkeeping only.  Autocast-safe: the Functions cast
+their floating inputs to fp32 (`custom_fwd(cast_inputs=torch.float32)`), as the reference's `trunc_exp`
+does (nerfstudio/field_components/activations.py:28-41).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+from torch.amp import custom_bwd, custom_fwd
+
+from . import lib
+from .lib import B2nGrid, B2nMlp, B2nMlpGrad, call, host_floats, ptr, stream
+
+_fwd = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_bwd = custom_bwd(device_type="cuda")
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------
+# hash grid
+# ----------------------------------------------------------------------------------------
+class GridSpec:
+    """Host-side description of a multiresolution grid (wraps the C struct; hashable cache of level metadata)."""
+
+    def __init__(self, scales: Sequence[float], log2_hashmap_size: int, n_features: int, mode: str = "torch",
+                 resolutions: Optional[Sequence[int]] = None, offsets: Optional[Sequence[int]] = None,
+                 sizes: Optional[Sequence[int]] = None, hashed: Optional[Sequence[bool]] = None):
+        L = len(scales)
+        if not 1 <= L <= lib.MAX_LEVELS:
+            raise ValueError(f"num_levels must be in 1..{lib.MAX_LEVELS}")
+        if n_features not in (1, 2, 4, 8):
+            raise ValueError("features_per_level must be 1, 2, 4 or 8")
+        T = 1 << log2_hashmap_size
+        g = B2nGrid()
+        g.n_levels, g.n_features, g.log2_hashmap_size = L, n_features, log2_hashmap_size
+        g.mode = lib.GRID_TORCH if mode == "torch" else lib.GRID_TCNN
+        for l in range(L):
+            g.scale[l] = float(scales[l])
+            g.resolution[l] = int(resolutions[l]) if resolutions is not None else 0
+            g.offset[l] = int(offsets[l]) if offsets is not None else l * T
+            g.size[l] = int(sizes[l]) if sizes is not None else T
+            g.hashed[l] = int(hashed[l]) if hashed is not None else 1
+        self.c = g
+        self.n_levels, self.n_features, self.mode = L, n_features, mode
+        self.out_dim = L * n_features
+        self.n_rows = max(int(g.offset[l]) + int(g.size[l]) for l in range(L))
+
+    @staticmethod
+    def tcnn(num_levels: int, base_res: int, per_level_scale: float, log2_hashmap_size: int, n_features: int):
+        """tiny-cuda-nn HashGrid level table: dense coarse levels, hashed fine ones."""
+        scales, res, offs, sizes, hashed, off = [], [], [], [], [], 0
+        for l in range(num_levels):
+            s = math.exp2(l * math.log2(per_level_scale)) * base_res - 1.0
+            r = int(math.ceil(s)) + 1
+            n = (r ** 3 + 7) // 8 * 8
+            size = min(n, 1 << log2_hashmap_size)
+            scales.append(s), res.append(r), offs.append(off), sizes.append(size), hashed.append(r ** 3 > size)
+            off += size
+        return GridSpec(scales, log2_hashmap_size, n_features, "tcnn", res, offs, sizes, hashed)
+
+
+def hashgrid_forward(x: Tensor, table: Tensor, grid: GridSpec, want_indices: bool = False):
+    """x [N,3] fp32 in [0,1], table [rows,F] -> y [N, L*F] (and int64 [N,L,8] corner rows if asked)."""
+    x, table = _c(x), _c(table)
+    n = x.shape[0]
+    y = torch.empty(n, grid.out_dim, device=x.device, dtype=torch.float32)
+    idx = torch.empty(n, grid.n_levels, 8, device=x.device, dtype=torch.int64) if want_indices else None
+    call("b2n_hashgrid_fwd", C.byref(grid.c), ptr(x), ptr(table), n, ptr(y), ptr(idx, torch.int64), stream())
+    return (y, idx) if want_indices else y
+
+
+def hashgrid_backward(x: Tensor, table: Tensor, dy: Tensor, grid: GridSpec, dtable: Optional[Tensor] = None,
+                      want_dx: bool = False):
+    x, table, dy = _c(x), _c(table), _c(dy)
+    if dtable is None:
+        dtable = torch.zeros_like(table)
+    dx = torch.empty_like(x) if want_dx else None
+    call("b2n_hashgrid_bwd", C.byref(grid.c), ptr(x), ptr(table), ptr(dy), x.shape[0], ptr(dtable), ptr(dx), stream())
+    return dtable, dx
+
+
+class _HashGridFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, table, grid):
+        ctx.grid = grid
+        ctx.save_for_backward(x, table)
+        return hashgrid_forward(x, table, grid)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dy):
+        x, table = ctx.saved_tensors
+        dtable, dx = hashgrid_backward(x, table, dy.float(), ctx.grid, want_dx=ctx.needs_input_grad[0])
+        return dx, (dtable if ctx.needs_input_grad[1] else None), None
+
+
+def hash_encode(x: Tensor, table: Tensor, grid: GridSpec) -> Tensor:
+    return _HashGridFn.apply(x, table, grid)
+
+
+# ----------------------------------------------------------------------------------------
+# tiny MLP
+# ----------------------------------------------------------------------------------------
+class MlpSpec:
+    def __init__(self, in_dim: int, out_dims: Sequence[int], skip: Sequence[int] = (), hidden_act: str = "relu",
+                 out_act: str = "none", bias: bool = True):
+        if len(out_dims) > lib.MAX_MLP_LAYERS:
+            raise ValueError(f"at most {lib.MAX_MLP_LAYERS} layers")
+        self.in_dim, self.out_dims, self.skip = int(in_dim), [int(o) for o in out_dims], set(int(s) for s in skip)
+        self.hidden_act, self.out_act, self.bias = hidden_act, out_act, bias
+        self.hidden_width = sum(self.out_dims[:-1])
+
+    def layer_in(self, i: int) -> int:
+        prev = self.in_dim if i == 0 else self.out_dims[i - 1]
+        return prev + self.in_dim if i in self.skip else prev
+
+    def fits_fused_kernel(self) -> bool:
+        """Shared-memory budget of the backward kernel (the larger one) — mirrors mlp.cu:bwd_smem."""
+        r8 = lambda v: (v + 7) // 8 * 8
+        w_total, kmax, wmax = 0, r8(self.in_dim), 8
+        for i, out in enumerate(self.out_dims):
+            inn = self.layer_in(i)
+            w_total += (out * r8(inn) + 3) // 4 * 4 + r8(out)
+            kmax, wmax = max(kmax, r8(inn)), max(wmax, r8(out))
+        smem = 4 * (2 * w_total + (wmax + 2 * kmax + (self.in_dim if self.skip else 0)) * 129)
+        return smem <= 227 * 1024
+
+    def struct(self, weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]]) -> B2nMlp:
+        m = B2nMlp()
+        m.n_layers, m.in_dim = len(self.out_dims), self.in_dim
+        m.hidden_act, m.out_act = lib.ACT[self.hidden_act], lib.ACT[self.out_act]
+        for i, out in enumerate(self.out_dims):
+            w = weights[i]
+            if tuple(w.shape) != (out, self.layer_in(i)):
+                raise ValueError(f"layer {i}: weight shape {tuple(w.shape)} != {(out, self.layer_in(i))}")
+            m.out_dims[i], m.skip[i] = out, int(i in self.skip)
+            m.w[i] = ptr(w).value
+            m.b[i] = ptr(biases[i]).value if biases[i] is not None else None
+        return m
+
+
+def mlp_forward(spec: MlpSpec, x: Tensor, weights, biases, save_hidden: bool):
+    x = _c(x)
+    n = x.shape[0]
+    y = torch.empty(n, spec.out_dims[-1], device=x.device, dtype=torch.float32)
+    hidden = torch.empty(max(spec.hidden_width, 1) * n, device=x.device, dtype=torch.float32) if save_hidden else None
+    m = spec.struct([_c(w) for w in weights], [None if b is None else _c(b) for b in biases])
+    call("b2n_mlp_fwd", C.byref(m), ptr(x), n, ptr(y), ptr(hidden), stream())
+    return y, hidden
+
+
+def mlp_backward(spec: MlpSpec, x, y, hidden, dy, weights, biases, dws, dbs, want_dx: bool):
+    m = spec.struct(weights, biases)
+    g = B2nMlpGrad()
+    for i in range(len(spec.out_dims)):
+        g.dw[i] = ptr(dws[i]).value if dws[i] is not None else None
+        g.db[i] = ptr(dbs[i]).value if dbs[i] is not None else None
+    dx = torch.empty_like(x) if want_dx else None
+    call("b2n_mlp_bwd", C.byref(m), C.byref(g), ptr(x), ptr(y), ptr(hidden), ptr(_c(dy)), x.shape[0], ptr(dx), stream())
+    return dx
+
+
+class _MlpFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, spec, x, *params):
+        L = len(spec.out_dims)
+        weights, biases = list(params[:L]), list(params[L:]) if spec.bias else [None] * L
+        weights = [_c(w) for w in weights]
+        biases = [None if b is None else _c(b) for b in biases]
+        x = _c(x)
+        need = any(ctx.needs_input_grad)
+        y, hidden = mlp_forward(spec, x, weights, biases, save_hidden=need)
+        ctx.spec = spec
+        if need:
+            ctx.save_for_backward(x, y, hidden, *weights, *[b for b in biases if b is not None])
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dy):
+        spec = ctx.spec
+        L = len(spec.out_dims)
+        x, y, hidden, *rest = ctx.saved_tensors
+        weights = rest[:L]
+        biases = list(rest[L:]) if spec.bias else [None] * L
+        dws = [torch.zeros_like(w) for w in weights]
+        dbs = [None if b is None else torch.zeros_like(b) for b in biases]
+        dx = mlp_backward(spec, x, y, hidden, dy.float(), weights, biases, dws, dbs, want_dx=ctx.needs_input_grad[1])
+        return (None, dx, *dws, *[d for d in dbs if d is not None])
+
+
+def mlp(spec: MlpSpec, x: Tensor, weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]]) -> Tensor:
+    params = list(weights) + ([b for b in biases] if spec.bias else [])
+    return _MlpFn.apply(spec, x, *params)
+
+
+# ----------------------------------------------------------------------------------------
+# encodings
+# ----------------------------------------------------------------------------------------
+def sh_encode(dirs: Tensor, levels: int, remap01: bool = False) -> Tensor:
+    """Real SH basis (no grad, as the reference's @torch.no_grad torch path)."""
+    if not 1 <= levels <= 5:
+        raise ValueError(f"Spherical harmonic encoding only supports 1 to 5 levels, requested {levels}")
+    d = _c(dirs.detach().float())
+    out = torch.empty(d.shape[0], levels * levels, device=d.device, dtype=torch.float32)
+    call("b2n_sh_fwd", ptr(d), d.shape[0], levels, int(remap01), ptr(out), stream())
+    return out
+
+
+class _FreqFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, freqs, include_input):
+        x = _c(x)
+        n, d = x.shape
+        fr = host_floats(freqs)
+        width = 2 * d * len(freqs) + (d if include_input else 0)
+        out = torch.empty(n, width, device=x.device, dtype=torch.float32)
+        call("b2n_freq_fwd", ptr(x), n, d, C.cast(fr, C.c_void_p), len(freqs), int(include_input), ptr(out), stream())
+        ctx.freqs, ctx.include_input = freqs, include_input
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        fr = host_floats(ctx.freqs)
+        dx = torch.empty_like(x)
+        call("b2n_freq_bwd", ptr(x), ptr(_c(dout.float())), x.shape[0], x.shape[1], C.cast(fr, C.c_void_p),
+             len(ctx.freqs), int(ctx.include_input), ptr(dx), stream())
+        return dx, None, None
+
+
+def freq_encode(x: Tensor, freqs: Sequence[float], include_input: bool) -> Tensor:
+    return _FreqFn.apply(x, tuple(float(f) for f in freqs), bool(include_input))
+
+
+# ----------------------------------------------------------------------------------------
+# positions / density activation
+# ----------------------------------------------------------------------------------------
+def positions_to_unit_cube(origins: Tensor, directions: Optional[Tensor], ebins: Optional[Tensor],
+                           contraction: bool, aabb: Optional[Sequence[float]]) -> Tuple[Tensor, Tensor]:
+    """Ray form: origins/directions [R,3] + euclidean bin edges [R,S+1] -> x [R*S,3], selector uint8 [R*S].
+    Point form (directions None): origins is positions [N,3]."""
+    o = _c(origins.float())
+    box = host_floats(aabb) if aabb is not None else None
+    boxp = C.cast(box, C.c_void_p) if box is not None else C.c_void_p(0)
+    if directions is None:
+        n = o.shape[0]
+        x = torch.empty(n, 3, device=o.device, dtype=torch.float32)
+        sel = torch.empty(n, device=o.device, dtype=torch.uint8)
+        call("b2n_positions_fwd", ptr(o), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), 0, n, 1, int(contraction), boxp,
+             ptr(x), ptr(sel, torch.uint8), stream())
+        return x, sel
+    d = _c(directions.float())
+    iv = ebins if isinstance(ebins, Intervals) else Intervals.from_edges(ebins)
+    R, S = iv.R, iv.S
+    x = torch.empty(R * S, 3, device=o.device, dtype=torch.float32)
+    sel = torch.empty(R * S, device=o.device, dtype=torch.uint8)
+    call("b2n_positions_fwd", ptr(o), ptr(d), iv.p_starts, iv.p_ends, iv.stride, R, S, int(contraction), boxp, ptr(x),
+         ptr(sel, torch.uint8), stream())
+    return x, sel
+
+
+class _DensityActFn(torch.autograd.Function):
+    """density = avg_init * trunc_exp(h) * selector."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, h, sel, avg_init):
+        h = _c(h)
+        n = h.numel()
+        out = torch.empty(n, device=h.device, dtype=torch.float32)
+        call("b2n_density_act_fwd", ptr(h), 1, ptr(sel, torch.uint8), n, float(avg_init), ptr(out), stream())
+        ctx.avg = float(avg_init)
+        ctx.save_for_backward(h, sel)
+        return out.view(h.shape)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        h, sel = ctx.saved_tensors
+        dh = torch.empty_like(h)
+        call("b2n_density_act_bwd", ptr(h), 1, ptr(sel, torch.uint8), ptr(_c(g.float())), h.numel(), ctx.avg, ptr(dh), 1,
+             stream())
+        return dh, None, None
+
+
+def density_activation(h: Tensor, sel: Optional[Tensor], avg_init: float) -> Tensor:
+    return _DensityActFn.apply(h, sel, avg_init)
+
+
+# ----------------------------------------------------------------------------------------
+# samplers
+# ----------------------------------------------------------------------------------------
+_LINSPACE_CACHE = {}
+
+
+def _linspace(start: float, end: float, steps: int, device) -> Tensor:
+    """torch.linspace evaluated on the CPU (the oracle's arithmetic) and cached on the device."""
+    key = (start, end, steps, str(device))
+    if key not in _LINSPACE_CACHE:
+        _LINSPACE_CACHE[key] = torch.linspace(start, end, steps).to(device)
+    return _LINSPACE_CACHE[key]
+
+
+def spaced_sample(nears: Tensor, fars: Tensor, num_samples: int, spacing: str, jitter: Optional[Tensor]):
+    """-> (spacing bins [R,S+1], euclidean bins [R,S+1]).  jitter None | [R,1] | [R,S+1]."""
+    n, f = _c(nears.float().reshape(-1)), _c(fars.float().reshape(-1))
+    R = n.shape[0]
+    lin = _linspace(0.0, 1.0, num_samples + 1, n.device)
+    per_bin = 0
+    if jitter is not None:
+        jitter = _c(jitter.float())
+        per_bin = int(jitter.numel() != R)
+        if per_bin and jitter.numel() != R * (num_samples + 1):
+            raise ValueError("jitter must be [R,1] or [R,S+1]")
+    sb = torch.empty(R, num_samples + 1, device=n.device, dtype=torch.float32)
+    eb = torch.empty_like(sb)
+    call("b2n_spaced_sample", ptr(n), ptr(f), ptr(lin), ptr(jitter), per_bin, R, num_samples, lib.SPACING[spacing],
+         ptr(sb), ptr(eb), stream())
+    return sb, eb
+
+
+def pdf_sample(sbins: Tensor, weights: Tensor, num_samples: int, jitter: Optional[Tensor], nears: Tensor, fars: Tensor,
+               spacing: str, anneal: float = 1.0, histogram_padding: float = 0.01, eps: float = 1e-5,
+               want_aux: bool = False):
+    """Inverse-CDF resampling (include_original=False).  -> (new spacing bins [R,nb], new euclidean bins [R,nb]
+    [, cdf [R,S+1], inds int64 [R,nb]])."""
+    sb, w = _c(sbins.float()), _c(weights.detach().float())
+    R, S = w.shape
+    nb = num_samples + 1
+    u_base = _linspace(0.0, 1.0 - (1.0 / nb), nb, sb.device)
+    per_bin = 0
+    if jitter is not None:
+        jitter = _c(jitter.float())
+        per_bin = int(jitter.numel() != R)
+    n, f = _c(nears.float().reshape(-1)), _c(fars.float().reshape(-1))
+    new_sb = torch.empty(R, nb, device=sb.device, dtype=torch.float32)
+    new_eb = torch.empty_like(new_sb)
+    cdf = torch.empty(R, S + 1, device=sb.device, dtype=torch.float32) if want_aux else None
+    inds = torch.empty(R, nb, device=sb.device, dtype=torch.int64) if want_aux else None
+    call("b2n_pdf_sample", ptr(sb), ptr(w), ptr(u_base), ptr(jitter), per_bin, ptr(n), ptr(f), R, S, nb, float(anneal),
+         float(histogram_padding), float(eps), lib.SPACING[spacing], ptr(new_sb), ptr(new_eb), ptr(cdf),
+         ptr(inds, torch.int64), stream())
+    return (new_sb, new_eb, cdf, inds) if want_aux else (new_sb, new_eb)
+
+
+# ----------------------------------------------------------------------------------------
+# weights / compositing / losses
+# ----------------------------------------------------------------------------------------
+class Intervals:
+    """Sample intervals along rays as the kernels take them: starts/ends pointers + a row stride.
+
+    `from_edges(e)` wraps an [R,S+1] edge array (starts=e, ends=e+1 element, stride S+1) — what every sampler of
+    the reference produces; `from_pairs(starts, ends)` takes two independent [R,S] arrays (packed or hand-built)."""
+
+    def __init__(self, base: Tensor, ends: Optional[Tensor], n_rays: int, n_samples: int, stride: int):
+        self.base, self.ends_t, self.R, self.S, self.stride = base, ends, n_rays, n_samples, stride
+
+    @staticmethod
+    def from_edges(edges: Tensor) -> "Intervals":
+        e = _c(edges.detach().float())
+        return Intervals(e, None, e.shape[0], e.shape[1] - 1, e.shape[1])
+
+    @staticmethod
+    def from_pairs(starts: Tensor, ends: Tensor) -> "Intervals":
+        s, e = _c(starts.detach().float()), _c(ends.detach().float())
+        return Intervals(s, e, s.shape[0], s.shape[1], s.shape[1])
+
+    @property
+    def p_starts(self):
+        return ptr(self.base)
+
+    @property
+    def p_ends(self):
+        return ptr(self.ends_t) if self.ends_t is not None else C.c_void_p(self.base.data_ptr() + 4)
+
+    def starts(self) -> Tensor:
+        return self.base[:, : self.S]
+
+    def ends(self) -> Tensor:
+        return self.ends_t if self.ends_t is not None else self.base[:, 1:]
+
+
+class _WeightsFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, iv, density):
+        d = _c(density)
+        w = torch.empty_like(d)
+        call("b2n_weights_fwd", iv.p_starts, iv.p_ends, iv.stride, ptr(d), iv.R, iv.S, ptr(w), stream())
+        ctx.iv = iv
+        ctx.save_for_backward(d)
+        return w
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dw):
+        (d,) = ctx.saved_tensors
+        iv = ctx.iv
+        dd = torch.empty_like(d)
+        call("b2n_weights_bwd", iv.p_starts, iv.p_ends, iv.stride, ptr(d), ptr(_c(dw.float())), iv.R, iv.S, ptr(dd),
+             stream())
+        return None, dd
+
+
+def _intervals(x) -> Intervals:
+    return x if isinstance(x, Intervals) else Intervals.from_edges(x)
+
+
+def render_weights(ebins, density: Tensor) -> Tensor:
+    """ebins: [R,S+1] euclidean edges (or an Intervals), density [R,S] -> weights [R,S]."""
+    return _WeightsFn.apply(_intervals(ebins), density)
+
+
+def _bg_args(background):
+    if background is None or (isinstance(background, str) and background == "random"):
+        return lib.BG_NONE, C.c_void_p(0), None
+    if isinstance(background, str) and background == "last_sample":
+        return lib.BG_LAST_SAMPLE, C.c_void_p(0), None
+    if isinstance(background, str):
+        background = {"white": (1.0, 1.0, 1.0), "black": (0.0, 0.0, 0.0)}[background]
+    arr = host_floats(background)
+    return lib.BG_CONSTANT, C.cast(arr, C.c_void_p), arr
+
+
+class _CompositeFn(torch.autograd.Function):
+    """-> (rgb [R,3], accumulation [R], expected depth [R] (unclipped))."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, rgb, weights, iv, background, eval_mode):
+        rgb, w = _c(rgb), _c(weights)
+        R, S = w.shape
+        mode, bgp, keep = _bg_args(background)
+        out = torch.empty(R, 3, device=w.device, dtype=torch.float32)
+        acc = torch.empty(R, device=w.device, dtype=torch.float32)
+        dep = torch.empty(R, device=w.device, dtype=torch.float32)
+        call("b2n_composite_fwd", ptr(rgb), ptr(w), iv.p_starts, iv.p_ends, iv.stride, R, S, mode, bgp, int(eval_mode),
+             ptr(out), ptr(acc), ptr(dep), C.c_void_p(0), C.c_void_p(0), stream())
+        ctx.background, ctx.iv = background, iv
+        ctx.save_for_backward(rgb, w)
+        return out, acc, dep
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, d_out, d_acc, d_dep):
+        rgb, w = ctx.saved_tensors
+        iv = ctx.iv
+        R, S = w.shape
+        mode, bgp, keep = _bg_args(ctx.background)
+        d_rgb = torch.empty_like(rgb)
+        d_w = torch.empty_like(w)
+        f = lambda t: None if t is None else _c(t.float())
+        call("b2n_composite_bwd", ptr(rgb), ptr(w), iv.p_starts, iv.p_ends, iv.stride, ptr(f(d_out)), ptr(f(d_acc)),
+             ptr(f(d_dep)), R, S, mode, bgp, ptr(d_rgb), ptr(d_w), stream())
+        return d_rgb, d_w, None, None, None
+
+
+def composite(rgb: Tensor, weights: Tensor, ebins, background="last_sample", eval_mode: bool = False):
+    """rgb [R,S,3], weights [R,S], ebins [R,S+1] | Intervals -> (rgb [R,3], acc [R], expected depth [R] pre-clip)."""
+    return _CompositeFn.apply(rgb, weights, _intervals(ebins), background, eval_mode)
+
+
+def accumulate(weights: Tensor) -> Tensor:
+    """AccumulationRenderer on dense samples: [R,S] -> [R] (differentiable through torch: a plain row sum)."""
+    return weights.sum(dim=-1)
+
+
+def median_depth(weights: Tensor, ebins) -> Tuple[Tensor, Tensor]:
+    w = _c(weights.detach().float())
+    iv = _intervals(ebins)
+    R, S = w.shape
+    dep = torch.empty(R, device=w.device, dtype=torch.float32)
+    idx = torch.empty(R, device=w.device, dtype=torch.int64)
+    call("b2n_composite_fwd", C.c_void_p(0), ptr(w), iv.p_starts, iv.p_ends, iv.stride, R, S, lib.BG_NONE, C.c_void_p(0),
+         0, C.c_void_p(0), C.c_void_p(0), C.c_void_p(0), ptr(dep), ptr(idx, torch.int64), stream())
+    return dep, idx
+
+
+class _InterlevelFn(torch.autograd.Function):
+    """sum over rows of the proposal-envelope loss for one proposal level; grad only w.r.t. wp."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, c, w, cp, wp):
+        c, w, cp, wp = _c(c), _c(w), _c(cp), _c(wp)
+        R, Sc, Sp = w.shape[0], w.shape[1], wp.shape[1]
+        rows = torch.empty(R, device=w.device, dtype=torch.float32)
+        d_wp = torch.empty_like(wp)
+        call("b2n_interlevel_fwd_bwd", ptr(c), ptr(w), ptr(cp), ptr(wp), R, Sc, Sp, 1.0, ptr(rows), ptr(d_wp), stream())
+        ctx.save_for_backward(d_wp)
+        return rows.sum()
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        (d_wp,) = ctx.saved_tensors
+        return None, None, None, d_wp * g
+
+
+def interlevel_loss(weights_list: List[Tensor], sdist_list: List[Tensor]) -> Tensor:
+    """losses.py:113-132 — weights [R,S_i], sdist [R,S_i+1]; last entry is the (detached) target histogram."""
+    c, w = sdist_list[-1].detach(), weights_list[-1].detach()
+    total = 0.0
+    for sd, wp in zip(sdist_list[:-1], weights_list[:-1]):
+        total = total + _InterlevelFn.apply(c, w, sd.detach(), wp) / float(w.shape[0] * w.shape[1])
+    return total
+
+
+class _DistortionFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, t, w):
+        t, w = _c(t), _c(w)
+        R, S = w.shape
+        rows = torch.empty(R, device=w.device, dtype=torch.float32)
+        d_w = torch.empty_like(w)
+        call("b2n_distortion_fwd_bwd", ptr(t), ptr(w), R, S, 1.0, ptr(rows), ptr(d_w), stream())
+        ctx.save_for_backward(d_w)
+        return rows.sum()
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        (d_w,) = ctx.saved_tensors
+        return None, d_w * g
+
+
+def distortion_loss(weights: Tensor, sdist: Tensor) -> Tensor:
+    """losses.py:135-154 on the last level: mean over rays."""
+    return _DistortionFn.apply(sdist.detach(), weights) / float(weights.shape[0])
+
+
+# ----------------------------------------------------------------------------------------
+# ray generation / colliders
+# ----------------------------------------------------------------------------------------
+def generate_rays(c2w: Tensor, intrinsics: Tensor, distortion: Optional[Tensor], ray_indices: Tensor):
+    """c2w [C,3,4], intrinsics [C,4]=(fx,fy,cx,cy), distortion [C,6]|None, ray_indices int64 [R,3]."""
+    c2w, intr, ri = _c(c2w.float()), _c(intrinsics.float()), _c(ray_indices.long())
+    dist = _c(distortion.float()) if distortion is not None else None
+    R = ri.shape[0]
+    dev = c2w.device
+    o = torch.empty(R, 3, device=dev)
+    d = torch.empty(R, 3, device=dev)
+    area = torch.empty(R, 1, device=dev)
+    nrm = torch.empty(R, 1, device=dev)
+    cam = torch.empty(R, 1, device=dev, dtype=torch.int64)
+    call("b2n_raygen", ptr(c2w), ptr(intr), ptr(dist), ptr(ri, torch.int64), R, ptr(o), ptr(d), ptr(area), ptr(nrm),
+         ptr(cam, torch.int64), stream())
+    return dict(origins=o, directions=d, pixel_area=area, directions_norm=nrm, camera_indices=cam)
+
+
+def aabb_collide(origins: Tensor, directions: Tensor, aabb: Sequence[float], near_plane: float):
+    o, d = _c(origins.float()), _c(directions.float())
+    R = o.shape[0]
+    n = torch.empty(R, 1, device=o.device)
+    f = torch.empty(R, 1, device=o.device)
+    box = host_floats(aabb)
+    call("b2n_aabb_collide", ptr(o), ptr(d), C.cast(box, C.c_void_p), float(near_plane), R, ptr(n), ptr(f), stream())
+    return n, f
+
+
+# ----------------------------------------------------------------------------------------
+# packed path
+# ----------------------------------------------------------------------------------------
+def pack_info(ray_indices: Tensor, n_rays: int) -> Tensor:
+    ri = _c(ray_indices.long())
+    info = torch.empty(n_rays, 2, device=ri.device, dtype=torch.int64)
+    call("b2n_pack_info", ptr(ri, torch.int64), ri.shape[0], n_rays, ptr(info, torch.int64), stream())
+    return info
+
+
+class _PackedWeightsFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, t_starts, t_ends, sigmas, packed_info):
+        ts, te, sg = _c(t_starts), _c(t_ends), _c(sigmas)
+        w, tr, al = torch.empty_like(sg), torch.empty_like(sg), torch.empty_like(sg)
+        call("b2n_packed_weights_fwd", ptr(ts), ptr(te), ptr(sg), ptr(packed_info, torch.int64), packed_info.shape[0],
+             ptr(w), ptr(tr), ptr(al), stream())
+        ctx.save_for_backward(ts, te, sg, packed_info)
+        ctx.mark_non_differentiable(tr, al)
+        return w, tr, al
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dw, _dt, _da):
+        ts, te, sg, info = ctx.saved_tensors
+        ds = torch.empty_like(sg)
+        call("b2n_packed_weights_bwd", ptr(ts), ptr(te), ptr(sg), ptr(info, torch.int64), ptr(_c(dw.float())),
+             info.shape[0], ptr(ds), stream())
+        return None, None, ds, None
+
+
+def packed_weights(t_starts, t_ends, sigmas, packed_info):
+    return _PackedWeightsFn.apply(t_starts, t_ends, sigmas, _c(packed_info.long()))
+
+
+class _PackedAccumFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, weights, values, packed_info):
+        w = _c(weights)
+        v = _c(values) if values is not None else None
+        d = 1 if v is None else v.shape[-1]
+        R = packed_info.shape[0]
+        out = torch.empty(R, d, device=w.device, dtype=torch.float32)
+        call("b2n_packed_accumulate_fwd", ptr(w), ptr(v), d, ptr(packed_info, torch.int64), R, ptr(out), stream())
+        ctx.d = d
+        ctx.has_values = v is not None
+        ctx.save_for_backward(w, v if v is not None else w, packed_info)
+        return out
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dout):
+        w, v, info = ctx.saved_tensors
+        v = v if ctx.has_values else None
+        dw = torch.empty_like(w)
+        dv = torch.empty_like(v) if v is not None else None
+        call("b2n_packed_accumulate_bwd", ptr(w), ptr(v), ctx.d, ptr(info, torch.int64), ptr(_c(dout.float())),
+             info.shape[0], ptr(dw), ptr(dv), stream())
+        return dw, dv, None
+
+
+def packed_accumulate(weights: Tensor, values: Optional[Tensor], packed_info: Tensor) -> Tensor:
+    return _PackedAccumFn.apply(weights, values, _c(packed_info.long()))
+
+
+def occgrid_march(origins, directions, binaries, roi_aabb, step, near_plane=0.0, far_plane=1e10, cone_angle=0.0,
+                  jitter=None, t_min=None, t_max=None):
+    """-> (ray_indices int64 [M], t_starts [M], t_ends [M]), sorted by ray then t.  binaries uint8/bool [levels,r,r,r]."""
+    o, d = _c(origins.float()), _c(directions.float())
+    R = o.shape[0]
+    b = _c(binaries.to(torch.uint8))
+    levels, res = b.shape[0], b.shape[1]
+    roi = host_floats(roi_aabb)
+    roip = C.cast(roi, C.c_void_p)
+    f = lambda t: None if t is None else _c(t.float().reshape(-1))
+    jit, tmn, tmx = f(jitter), f(t_min), f(t_max)
+    counts = torch.empty(R, device=o.device, dtype=torch.int32)
+    call("b2n_occgrid_count", ptr(o), ptr(d), ptr(tmn), ptr(tmx), ptr(b, torch.uint8), levels, res, roip, float(step),
+         float(cone_angle), float(near_plane), float(far_plane), ptr(jit), R, ptr(counts, torch.int32), stream())
+    csum = torch.cumsum(counts.long(), 0)
+    offsets = _c(csum - counts.long())
+    M = int(csum[-1].item()) if R > 0 else 0
+    ri = torch.empty(M, device=o.device, dtype=torch.int64)
+    ts = torch.empty(M, device=o.device, dtype=torch.float32)
+    te = torch.empty(M, device=o.device, dtype=torch.float32)
+    if M > 0:
+        call("b2n_occgrid_fill", ptr(o), ptr(d), ptr(tmn), ptr(tmx), ptr(b, torch.uint8), levels, res, roip, float(step),
+             float(cone_angle), float(near_plane), float(far_plane), ptr(jit), R, ptr(offsets, torch.int64),
+             ptr(ri, torch.int64), ptr(ts), ptr(te), stream())
+    return ri, ts, te
+
+
+# ----------------------------------------------------------------------------------------
+# optimiser
+# ----------------------------------------------------------------------------------------
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-15,
+              grad_scale: float = 1.0) -> None:
+    call("b2n_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), float(lr), float(betas[0]),
+         float(betas[1]), float(eps), float(grad_scale), stream())

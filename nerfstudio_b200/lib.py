@@ -1,0 +1,156 @@
+"""ctypes binding of libb200nerf.so (include/b200nerf.h).  No torch types cross this boundary: tensors are
+passed as raw device pointers + sizes and the current CUDA stream as a void*.
+
+The product path fails loudly: if the shared library is missing, cannot be loaded, or a call returns an
+error code, a RuntimeError/ValueError is raised.  There is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200nerf.so")
+
+MAX_LEVELS = 32
+MAX_MLP_LAYERS = 10
+
+GRID_TORCH, GRID_TCNN = 0, 1
+ACT = {"none": 0, "relu": 1, "sigmoid": 2, "softplus": 3, "tanh": 4}
+SPACING = {"uniform": 0, "piecewise": 1, "lindisp": 2, "sqrt": 3, "log": 4}
+BG_NONE, BG_LAST_SAMPLE, BG_CONSTANT = 0, 1, 2
+
+
+class B2nGrid(C.Structure):
+    _fields_ = [
+        ("n_levels", C.c_int32), ("n_features", C.c_int32), ("log2_hashmap_size", C.c_int32), ("mode", C.c_int32),
+        ("scale", C.c_float * MAX_LEVELS), ("resolution", C.c_uint32 * MAX_LEVELS),
+        ("offset", C.c_uint32 * MAX_LEVELS), ("size", C.c_uint32 * MAX_LEVELS), ("hashed", C.c_uint32 * MAX_LEVELS),
+    ]
+
+
+class B2nMlp(C.Structure):
+    _fields_ = [
+        ("n_layers", C.c_int32), ("in_dim", C.c_int32), ("hidden_act", C.c_int32), ("out_act", C.c_int32),
+        ("out_dims", C.c_int32 * MAX_MLP_LAYERS), ("skip", C.c_int32 * MAX_MLP_LAYERS),
+        ("w", C.c_void_p * MAX_MLP_LAYERS), ("b", C.c_void_p * MAX_MLP_LAYERS),
+    ]
+
+
+class B2nMlpGrad(C.Structure):
+    _fields_ = [("dw", C.c_void_p * MAX_MLP_LAYERS), ("db", C.c_void_p * MAX_MLP_LAYERS)]
+
+
+_P, _I64, _I32, _F = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+# name -> argtypes (return type is always int unless listed in _RET)
+_SIGNATURES = {
+    "b2n_device_info": [_P],
+    "b2n_tune": [C.c_char_p, C.c_int],
+    "b2n_hashgrid_fwd": [C.POINTER(B2nGrid), _P, _P, _I64, _P, _P, _P],
+    "b2n_hashgrid_bwd": [C.POINTER(B2nGrid), _P, _P, _P, _I64, _P, _P, _P],
+    "b2n_mlp_fwd": [C.POINTER(B2nMlp), _P, _I64, _P, _P, _P],
+    "b2n_mlp_bwd": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _I64, _P, _P],
+    "b2n_sh_fwd": [_P, _I64, _I32, _I32, _P, _P],
+    "b2n_freq_fwd": [_P, _I64, _I32, _P, _I32, _I32, _P, _P],
+    "b2n_freq_bwd": [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P],
+    "b2n_positions_fwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P],
+    "b2n_density_act_fwd": [_P, _I64, _P, _I64, _F, _P, _P],
+    "b2n_density_act_bwd": [_P, _I64, _P, _P, _I64, _F, _P, _I64, _P],
+    "b2n_spaced_sample": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P, _P],
+    "b2n_pdf_sample": [_P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P],
+    "b2n_weights_fwd": [_P, _P, _I64, _P, _I64, _I32, _P, _P],
+    "b2n_weights_bwd": [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P],
+    "b2n_composite_fwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P],
+    "b2n_composite_bwd": [_P, _P, _P, _P, _I64, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _P],
+    "b2n_interlevel_fwd_bwd": [_P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _P, _P],
+    "b2n_distortion_fwd_bwd": [_P, _P, _I64, _I32, _F, _P, _P, _P],
+    "b2n_raygen": [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P],
+    "b2n_aabb_collide": [_P, _P, _P, _F, _I64, _P, _P, _P],
+    "b2n_pack_info": [_P, _I64, _I64, _P, _P],
+    "b2n_packed_weights_fwd": [_P, _P, _P, _P, _I64, _P, _P, _P, _P],
+    "b2n_packed_weights_bwd": [_P, _P, _P, _P, _P, _I64, _P, _P],
+    "b2n_packed_accumulate_fwd": [_P, _P, _I32, _P, _I64, _P, _P],
+    "b2n_packed_accumulate_bwd": [_P, _P, _I32, _P, _P, _I64, _P, _P, _P],
+    "b2n_occgrid_count": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P],
+    "b2n_occgrid_fill": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P, _P, _P, _P],
+    "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _F, _P],
+}
+_RET = {"b2n_version": C.c_char_p, "b2n_last_error": C.c_char_p}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RET))
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (never builds, never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m nerfstudio_b200.build` (nvcc, sm_100a). "
+            "nerfstudio_b200 has no CPU/PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, C.c_int
+    for name, ret in _RET.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = [], ret
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().b2n_last_error().decode()
+
+
+def check(code: int, what: str) -> None:
+    if code == 0:
+        return
+    msg = last_error()
+    if code < 0:
+        raise ValueError(f"{what}: {msg} (code {code})")
+    raise RuntimeError(f"{what}: CUDA error {code}: {msg}")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: Optional[torch.Tensor], dtype: Optional[torch.dtype] = torch.float32) -> C.c_void_p:
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("nerfstudio_b200 kernels need CUDA tensors (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def host_floats(values) -> C.Array:
+    vals = [float(v) for v in values]
+    return (C.c_float * len(vals))(*vals)
+
+
+def device_info() -> dict:
+    out = (C.c_int32 * 4)()
+    call("b2n_device_info", C.cast(out, C.c_void_p))
+    return dict(sm_count=out[0], cc_major=out[1], cc_minor=out[2], max_smem_optin=out[3])
+
+
+def tune(key: str, value: int) -> bool:
+    return bool(load().b2n_tune(key.encode(), int(value)))

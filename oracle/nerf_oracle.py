@@ -591,12 +591,12 @@ def packed_weights(t_starts: Tensor, t_ends: Tensor, sigmas: Tensor, ray_indices
     sd = sigmas * (t_ends - t_starts)
     alphas = 1.0 - torch.exp(-sd)
     info = pack_info(ray_indices, n_rays)
-    cs = torch.cumsum(sd, 0)
-    excl = cs - sd
-    base = torch.zeros(n_rays, dtype=sd.dtype)
+    cs = torch.cumsum(sd.double(), 0)  # fp64 so that the per-ray prefix keeps fp32 accuracy on long packs
+    excl = cs - sd.double()
+    base = torch.zeros(n_rays, dtype=torch.float64)
     nonempty = info[:, 1] > 0
     base[nonempty] = excl[info[nonempty, 0]]
-    trans = torch.exp(-(excl - base[ray_indices]))
+    trans = torch.exp(-(excl - base[ray_indices]).to(sd.dtype))
     return trans * alphas, trans, alphas
 
 
@@ -621,6 +621,7 @@ def ray_aabb_intersect(o: Tensor, d: Tensor, aabb: Tensor, near: float = 0.0, fa
 def occgrid_march(
     o: Tensor, d: Tensor, binaries: Tensor, aabb: Tensor, step: float, near: float, far: float,
     cone_angle: float = 0.0, jitter: Optional[Tensor] = None, max_samples_per_ray: int = 1 << 20,
+    t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None,
 ):
     """Occupancy-grid ray marching with nerfacc-style multi-level grids (pure-python; small cases only).
 
@@ -635,6 +636,11 @@ def occgrid_march(
     half = (aabb[3:] - aabb[:3]) / 2
     big = torch.cat([centre - half * 2 ** (levels - 1), centre + half * 2 ** (levels - 1)])
     tmin, tmax, hit = ray_aabb_intersect(o, d, big, near, far)
+    if t_min is not None:
+        tmin = torch.maximum(tmin, t_min.reshape(-1))
+    if t_max is not None:
+        tmax = torch.minimum(tmax, t_max.reshape(-1))
+    hit = tmax > tmin
     ri, ts, te = [], [], []
     f32 = torch.float32
     for r in range(o.shape[0]):
@@ -651,7 +657,9 @@ def occgrid_march(
             p = o[r] + d[r] * mid
             rel = torch.abs(p - centre) / half
             m = float(rel.max())
-            lvl = 0 if m <= 1.0 else int(math.ceil(math.log2(m)))
+            lvl = 0
+            while lvl < levels and m > float(1 << lvl):  # finest level whose box contains the point
+                lvl += 1
             if lvl < levels:
                 scale = 2.0 ** lvl
                 q = ((p - centre) / (half * scale) + 1.0) * 0.5

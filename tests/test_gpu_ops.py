@@ -1,0 +1,361 @@
+"""GPU parity: every C-ABI kernel vs the golden vectors recorded from the reference and vs the oracle.
+
+Bars (north_star): bit-exact for integer / index outputs, <= 1e-4 relative (max-norm) for fp32 — most ops are
+held to a tighter 2e-5.  All calls go through nerfstudio_b200.functional -> ctypes -> libb200nerf.so.
+"""
+import pytest
+import torch
+
+from conftest import assert_close
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+TIGHT = 2e-5
+
+
+@pytest.fixture(scope="module")
+def F():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from nerfstudio_b200 import functional
+
+    return functional
+
+
+def cu(t):
+    return t.cuda() if isinstance(t, torch.Tensor) else t
+
+
+# ------------------------------------------------------------------------------------------------
+def test_hashgrid_golden(F, golden):
+    g = golden("hash_encoding")
+    for nm in ("small", "f4", "mid"):
+        L, lo, hi, log2T, Fd = (int(v) for v in g[f"{nm}_cfg"])
+        grid = F.GridSpec(g[f"{nm}_scalings"].tolist(), log2T, Fd)
+        x, table = cu(g[f"{nm}_x"]), cu(g[f"{nm}_table"])
+        y, idx = F.hashgrid_forward(x, table, grid, want_indices=True)
+        assert torch.equal(idx.cpu(), g[f"{nm}_idx"]), f"{nm}: corner indices must be bit-exact"
+        assert_close(y, g[f"{nm}_y"], TIGHT, nm)
+        dtable, dx = F.hashgrid_backward(x, table, cu(g[f"{nm}_dy"]), grid, want_dx=True)
+        assert_close(dtable, g[f"{nm}_dtable"], TIGHT, nm + " dtable")
+        # dx against autograd of the oracle
+        xr = g[f"{nm}_x"].clone().requires_grad_(True)
+        yo = O.hash_encode(xr, g[f"{nm}_table"], g[f"{nm}_scalings"], log2T)
+        (gx,) = torch.autograd.grad(yo, xr, g[f"{nm}_dy"])
+        assert_close(dx, gx, REL, nm + " dx")
+
+
+def test_hashgrid_full_size_properties(F):
+    """BASELINE size (L=16, T=2^19, N=196608): indices vs oracle on a slice, linearity in the table, and
+    scatter/gather adjointness  <dy, enc(table)> == <dtable, table>."""
+    torch.manual_seed(0)
+    scal = O.hash_level_scalings(16, 16, 2048)
+    grid = F.GridSpec(scal.tolist(), 19, 2)
+    N = 196608
+    x = torch.rand(N, 3, device="cuda")
+    t1 = (torch.rand(16 << 19, 2, device="cuda") * 2 - 1) * 1e-3
+    t2 = torch.randn_like(t1) * 1e-3
+    y1, idx = F.hashgrid_forward(x, t1, grid, want_indices=True)
+    idx_o, _ = O.hash_corner_indices(x[:4096].cpu(), scal, 19)
+    assert torch.equal(idx[:4096].cpu(), idx_o)
+    y2 = F.hashgrid_forward(x, t2, grid)
+    y12 = F.hashgrid_forward(x, t1 + 2 * t2, grid)
+    assert_close(y12, y1 + 2 * y2, 1e-5, "linearity")
+    dy = torch.randn_like(y1)
+    dt, _ = F.hashgrid_backward(x, t1, dy, grid)
+    lhs = (dy.double() * y1.double()).sum()
+    rhs = (dt.double() * t1.double()).sum()
+    assert abs(float(lhs - rhs)) <= 1e-4 * abs(float(lhs)) + 1e-9
+    yo = O.hash_encode(x[:2048].cpu(), t1.cpu(), scal, 19)
+    assert_close(y1[:2048], yo, TIGHT)
+
+
+def test_hashgrid_tcnn_mode(F):
+    """tcnn-mode addressing vs the oracle's restatement of the published semantics (parity unpinned upstream)."""
+    torch.manual_seed(1)
+    g = 1.3819
+    meta, rows = O.tcnn_grid_meta(8, 16, g, 12)
+    grid = F.GridSpec.tcnn(8, 16, g, 12, 2)
+    assert grid.n_rows == rows
+    x = torch.rand(500, 3)
+    table = torch.randn(rows, 2) * 0.1
+    y = F.hashgrid_forward(x.cuda(), table.cuda(), grid)
+    assert_close(y, O.tcnn_hash_encode(x, table, meta), TIGHT)
+
+
+def test_hashgrid_empty_and_errors(F):
+    grid = F.GridSpec([16.0, 32.0], 8, 2)
+    y = F.hashgrid_forward(torch.empty(0, 3, device="cuda"), torch.zeros(512, 2, device="cuda"), grid)
+    assert y.shape == (0, 4)
+    with pytest.raises(ValueError):
+        F.GridSpec([16.0], 8, 3)
+    with pytest.raises(RuntimeError):
+        F.hashgrid_forward(torch.zeros(4, 3), torch.zeros(512, 2), grid)  # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------------
+def _mlp_cfg(nm):
+    return dict(base=(2, (), "none"), head=(3, (), "sigmoid"), prop=(2, (), "none"), skip=(6, (3,), "relu"),
+                one=(1, (), "none"))[nm]
+
+
+def test_mlp_golden(F, golden):
+    g = golden("mlp")
+    for nm in ("base", "head", "prop", "skip", "one"):
+        n, skip, oact = _mlp_cfg(nm)
+        ws = [cu(g[f"{nm}_w{i}"]).requires_grad_(True) for i in range(n)]
+        bs = [cu(g[f"{nm}_b{i}"]).requires_grad_(True) for i in range(n)]
+        x = cu(g[f"{nm}_x"]).requires_grad_(True)
+        spec = F.MlpSpec(x.shape[1], [w.shape[0] for w in ws], skip=skip, out_act=oact)
+        y = F.mlp(spec, x, ws, bs)
+        assert_close(y, g[f"{nm}_y"], TIGHT, nm)
+        grads = torch.autograd.grad(y, [x] + ws + bs, cu(g[f"{nm}_dy"]))
+        assert_close(grads[0], g[f"{nm}_dx"], TIGHT, nm + " dx")
+        for i in range(n):
+            assert_close(grads[1 + i], g[f"{nm}_dw{i}"], TIGHT, f"{nm} dw{i}")
+            assert_close(grads[1 + n + i], g[f"{nm}_db{i}"], TIGHT, f"{nm} db{i}")
+
+
+def test_mlp_large_batch_vs_oracle(F):
+    """Ragged batch (not a multiple of the 128-row tile), many tiles per CTA; no-bias (tcnn-style) variant too."""
+    torch.manual_seed(3)
+    for bias in (True, False):
+        n = 128 * 700 + 37
+        x = torch.randn(n, 63)
+        ws = [torch.randn(64, 63) * 0.2, torch.randn(64, 64) * 0.2, torch.randn(3, 64) * 0.2]
+        bs = [torch.randn(64) * 0.1, torch.randn(64) * 0.1, torch.randn(3) * 0.1] if bias else [None] * 3
+        dy = torch.randn(n, 3)
+        wl = [w.clone().requires_grad_(True) for w in ws]
+        bl = [b.clone().requires_grad_(True) if b is not None else None for b in bs]
+        yo = O.mlp_forward(x, wl, bl, out_act="sigmoid")
+        go = torch.autograd.grad(yo, wl + [b for b in bl if b is not None], dy)
+        wc = [w.cuda().requires_grad_(True) for w in ws]
+        bc = [b.cuda().requires_grad_(True) if b is not None else None for b in bs]
+        spec = F.MlpSpec(63, [64, 64, 3], out_act="sigmoid", bias=bias)
+        y = F.mlp(spec, x.cuda(), wc, bc)
+        assert_close(y, yo, TIGHT)
+        gc = torch.autograd.grad(y, wc + [b for b in bc if b is not None], dy.cuda())
+        for a, b in zip(gc, go):
+            assert_close(a, b, REL)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_encodings_golden(F, golden):
+    g = golden("encodings")
+    d = cu(g["dirs"])
+    for lv in range(1, 6):
+        assert_close(F.sh_encode(d, lv, remap01=True), g[f"sh{lv}"], TIGHT, f"sh{lv}")
+        assert_close(F.sh_encode(d, lv, remap01=False), g[f"sh{lv}_raw"], TIGHT)
+    with pytest.raises(ValueError):
+        F.sh_encode(d, 6)
+    x = cu(g["x"]).requires_grad_(True)
+    freqs = (2 ** torch.linspace(0.0, 8.0, 10)).tolist()
+    y = F.freq_encode(x, freqs, True)
+    assert_close(y, g["pe_y"], 2e-4, "nerf enc")  # sin of arguments up to ~3e3: fp32 argument rounding
+    (gx,) = torch.autograd.grad(y, x, cu(g["pe_dy"]))
+    assert_close(gx, g["pe_dx"], 2e-4)
+    assert_close(F.freq_encode(cu(g["x"]), (2 ** torch.linspace(0.0, 4.0, 4)).tolist(), True), g["de_y"], TIGHT)
+    assert_close(F.freq_encode(cu(g["x"]), (2 ** torch.linspace(0.0, 1.0, 2)).tolist(), False), g["p2_y"], TIGHT)
+    # contraction through the positions kernel (point form): (contract(x)+2)/4 * selector
+    px, sel = F.positions_to_unit_cube(cu(g["contract_x"]), None, None, True, None)
+    ref, sel_o = O.normalize_and_select(g["contract_x"], None, True)
+    assert torch.equal(px.cpu(), ref), "contracted positions must be bit-identical (they feed floor/ceil)"
+    assert torch.equal(sel.cpu().bool(), sel_o)
+
+
+def test_positions_ray_form_bit_exact(F, golden):
+    g = golden("nerfacto_field")
+    for nm, con in (("train", True), ("aabb", False)):
+        o, d, eb = g[f"{nm}_origins"], g[f"{nm}_directions"], g[f"{nm}_ebins"]
+        pos = O.frustum_positions(o, d, eb[:, :-1], eb[:, 1:])
+        ref, sel_o = O.normalize_and_select(pos, g["aabb"], con)
+        x, sel = F.positions_to_unit_cube(cu(o), cu(d), cu(eb), con, g["aabb"].flatten().tolist())
+        assert torch.equal(x.cpu().view_as(ref), ref), nm
+        assert torch.equal(sel.cpu().bool().view_as(sel_o), sel_o)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_samplers_golden(F, golden):
+    g = golden("samplers")
+    for kind in ("piecewise", "uniform"):
+        for mode in ("eval", "single", "multi"):
+            jit = g.get(f"{kind}_{mode}_jitter")
+            sb, eb = F.spaced_sample(cu(g["nears"]), cu(g["fars"]), 32, kind, cu(jit) if jit is not None else None)
+            assert torch.equal(sb.cpu(), g[f"{kind}_{mode}_sbins"].expand(64, -1)), (kind, mode)
+            assert torch.equal(eb.cpu(), g[f"{kind}_{mode}_ebins"]), (kind, mode)
+    sb0 = cu(g["piecewise_eval_sbins"])
+    w = cu(g["pdf_weights"][..., 0])
+    for mode in ("eval", "single", "multi"):
+        jit = g.get(f"pdf_{mode}_jitter")
+        nsb, neb, cdf, inds = F.pdf_sample(sb0, w, 16, cu(jit) if jit is not None else None, cu(g["nears"]),
+                                           cu(g["fars"]), "piecewise", want_aux=True)
+        ref = O.pdf_sample(g["piecewise_eval_sbins"], g["pdf_weights"][..., 0], 16, jit)
+        assert_close(cdf, ref["cdf"], 1e-6, "cdf")
+        # index work: bit-exact given identical floating-point inputs (the kernel's own cdf) ...
+        u = ref["u"]
+        assert torch.equal(inds.cpu(), torch.searchsorted(cdf.cpu(), u, side="right")), mode
+        # ... and against the reference's recorded indices (identical here: same fp64-accumulated cdf)
+        mism = (inds.cpu() != g[f"pdf_{mode}_inds"]).float().mean().item()
+        assert mism <= 1e-3, f"{mode}: {mism:.2e} of searchsorted indices differ from the reference"
+        assert_close(nsb, g[f"pdf_{mode}_sbins"], 1e-5, mode)  # (u-c0)/(c1-c0) amplifies 1-ulp cdf differences
+        assert_close(neb, g[f"pdf_{mode}_ebins"], 1e-5, mode)
+    n, f = F.aabb_collide(cu(g["origins"]), cu(g["directions"]), [-1, -1, -1, 1, 1, 1], 0.1)
+    assert torch.equal(n.cpu(), g["aabb_nears"]) and torch.equal(f.cpu(), g["aabb_fars"])
+
+
+def test_pdf_sample_full_size(F):
+    """4096 rays x 256 -> 96: inds vs searchsorted on the kernel's cdf (bit-exact), bins sorted, within [0,1]."""
+    torch.manual_seed(5)
+    R, S = 4096, 256
+    sb, eb = F.spaced_sample(torch.full((R, 1), 0.05).cuda(), torch.full((R, 1), 1000.0).cuda(), S, "piecewise",
+                             torch.rand(R, 1).cuda())
+    w = (torch.rand(R, S) ** 8).cuda()
+    jit = torch.rand(R, 1).cuda()
+    near, far = torch.full((R, 1), 0.05).cuda(), torch.full((R, 1), 1000.0).cuda()
+    nsb, neb, cdf, inds = F.pdf_sample(sb, w, 96, jit, near, far, "piecewise", want_aux=True)
+    ref = O.pdf_sample(sb.cpu(), w.cpu(), 96, jit.cpu())
+    assert torch.equal(inds.cpu(), torch.searchsorted(cdf.cpu(), ref["u"], side="right"))
+    assert (inds.cpu() != ref["inds"]).float().mean().item() <= 1e-4
+    assert_close(nsb, ref["bins"], 1e-5)
+    assert bool((nsb[:, 1:] >= nsb[:, :-1]).all()) and float(nsb.min()) >= 0 and float(nsb.max()) <= 1
+
+
+# ------------------------------------------------------------------------------------------------
+def test_render_golden(F, golden):
+    g = golden("render")
+    eb = cu(g["ebins"])
+    dens = cu(g["density"][..., 0]).requires_grad_(True)
+    w = F.render_weights(eb, dens)
+    assert_close(w, g["weights"][..., 0], TIGHT, "weights")
+    (gd,) = torch.autograd.grad(w, dens, cu(g["d_weights"][..., 0]))
+    assert_close(gd, g["d_density"][..., 0], REL, "d_density")
+    for bg in ("last_sample", "white", "black", "random"):
+        rgb = cu(g["rgb_samples"]).requires_grad_(True)
+        wd = cu(g["weights"][..., 0]).requires_grad_(True)
+        comp, acc, dep = F.composite(rgb, wd, eb, bg)
+        assert_close(comp, g[f"rgb_{bg}"], TIGHT, bg)
+        g_rgb, g_w = torch.autograd.grad(comp, [rgb, wd], cu(g[f"rgb_{bg}_dout"]))
+        assert_close(g_rgb, g[f"rgb_{bg}_drgb"], TIGHT)
+        assert_close(g_w, g[f"rgb_{bg}_dw"][..., 0], TIGHT)
+    comp, acc, dep = F.composite(cu(g["rgb_samples_nan"]), cu(g["weights"][..., 0]), eb, "last_sample", eval_mode=True)
+    assert_close(comp, g["rgb_eval"], TIGHT)
+    assert_close(acc, g["accumulation"][..., 0], TIGHT)
+    md, idx = F.median_depth(cu(g["weights"][..., 0]), eb)
+    starts, ends = g["ebins"][:, :-1, None], g["ebins"][:, 1:, None]
+    ref_d, ref_i = O.depth_median(g["weights"], starts, ends)
+    assert torch.equal(idx.cpu(), ref_i[:, 0]), "median index must be bit-exact"
+    assert torch.equal(md.cpu(), g["depth_median"][:, 0])
+    wd = cu(g["weights"][..., 0]).requires_grad_(True)
+    _, _, dep = F.composite(cu(g["rgb_samples"]), wd, eb, "random")
+    steps = (g["ebins"][:, :-1] + g["ebins"][:, 1:]) / 2
+    depc = torch.clip(dep, float(steps.min()), float(steps.max()))
+    assert_close(depc, g["depth_expected"][:, 0], TIGHT)
+    (gw,) = torch.autograd.grad(depc, wd, cu(g["depth_expected_dout"][:, 0]))
+    assert_close(gw, g["depth_expected_dw"][..., 0], REL)
+
+
+def test_losses_golden(F, golden):
+    g = golden("losses")
+    w = [cu(g[f"w{i}"][..., 0]).requires_grad_(True) for i in range(3)]
+    sd = [cu(g[f"sb{i}"]) for i in range(3)]
+    li = F.interlevel_loss(w, sd)
+    assert_close(li, g["interlevel"], TIGHT)
+    g0, g1 = torch.autograd.grad(li, w[:2])
+    assert_close(g0, g["interlevel_dw0"][..., 0], REL)
+    assert_close(g1, g["interlevel_dw1"][..., 0], REL)
+    ld = F.distortion_loss(w[2], sd[2])
+    assert_close(ld, g["distortion"], TIGHT)
+    (g2,) = torch.autograd.grad(ld, [w[2]])
+    assert_close(g2, g["distortion_dw2"][..., 0], REL)
+
+
+def test_raygen_golden(F, golden):
+    g = golden("raygen")
+    intr = torch.stack([g["fx"], g["fy"], g["cx"], g["cy"]], -1)
+    for nm, dist in (("nodist", None), ("dist", g["dist"])):
+        r = F.generate_rays(cu(g["c2w"]), cu(intr), cu(dist) if dist is not None else None, cu(g[f"{nm}_ray_indices"]))
+        assert torch.equal(r["origins"].cpu(), g[f"{nm}_origins"])
+        assert_close(r["directions"], g[f"{nm}_directions"], TIGHT, nm)
+        assert_close(r["pixel_area"], g[f"{nm}_pixel_area"], REL, nm)
+        assert_close(r["directions_norm"], g[f"{nm}_directions_norm"], TIGHT)
+        assert torch.equal(r["camera_indices"].cpu(), g[f"{nm}_camera_indices"])
+
+
+# ------------------------------------------------------------------------------------------------
+def test_packed_path_vs_oracle(F):
+    torch.manual_seed(7)
+    R = 300
+    counts = torch.randint(0, 40, (R,))
+    counts[5] = 0
+    counts[R - 1] = 0
+    ri = torch.repeat_interleave(torch.arange(R), counts)
+    M = ri.numel()
+    info = F.pack_info(ri.cuda(), R)
+    assert torch.equal(info.cpu(), O.pack_info(ri, R))
+    ts = torch.rand(M).cumsum(0) * 0.01
+    te = ts + 0.005
+    sig = (torch.rand(M) * 50).requires_grad_(True)
+    wo, to, ao = O.packed_weights(ts, te, sig, ri, R)
+    dw = torch.randn(M)
+    (gs,) = torch.autograd.grad(wo, sig, dw)
+    sc = sig.detach().cuda().requires_grad_(True)
+    w, tr, al = F.packed_weights(ts.cuda(), te.cuda(), sc, info)
+    assert_close(w, wo, TIGHT)
+    assert_close(tr, to, TIGHT)
+    assert_close(al, ao, TIGHT)
+    (gc,) = torch.autograd.grad(w, sc, dw.cuda())
+    assert_close(gc, gs, REL)
+    vals = torch.rand(M, 3, requires_grad=True)
+    wl = wo.detach().clone().requires_grad_(True)
+    acc_o = O.accumulate_along_rays(wl, vals, ri, R)
+    dout = torch.randn(R, 3)
+    gwo, gvo = torch.autograd.grad(acc_o, [wl, vals], dout)
+    wc, vc = wo.detach().cuda().requires_grad_(True), vals.detach().cuda().requires_grad_(True)
+    acc = F.packed_accumulate(wc, vc, info)
+    assert_close(acc, acc_o, TIGHT)
+    gw, gv = torch.autograd.grad(acc, [wc, vc], dout.cuda())
+    assert_close(gw, gwo, TIGHT)
+    assert_close(gv, gvo, TIGHT)
+    assert_close(F.packed_accumulate(wc, None, info), O.accumulate_along_rays(wo.detach(), None, ri, R), TIGHT)
+
+
+def test_occgrid_march_bit_exact_vs_oracle(F):
+    torch.manual_seed(8)
+    levels, res = 2, 16
+    binaries = torch.rand(levels, res, res, res) > 0.6
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+    R = 48
+    o = torch.randn(R, 3) * 1.5
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(R, 3), dim=-1)
+    jit = torch.rand(R)
+    for cone, jitter in ((0.0, None), (0.01, jit)):
+        ri_o, ts_o, te_o = O.occgrid_march(o, d, binaries, aabb, 0.05, 0.0, 1e10, cone, jitter)
+        ri, ts, te = F.occgrid_march(o.cuda(), d.cuda(), binaries.cuda(), aabb.tolist(), 0.05, 0.0, 1e10, cone,
+                                     None if jitter is None else jitter.cuda())
+        assert torch.equal(ri.cpu(), ri_o), "ray indices / counts must be bit-exact"
+        assert torch.equal(ts.cpu(), ts_o) and torch.equal(te.cpu(), te_o)
+    # empty grid -> no samples
+    ri, ts, te = F.occgrid_march(o.cuda(), d.cuda(), torch.zeros_like(binaries).cuda(), aabb.tolist(), 0.05)
+    assert ri.numel() == 0
+
+
+def test_adam_vs_oracle(F):
+    torch.manual_seed(9)
+    n = 100003
+    p, g = torch.randn(n), torch.randn(n) * 1e-3
+    g[::7] = 0.0
+    m, v = torch.zeros(n), torch.zeros(n)
+    pc, mc, vc = p.cuda(), m.cuda(), v.cuda()
+    pt = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=1e-2, eps=1e-15)
+    for step in range(1, 4):
+        O.adam_step(p, g * step, m, v, step, 1e-2)
+        F.adam_step(pc, (g * step).cuda(), mc, vc, step, 1e-2)
+        pt.grad = (g * step).clone()
+        opt.step()
+    assert_close(p, pt.detach(), 1e-6, "oracle adam vs torch.optim.Adam")
+    assert_close(pc, p, 1e-5)
+    assert_close(mc, m, 1e-5)
+    assert_close(vc, v, 1e-5)

@@ -229,9 +229,10 @@ int b2n_occgrid_fill(const float* origins, const float* directions, const float*
 
 /* ---- optimiser step either side of the path: torch.optim.Adam semantics ---------------
  * p,g,m,v flat fp32 [n]; step is the 1-based step count; grads are multiplied by grad_scale first
- * (1/world_size after a sum-allreduce, or 1/loss_scale). */
-int b2n_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr, float beta1,
-                  float beta2, float eps, float grad_scale, void* stream);
+ * (1/world_size after a sum-allreduce, or 1/loss_scale).  Hyper-parameters are doubles: 1-beta and the bias
+ * corrections are formed in double, as torch does with its Python floats. */
+int b2n_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, double lr, double beta1,
+                  double beta2, double eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

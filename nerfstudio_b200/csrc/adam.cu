@@ -34,17 +34,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-extern "C" int b2n_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, float lr,
-                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
+extern "C" int b2n_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, double lr,
+                             double beta1, double beta2, double eps, float grad_scale, void* stream) {
   if (n == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(p && g && m && v, "null pointer");
   B2N_REQUIRE(step >= 1, "step is 1-based");
   B2N_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
   if (n == 0) return B2N_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   const int grid = (int)min(div_up(n / 4 + 1, 256), (int64_t)b2n_sm_count() * 8);
-  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, (float)(1.0 - (double)beta1),
-                                                      (float)(1.0 - (double)beta2),
-                                                      (float)(1.0 / sqrt(bc2)), eps, grad_scale);
+  adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(lr / bc1), (float)beta1, (float)beta2,
+                                                      (float)(1.0 - beta1), (float)(1.0 - beta2),
+                                                      (float)(1.0 / sqrt(bc2)), (float)eps, grad_scale);
   B2N_LAUNCH_CHECK();
 }

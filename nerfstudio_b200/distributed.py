@@ -1,0 +1,45 @@
+"""Ray-batch data parallelism: every rank renders its own rays; ONE collective per step averages the flat
+gradient buffer (replaces DDP's bucketed allreduce + `find_unused_parameters` graph walk of the reference:
+nerfstudio/pipelines/base_pipeline.py:279-282, scripts/train.py:139-157).
+
+The sum-allreduce runs through torch.distributed (NCCL over NVLink/NVSwitch on a B200 box; gloo in CPU tests);
+the 1/world_size scaling is folded into the fused Adam kernel's `grad_scale`, so no extra pass over the buffer."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str = "nccl") -> tuple:
+    """(rank, local_rank, world_size) from torchrun's environment; initialises the process group when W > 1."""
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world
+
+
+class FlatGradAllReduce:
+    """callable(flat_grad) -> grad_scale.  Sums the flat gradient over ranks in place, returns 1/world_size."""
+
+    def __init__(self, group=None) -> None:
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def __call__(self, flat_grad: torch.Tensor) -> float:
+        if self.world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+        return 1.0 / self.world
+
+
+def broadcast_parameters(flat_params: torch.Tensor, src: int = 0, group=None) -> None:
+    """Make every replica start from rank `src`'s weights (what DDP's constructor does)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(flat_params, src=src, group=group)

@@ -27,6 +27,39 @@ def _c(t: Tensor) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------
+# optional per-kernel timing (CUDA events on the launching stream) for bench.py's roofline line
+# ----------------------------------------------------------------------------------------
+PROFILE_KERNELS = False
+KERNEL_TIMES: dict = {}
+
+
+class _Timed:
+    def __init__(self, key: str, algorithmic_bytes: int):
+        self.key, self.bytes = key, algorithmic_bytes
+
+    def __enter__(self):
+        if PROFILE_KERNELS:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE_KERNELS:
+            self.e1.record()
+            KERNEL_TIMES.setdefault(self.key, {"bytes": self.bytes, "events": []})["events"].append((self.e0, self.e1))
+
+
+def kernel_time_summary() -> dict:
+    """key -> {launches, ms_total, ms_avg, bytes_per_launch}; call after torch.cuda.synchronize()."""
+    out = {}
+    for k, v in KERNEL_TIMES.items():
+        ms = [a.elapsed_time(b) for a, b in v["events"]]
+        if ms:
+            out[k] = {"launches": len(ms), "ms_total": sum(ms), "ms_avg": sum(ms) / len(ms), "bytes_per_launch": v["bytes"]}
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # hash grid
 # ----------------------------------------------------------------------------------------
 class GridSpec:
@@ -75,7 +108,9 @@ def hashgrid_forward(x: Tensor, table: Tensor, grid: GridSpec, want_indices: boo
     n = x.shape[0]
     y = torch.empty(n, grid.out_dim, device=x.device, dtype=torch.float32)
     idx = torch.empty(n, grid.n_levels, 8, device=x.device, dtype=torch.int64) if want_indices else None
-    call("b2n_hashgrid_fwd", C.byref(grid.c), ptr(x), ptr(table), n, ptr(y), ptr(idx, torch.int64), stream())
+    # algorithmic bytes: 8 corners x F floats per (point, level)  
+    with _Timed(f"hashgrid_fwd[N={n},L={grid.n_levels},F={grid.n_features}]", n * grid.n_levels * 8 * grid.n_features * 4):
+        call("b2n_hashgrid_fwd", C.byref(grid.c), ptr(x), ptr(table), n, ptr(y), ptr(idx, torch.int64), stream())
     return (y, idx) if want_indices else y
 
 
@@ -85,7 +120,10 @@ def hashgrid_backward(x: Tensor, table: Tensor, dy: Tensor, grid: GridSpec, dtab
     if dtable is None:
         dtable = torch.zeros_like(table)
     dx = torch.empty_like(x) if want_dx else None
-    call("b2n_hashgrid_bwd", C.byref(grid.c), ptr(x), ptr(table), ptr(dy), x.shape[0], ptr(dtable), ptr(dx), stream())
+    n = x.shape[0]
+    # scatter-add counted as read + write of every touched row
+    with _Timed(f"hashgrid_bwd[N={n},L={grid.n_levels},F={grid.n_features}]", 2 * n * grid.n_levels * 8 * grid.n_features * 4):
+        call("b2n_hashgrid_bwd", C.byref(grid.c), ptr(x), ptr(table), ptr(dy), n, ptr(dtable), ptr(dx), stream())
     return dtable, dx
 
 

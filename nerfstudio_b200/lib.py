@@ -77,7 +77,7 @@ _SIGNATURES = {
     "b2n_packed_accumulate_bwd": [_P, _P, _I32, _P, _P, _I64, _P, _P, _P],
     "b2n_occgrid_count": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P],
     "b2n_occgrid_fill": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P, _P, _P, _P],
-    "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _F, _P],
+    "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P],
 }
 _RET = {"b2n_version": C.c_char_p, "b2n_last_error": C.c_char_p}
 
@@ -120,7 +120,12 @@ def check(code: int, what: str) -> None:
     raise RuntimeError(f"{what}: CUDA error {code}: {msg}")
 
 
+LAUNCHES = 0  # kernel-launching C-ABI calls made by this process (bench.py reports it as gpu_launches)
+
+
 def call(name: str, *args) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     check(getattr(load(), name)(*args), name)
 
 

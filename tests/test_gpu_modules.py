@@ -1,0 +1,344 @@
+"""GPU parity of the drop-in modules (reference-interface mirrors) against golden vectors from the reference."""
+import pytest
+import torch
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda")
+
+
+def cu(t):
+    return t.cuda()
+
+
+class FakeRand:
+    """Replays recorded random draws in the order the samplers ask for them."""
+
+    def __init__(self, draws):
+        self.draws, self._rand = list(draws), torch.rand
+
+    def __enter__(self):
+        def rand(*size, **kw):
+            t = self.draws.pop(0)
+            shape = tuple(size[0]) if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else tuple(size)
+            assert tuple(t.shape) == shape, (t.shape, shape)
+            return t.to(kw.get("device", "cpu"))
+
+        torch.rand = rand
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand = self._rand
+
+
+def test_density_field_module(cuda, golden):
+    from nerfstudio_b200.field_components.spatial_distortions import SceneContraction
+    from nerfstudio_b200.fields.density_fields import HashMLPDensityField
+
+    g = golden("density_field")
+    for nm, con in (("contract", True), ("aabb", False)):
+        f = HashMLPDensityField(g["aabb"], num_layers=2, hidden_dim=16, num_levels=5, max_res=128, base_res=16,
+                                log2_hashmap_size=12, average_init_density=0.01,
+                                spatial_distortion=SceneContraction(order=float("inf")) if con else None,
+                                implementation="torch")
+        assert torch.equal(f.encoding.scalings, g[f"{nm}_scalings"])
+        sd = {"encoding.hash_table": g[f"{nm}_table"], "mlp_base.0.hash_table": g[f"{nm}_table"]}
+        for i in range(2):
+            sd[f"mlp_base.1.layers.{i}.weight"], sd[f"mlp_base.1.layers.{i}.bias"] = g[f"{nm}_w{i}"], g[f"{nm}_b{i}"]
+        f.load_state_dict(sd, strict=False)
+        f = f.cuda()
+        dens = f.density_fn(cu(g[f"{nm}_pos"]))
+        assert_close(dens, g[f"{nm}_density"], REL, nm)
+        params = [f.encoding.hash_table] + [p for l in f.mlp_base[1].layers for p in (l.weight, l.bias)]
+        grads = torch.autograd.grad(dens, params, cu(g[f"{nm}_dy"]))
+        assert_close(grads[0], g[f"{nm}_dtable"], REL, nm + " dtable")
+        for i in range(2):
+            assert_close(grads[1 + 2 * i], g[f"{nm}_dw{i}"], REL, f"{nm} dw{i}")
+            assert_close(grads[2 + 2 * i], g[f"{nm}_db{i}"], REL, f"{nm} db{i}")
+
+
+def _bundle(o, d, cams, near=0.05, far=1000.0):
+    from nerfstudio_b200.cameras.rays import RayBundle
+
+    R = o.shape[0]
+    return RayBundle(origins=o.cuda(), directions=d.cuda(), pixel_area=torch.full((R, 1), 1e-6).cuda(),
+                     camera_indices=cams.cuda(), nears=torch.full((R, 1), near).cuda(), fars=torch.full((R, 1), far).cuda())
+
+
+def test_nerfacto_field_module(cuda, golden):
+    from nerfstudio_b200.field_components.field_heads import FieldHeadNames
+    from nerfstudio_b200.field_components.spatial_distortions import SceneContraction
+    from nerfstudio_b200.fields.nerfacto_field import NerfactoField
+
+    g = golden("nerfacto_field")
+    for nm, con, training in (("train", True, True), ("eval_avg", True, False), ("aabb", False, True)):
+        f = NerfactoField(g["aabb"], num_images=8, num_levels=6, base_res=16, max_res=256, log2_hashmap_size=12,
+                          spatial_distortion=SceneContraction(order=float("inf")) if con else None,
+                          average_init_density=0.01, use_average_appearance_embedding=(nm == "eval_avg"),
+                          implementation="torch")
+        sd = {"mlp_base.model.0.hash_table": g[f"{nm}_table"], "embedding_appearance.embedding.weight": g[f"{nm}_emb"]}
+        for i in range(2):
+            sd[f"mlp_base.model.1.layers.{i}.weight"], sd[f"mlp_base.model.1.layers.{i}.bias"] = g[f"{nm}_wb{i}"], g[f"{nm}_bb{i}"]
+        for i in range(3):
+            sd[f"mlp_head.layers.{i}.weight"], sd[f"mlp_head.layers.{i}.bias"] = g[f"{nm}_wh{i}"], g[f"{nm}_bh{i}"]
+        missing = f.load_state_dict(sd, strict=False)
+        assert not missing.unexpected_keys
+        f = f.cuda().train(training)
+        rb = _bundle(g[f"{nm}_origins"], g[f"{nm}_directions"], g[f"{nm}_cams"])
+        rs = rb.samples_from_bins(cu(g[f"{nm}_ebins"]), None, None)
+        fo = f(rs)
+        dens, rgb = fo[FieldHeadNames.DENSITY], fo[FieldHeadNames.RGB]
+        assert_close(dens, g[f"{nm}_density"], REL, nm + " density")
+        assert_close(rgb, g[f"{nm}_rgb"], REL, nm + " rgb")
+        named = {"table": f.mlp_base.model[0].hash_table}
+        for i, l in enumerate(f.mlp_base.model[1].layers):
+            named[f"wb{i}"], named[f"bb{i}"] = l.weight, l.bias
+        for i, l in enumerate(f.mlp_head.layers):
+            named[f"wh{i}"], named[f"bh{i}"] = l.weight, l.bias
+        if training:
+            named["emb"] = f.embedding_appearance.embedding.weight
+        grads = torch.autograd.grad([dens, rgb], list(named.values()), [cu(g[f"{nm}_d_density"]), cu(g[f"{nm}_d_rgb"])])
+        for k, gr in zip(named, grads):
+            assert_close(gr, g[f"{nm}_g_{k}"], REL, f"{nm} g_{k}")
+
+
+def _load_pipeline(model, g):
+    sd = {}
+    for j in range(2):
+        sd[f"proposal_networks.{j}.encoding.hash_table"] = g[f"p{j}_table"]
+        sd[f"proposal_networks.{j}.mlp_base.0.hash_table"] = g[f"p{j}_table"]
+        for i in range(2):
+            sd[f"proposal_networks.{j}.mlp_base.1.layers.{i}.weight"] = g[f"p{j}_w{i}"]
+            sd[f"proposal_networks.{j}.mlp_base.1.layers.{i}.bias"] = g[f"p{j}_b{i}"]
+    sd["field.mlp_base.model.0.hash_table"] = g["f_table"]
+    sd["field.embedding_appearance.embedding.weight"] = g["f_emb"]
+    for i in range(2):
+        sd[f"field.mlp_base.model.1.layers.{i}.weight"], sd[f"field.mlp_base.model.1.layers.{i}.bias"] = g[f"f_wb{i}"], g[f"f_bb{i}"]
+    for i in range(3):
+        sd[f"field.mlp_head.layers.{i}.weight"], sd[f"field.mlp_head.layers.{i}.bias"] = g[f"f_wh{i}"], g[f"f_bh{i}"]
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+
+
+def _named_params(model):
+    named = {}
+    for j, p in enumerate(model.proposal_networks):
+        named[f"p{j}_table"] = p.encoding.hash_table
+        for i, l in enumerate(p.mlp_base[1].layers):
+            named[f"p{j}_w{i}"], named[f"p{j}_b{i}"] = l.weight, l.bias
+    f = model.field
+    named["f_table"], named["f_emb"] = f.mlp_base.model[0].hash_table, f.embedding_appearance.embedding.weight
+    for i, l in enumerate(f.mlp_base.model[1].layers):
+        named[f"f_wb{i}"], named[f"f_bb{i}"] = l.weight, l.bias
+    for i, l in enumerate(f.mlp_head.layers):
+        named[f"f_wh{i}"], named[f"f_bh{i}"] = l.weight, l.bias
+    return named
+
+
+def _pipeline_model(g):
+    from nerfstudio_b200.nerfacto import NerfactoModel, NerfactoModelConfig
+
+    cfg = NerfactoModelConfig(
+        num_levels=8, max_res=512, log2_hashmap_size=13, num_proposal_samples_per_ray=(32, 20),
+        num_nerf_samples_per_ray=12, average_init_density=0.01, implementation="torch",
+        use_average_appearance_embedding=False,
+        proposal_net_args_list=[
+            {"hidden_dim": 16, "log2_hashmap_size": 12, "num_levels": 5, "max_res": 128, "use_linear": False},
+            {"hidden_dim": 16, "log2_hashmap_size": 12, "num_levels": 5, "max_res": 256, "use_linear": False}])
+    model = NerfactoModel(cfg, g["aabb"], num_train_data=8)
+    _load_pipeline(model, g)
+    return model.cuda()
+
+
+def test_full_nerfacto_pipeline_train_and_eval(cuda, golden):
+    """The whole hot path (sampler loop, fields, weights, renderers, losses, gradients) vs the reference's own
+    composition of its modules on identical rays / weights / random draws."""
+    g = golden("nerfacto_pipeline")
+    model = _pipeline_model(g)
+    for mode in ("train", "eval"):
+        training = mode == "train"
+        model.train(training)
+        model.proposal_sampler.set_anneal(0.7 if training else 1.0)
+        model.proposal_sampler._step = 0
+        rb = _bundle(g["origins"], g["directions"], g[f"{mode}_cams"])
+        draws = [g["train_rand0"], g["train_rand1"], g["train_rand2"]] if training else []
+        with FakeRand(draws):
+            out = model.get_outputs(rb)
+        if training:
+            for i in range(3):
+                rs = out["ray_samples_list"][i]
+                assert_close(rs.spacing_bins, g[f"{mode}_sbins{i}"], REL, f"sbins{i}")
+                assert_close(rs.euclidean_bins, g[f"{mode}_ebins{i}"], REL, f"ebins{i}")
+                assert_close(out["weights_list"][i], g[f"{mode}_w{i}"], REL, f"w{i}")
+        assert_close(out["rgb"], g[f"{mode}_rgb"], REL, mode + " rgb")
+        assert_close(out["accumulation"], g[f"{mode}_acc"], REL, mode + " acc")
+        assert_close(out["expected_depth"], g[f"{mode}_exp_depth"], REL, mode + " expected depth")
+        # median depth picks a sample; a 1-ulp difference in cumulative weight can move it by one sample
+        same = (out["depth"].cpu() == g[f"{mode}_depth"]).float().mean().item()
+        assert same >= 0.97, f"median depth agrees on {same:.3f} of rays"
+        if training:
+            batch = {"image": cu(g["gt"])}
+            metrics = model.get_metrics_dict(out, batch)
+            losses = model.get_loss_dict(out, batch, metrics)
+            assert_close(losses["rgb_loss"], g["loss_rgb"], REL)
+            assert_close(losses["interlevel_loss"], g["loss_interlevel"], REL)
+            assert_close(losses["distortion_loss"], g["loss_distortion"], REL)
+            loss = sum(losses.values())
+            assert_close(loss, g["loss"], REL)
+            named = _named_params(model)
+            grads = torch.autograd.grad(loss, list(named.values()))
+            for k, gr in zip(named, grads):
+                assert_close(gr, g["g_" + k], 2e-4 if "table" in k else REL, "g_" + k)
+
+
+def test_trainer_step_matches_torch_adam(cuda, golden):
+    """One Trainer.train_iteration == the same forward/backward followed by torch.optim.Adam on a deep copy."""
+    import copy
+
+    from nerfstudio_b200.nerfacto import Trainer
+
+    g = golden("nerfacto_pipeline")
+    model = _pipeline_model(g).train()
+    ref = copy.deepcopy(model)
+    rb = _bundle(g["origins"], g["directions"], g["train_cams"])
+    batch = {"image": cu(g["gt"])}
+    draws = [g["train_rand0"], g["train_rand1"], g["train_rand2"]]
+    tr = Trainer(model)
+    with FakeRand(list(draws)):
+        stats = tr.train_iteration(rb, batch)
+    opt = torch.optim.Adam([p for p in ref.parameters()], lr=1e-2, eps=1e-15)
+    ref.before_train_iteration(0)
+    with FakeRand(list(draws)):
+        out = ref(_bundle(g["origins"], g["directions"], g["train_cams"]))
+    m = ref.get_metrics_dict(out, batch)
+    loss = sum(ref.get_loss_dict(out, batch, m).values())
+    loss.backward()
+    opt.step()
+    assert_close(stats["loss"], loss.detach(), 1e-5)
+    for (k, a), (_, b) in zip(model.state_dict().items(), ref.state_dict().items()):
+        if a.dtype.is_floating_point:
+            assert_close(a, b, 1e-4, k)
+
+
+def test_state_dict_keys_match_reference_layout(cuda, golden):
+    """Checkpoint compatibility: key names and shapes of the torch-path modules."""
+    g = golden("nerfacto_pipeline")
+    model = _pipeline_model(g)
+    keys = set(model.state_dict().keys())
+    for k in ("field.aabb", "field.max_res", "field.num_levels", "field.log2_hashmap_size",
+              "field.embedding_appearance.embedding.weight", "field.mlp_base.model.0.hash_table",
+              "field.mlp_base.model.1.layers.0.weight", "field.mlp_base.model.1.layers.1.bias",
+              "field.mlp_head.layers.2.weight", "proposal_networks.0.encoding.hash_table",
+              "proposal_networks.0.mlp_base.0.hash_table", "proposal_networks.1.mlp_base.1.layers.1.weight"):
+        assert k in keys, k
+    pn = model.proposal_networks[0]
+    assert pn.encoding.hash_table is pn.mlp_base[0].hash_table  # one shared Parameter under two keys
+
+
+def test_tcnn_shim_modules(cuda):
+    """implementation="tcnn" routes through the tinycudann-compatible shim: flat params, tcnn grid semantics."""
+    from oracle import nerf_oracle as O
+    from nerfstudio_b200.field_components.encodings import HashEncoding, SHEncoding
+    from nerfstudio_b200.field_components.mlp import MLP, MLPWithHashEncoding
+
+    enc = HashEncoding(num_levels=8, min_res=16, max_res=512, log2_hashmap_size=12, implementation="tcnn").cuda()
+    assert enc.tcnn_encoding is not None and enc.tcnn_encoding.params.dim() == 1
+    meta, rows = O.tcnn_grid_meta(8, 16, float(enc.growth_factor), 12)
+    assert enc.tcnn_encoding.params.numel() == rows * 2
+    x = torch.rand(300, 3)
+    y = enc(x.cuda())
+    assert_close(y, O.tcnn_hash_encode(x, enc.tcnn_encoding.params.detach().cpu().view(rows, 2), meta), REL)
+    mlp = MLP(in_dim=16, num_layers=3, layer_width=64, out_dim=4, implementation="tcnn").cuda()
+    assert [n for n, _ in mlp.named_parameters()] == ["tcnn_encoding.params"]
+    p = mlp.tcnn_encoding.params.detach().cpu()
+    ws = [p[:64 * 16].view(64, 16), p[64 * 16: 64 * 16 + 64 * 64].view(64, 64), p[64 * 16 + 64 * 64:].view(4, 64)]
+    xi = torch.randn(200, 16)
+    assert_close(mlp(xi.cuda()), O.mlp_forward(xi, ws, [None] * 3), 2e-5)
+    fused = MLPWithHashEncoding(num_levels=4, max_res=128, log2_hashmap_size=10, num_layers=2, layer_width=32, out_dim=8,
+                                implementation="tcnn").cuda()
+    out = fused(torch.rand(64, 3).cuda())
+    assert out.shape == (64, 8)
+    out.sum().backward()
+    assert fused.model.params.grad is not None and torch.isfinite(fused.model.params.grad).all()
+    sh = SHEncoding(levels=4, implementation="tcnn").cuda()
+    d = torch.nn.functional.normalize(torch.randn(50, 3), dim=-1)
+    ref = O.sh_components(4, d) * torch.tensor([1, -1] * 8, dtype=torch.float32)
+    assert_close(sh(((d + 1) / 2).cuda()), ref, 2e-5)
+
+
+def test_vanilla_nerf_field_module(cuda, golden):
+    from nerfstudio_b200.field_components.encodings import NeRFEncoding
+    from nerfstudio_b200.field_components.field_heads import FieldHeadNames
+    from nerfstudio_b200.fields.vanilla_nerf_field import NeRFField
+
+    g = golden("vanilla_field")
+    pe = NeRFEncoding(in_dim=3, num_frequencies=10, min_freq_exp=0.0, max_freq_exp=8.0, include_input=True)
+    de = NeRFEncoding(in_dim=3, num_frequencies=4, min_freq_exp=0.0, max_freq_exp=4.0, include_input=True)
+    f = NeRFField(position_encoding=pe, direction_encoding=de, base_mlp_num_layers=8, base_mlp_layer_width=64,
+                  head_mlp_num_layers=2, head_mlp_layer_width=32)
+    sd = {}
+    for i in range(8):
+        sd[f"mlp_base.layers.{i}.weight"], sd[f"mlp_base.layers.{i}.bias"] = g[f"wb{i}"], g[f"bb{i}"]
+    for i in range(2):
+        sd[f"mlp_head.layers.{i}.weight"], sd[f"mlp_head.layers.{i}.bias"] = g[f"wh{i}"], g[f"bh{i}"]
+    sd["field_output_density.net.weight"], sd["field_output_density.net.bias"] = g["w_sigma"], g["b_sigma"]
+    sd["field_heads.0.net.weight"], sd["field_heads.0.net.bias"] = g["w_rgb"], g["b_rgb"]
+    f.load_state_dict(sd)
+    f = f.cuda()
+    R = g["origins"].shape[0]
+    rb = _bundle(g["origins"], g["directions"], torch.zeros(R, 1, dtype=torch.long), 2.0, 6.0)
+    rs = rb.samples_from_bins(cu(g["ebins"]), None, None)
+    fo = f(rs)
+    assert_close(fo[FieldHeadNames.DENSITY], g["density"], REL)
+    assert_close(fo[FieldHeadNames.RGB], g["rgb"], REL)
+
+
+def test_instant_ngp_packed_path(cuda):
+    """VolumetricSampler + nerfacc-shim OccGridEstimator + packed renderers, as NGPModel.get_outputs wires them
+    (models/instant_ngp.py:173-218): counts/indices vs the oracle march, weights/colour vs the oracle packed ops."""
+    from oracle import nerf_oracle as O
+    from nerfstudio_b200.cameras.rays import RayBundle
+    from nerfstudio_b200.model_components.ray_samplers import VolumetricSampler
+    from nerfstudio_b200.model_components.renderers import AccumulationRenderer, DepthRenderer, RGBRenderer
+    from nerfstudio_b200.shims import nerfacc
+
+    torch.manual_seed(3)
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1])
+    grid = nerfacc.OccGridEstimator(roi_aabb=aabb, resolution=16, levels=2).cuda()
+    binaries = torch.rand(2, 16, 16, 16) > 0.5
+    grid.binaries = binaries.cuda()
+    R = 64
+    o = torch.randn(R, 3) * 1.5
+    d = torch.nn.functional.normalize(-o + 0.2 * torch.randn(R, 3), dim=-1)
+    rb = RayBundle(origins=o.cuda(), directions=d.cuda(), pixel_area=torch.ones(R, 1).cuda(),
+                   camera_indices=torch.zeros(R, 1, dtype=torch.long).cuda())
+    sampler = VolumetricSampler(occupancy_grid=grid, density_fn=None).eval()
+    rs, ri = sampler(rb, render_step_size=0.05, near_plane=0.0, far_plane=None, alpha_thre=0.0, cone_angle=0.0)
+    ri_o, ts_o, te_o = O.occgrid_march(o, d, binaries, aabb, 0.05, 0.0, 1e10, 0.0, None)
+    assert torch.equal(ri.cpu(), ri_o) and torch.equal(rs.frustums.starts[:, 0].cpu(), ts_o)
+    M = ri.numel()
+    sig = torch.rand(M) * 20
+    rgb = torch.rand(M, 3)
+    info = nerfacc.pack_info(ri, R)
+    assert torch.equal(info.cpu(), O.pack_info(ri_o, R))
+    w = nerfacc.render_weight_from_density(rs.frustums.starts[..., 0], rs.frustums.ends[..., 0], sig.cuda(), packed_info=info)[0]
+    wo, _, _ = O.packed_weights(ts_o, te_o, sig, ri_o, R)
+    assert_close(w, wo, REL)
+    ren = RGBRenderer(background_color="random").train()
+    comp = ren(rgb=rgb.cuda(), weights=w[..., None], ray_indices=ri, num_rays=R)
+    assert_close(comp, O.accumulate_along_rays(wo, rgb, ri_o, R), REL)
+    acc = AccumulationRenderer()(weights=w[..., None], ray_indices=ri, num_rays=R)
+    assert_close(acc, O.accumulate_along_rays(wo, None, ri_o, R), REL)
+    dep = DepthRenderer("expected")(weights=w[..., None], ray_samples=rs, ray_indices=ri, num_rays=R)
+    steps = ((ts_o + te_o) / 2)[:, None]
+    ref = O.accumulate_along_rays(wo, steps, ri_o, R) / (O.accumulate_along_rays(wo, None, ri_o, R) + 1e-10)
+    assert_close(dep, torch.clip(ref, steps.min(), steps.max()), REL)

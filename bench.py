@@ -191,7 +191,16 @@ def run_b200(args) -> None:
     model = NerfactoModel(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_train_data=NUM_IMAGES).to(dev)
     if args.force_proposal_update:
         model.proposal_sampler.update_sched = lambda step: -1  # proposal networks trained on every step
-    trainer = Trainer(model, allreduce=D.FlatGradAllReduce() if world > 1 else None)
+    allreduce = D.FlatGradAllReduce() if world > 1 else None
+    if args.engine == "autograd":
+        trainer = Trainer(model, allreduce=allreduce)
+        engine = None
+    else:
+        from nerfstudio_b200.engine import NerfactoStep
+
+        engine = NerfactoStep(model, RAYS_PER_GPU, allreduce=allreduce, use_graph=(args.engine == "graph"),
+                              always_update_proposals=args.force_proposal_update)
+        trainer = engine
     D.broadcast_parameters(trainer.optim.flat)
     n_params = trainer.optim.flat.numel()
 
@@ -206,13 +215,19 @@ def run_b200(args) -> None:
 
     def step_resident(i):
         rays, gt = resident[i % n_batches]
+        if engine is not None:
+            engine.set_batch(rays["origins"], rays["directions"], rays["camera_indices"], gt)  # device -> device
+            return engine.step()
         return trainer.train_iteration(bundle_from(rays), {"image": gt})
 
     def step_e2e(i):
-        rays, gt = host[i % n_batches]
+        rays, gt = host[i % n_batches]  # pinned host memory -> device inside the timed region
+        if engine is not None:
+            engine.set_batch(rays["origins"], rays["directions"], rays["camera_indices"], gt)
+            return float(engine.step()[3].item())  # device -> host read of the step's loss
         d_rays = {k: v.to(dev, non_blocking=True) for k, v in rays.items()}
         stats = trainer.train_iteration(bundle_from(d_rays), {"image": gt.to(dev, non_blocking=True)})
-        return float(stats["loss"].item())  # device -> host read of the step's result
+        return float(stats["loss"].item())
 
     def barrier():
         if world > 1:
@@ -239,13 +254,35 @@ def run_b200(args) -> None:
         step_resident(i)
     lib.LAUNCHES = 0
     F.KERNEL_TIMES.clear()
-    F.PROFILE_KERNELS = True
+    F.PROFILE_KERNELS = engine is None
     ms, clocks = timed(step_resident, args.steps, ClockSampler(local))
     F.PROFILE_KERNELS = False
     launches = lib.LAUNCHES
     torch.cuda.synchronize()
-    kt = F.kernel_time_summary()
     value = world * RAYS_PER_GPU * args.steps / (ms * 1e-3)
+    kt = F.kernel_time_summary()
+    if engine is not None:
+        # per-kernel durations: the same launch sequence run eagerly with CUDA events around every C-ABI call
+        # (a CUDA graph has no per-node events); `launches` = our kernel launches replayed per graph x steps
+        was_graph, engine.use_graph = engine.use_graph, False
+        lib.LAUNCHES, lib.PROFILE = 0, None
+        step_resident(0)
+        launches = lib.LAUNCHES * args.steps
+        lib.PROFILE = {}
+        n_prof = 5
+        for i in range(n_prof):
+            step_resident(i)
+        torch.cuda.synchronize()
+        prof, lib.PROFILE = lib.profile_summary(), None
+        engine.use_graph = was_graph
+        S = engine.S
+        hb = {f"b2n_hashgrid_fwd[n={RAYS_PER_GPU * S[i]}]": RAYS_PER_GPU * S[i] * L * 8 * 2 * 4 for i, L in ((0, 5), (1, 5), (2, 16))}
+        hb.update({f"b2n_hashgrid_bwd[n={RAYS_PER_GPU * S[i]}]": 2 * RAYS_PER_GPU * S[i] * L * 8 * 2 * 4 for i, L in ((0, 5), (1, 5), (2, 16))})
+        kt = {k: {"launches": c, "ms_total": t, "ms_avg": t / c, "bytes_per_launch": hb[k]} for k, (c, t) in prof.items() if k in hb}
+        kernel_table = {k: round(t / n_prof, 4) for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+        ms_prof = sum(t for _, t in prof.values()) / n_prof
+    else:
+        kernel_table, ms_prof, n_prof = None, ms / args.steps, args.steps
 
     for i in range(3):
         step_e2e(i)
@@ -263,10 +300,11 @@ def run_b200(args) -> None:
         name, st = dom
         ach = st["bytes_per_launch"] / (st["ms_avg"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "launches_per_step": st["launches"] / args.steps,
-                    "ms_avg": st["ms_avg"], "share_of_step": st["ms_total"] / ms,
+                    "traffic": None, "peak_source": peak_src, "launches_per_step": st["launches"] / n_prof,
+                    "ms_avg": st["ms_avg"], "share_of_step": st["ms_avg"] * st["launches"] / n_prof / ms_prof,
                     "all_hash_kernels": {k: {"ms_avg": v["ms_avg"], "GBps": v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9,
-                                             "launches_per_step": v["launches"] / args.steps} for k, v in kt.items()}}
+                                             "launches_per_step": v["launches"] / n_prof} for k, v in kt.items()},
+                    "kernel_ms_per_step": kernel_table}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rps, sec, cores = time_cpu(512, 3, 1)
@@ -278,7 +316,7 @@ def run_b200(args) -> None:
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch_rays": world * RAYS_PER_GPU,
                    "parallelism": f"ray-batch data parallel x{world}, one flat-gradient allreduce/step" if world > 1 else "single GPU",
-                   "precision": "fp32 tables, fp32 SIMT MLPs (1e-4 parity mode)", "optimizer": "fused Adam over one flat buffer",
+                   "precision": "fp32 tables, fp32 SIMT MLPs (1e-4 parity mode)", "optimizer": "fused Adam over one flat buffer", "engine": args.engine,
                    "proposal_update": "every step" if args.force_proposal_update else "reference schedule",
                    "l2": f"per-step working set {4 * 4 * n_params / 1e6:.0f} MB (params+grads+Adam moments) > 126 MB L2",
                    "params": n_params},
@@ -297,6 +335,9 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="graph", choices=["graph", "eager", "autograd"],
+                    help="graph: CUDA-graph replay of the hand-written step (default); eager: same launches without a "
+                         "graph; autograd: the drop-in modules under torch.autograd")
     ap.add_argument("--reference-schedule", dest="force_proposal_update", action="store_false",
                     help="use nerfacto's proposal-update schedule instead of training the proposal nets every step")
     args = ap.parse_args()

@@ -151,11 +151,13 @@ int b2n_spaced_sample(const float* nears, const float* fars, const float* lin, c
                       float* sbins, float* ebins, void* stream);
 /* PDFSampler.generate_ray_samples (ray_samplers.py:276-372), include_original=False.
  * bins [R,S+1] spacing-domain edges, weights [R,S] (annealing w**anneal fused in: pass anneal=1 for none),
- * u_base [nb] = linspace(0,1-1/nb,nb) from the host, jitter NULL | [R] | [R,nb].
+ * u_base [nb] = linspace(0,1-1/nb,nb) from the host, jitter NULL | [R] | [R,nb].  anneal_dev (optional) points
+ * to the exponent in device memory and overrides `anneal` (lets a captured CUDA graph see a changing schedule).
  * Outputs new_sbins [R,nb], new_ebins [R,nb]; optional cdf_out [R,S+1], inds_out int64 [R,nb]. */
 int b2n_pdf_sample(const float* bins, const float* weights, const float* u_base, const float* jitter,
                    int32_t jitter_per_bin, const float* nears, const float* fars, int64_t n_rays, int32_t n_in,
-                   int32_t n_out, float anneal, float histogram_padding, float eps, int32_t spacing,
+                   int32_t n_out, float anneal, const float* anneal_dev, float histogram_padding, float eps,
+                   int32_t spacing,
                    float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out, void* stream);
 
 /* ---- a21-a23: transmittance weights and compositing ---------------------------------------------------
@@ -233,6 +235,27 @@ int b2n_occgrid_fill(const float* origins, const float* directions, const float*
  * corrections are formed in double, as torch does with its Python floats. */
 int b2n_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step, double lr, double beta1,
                   double beta2, double eps, float grad_scale, void* stream);
+
+/* same update with the per-step scalars in device memory: hyper3 = {lr/(1-beta1^t), 1/sqrt(1-beta2^t), grad_scale}
+ * (CUDA-graph friendly: the host refreshes 12 bytes before each replay). */
+int b2n_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper3, double beta1,
+                      double beta2, double eps, void* stream);
+
+/* ---- glue of the captured nerfacto step (fields/nerfacto_field.py:234-310; models/nerfacto.py:363-391) -----
+ * head_in [R*S, n_sh+geo+n_emb] = [ sh[ray] | base_out[n, 1:1+geo] | emb row ]; emb_mode 0 = zeros,
+ * 1 = emb[cam[ray]] (training), 2 = emb[0] (a pre-averaged row, eval). */
+int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
+                       const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
+                       int32_t n_samples, float* out, void* stream);
+/* d_base_out [R*S, base_w] (col 0 = d_dens_pre, cols 1..geo from d_in) is overwritten; d_emb rows are ACCUMULATED. */
+int b2n_head_input_bwd(const float* d_in, int32_t n_sh, int32_t geo, int32_t n_emb, const float* d_dens_pre,
+                       const int64_t* cam, int64_t n_rays, int32_t n_samples, float* d_base_out, int32_t base_w,
+                       float* d_emb, void* stream);
+/* loss_out[0] += mean((pred-gt)^2); d_pred = gscale * 2 (pred-gt)/n  (either output may be NULL) */
+int b2n_mse_fwd_bwd(const float* pred, const float* gt, int64_t n, float gscale, float* loss_out, float* d_pred,
+                    void* stream);
+/* out[0] += scale * sum(rows[0..n)) */
+int b2n_sum_rows(const float* rows, int64_t n, float scale, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,3 +48,48 @@ extern "C" int b2n_adam_step(float* p, const float* g, float* m, float* v, int64
                                                       (float)(1.0 / sqrt(bc2)), (float)eps, grad_scale);
   B2N_LAUNCH_CHECK();
 }
+
+
+// Graph-capturable variant: the per-step scalars live in device memory (hyper[0] = lr / (1 - beta1^t),
+// hyper[1] = 1 / sqrt(1 - beta2^t), hyper[2] = grad scale), refreshed by a 12-byte copy before each replay.
+__global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                       float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                       const float* __restrict__ hyper, float b1, float b2, float omb1,
+                                                       float omb2, float eps) {
+  const float lr_c = __ldg(hyper), inv_sqrt_bc2 = __ldg(hyper + 1), gscale = __ldg(hyper + 2);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] * gscale;
+      ma[k] = b1 * ma[k] + omb1 * gk;
+      va[k] = b2 * va[k] + omb2 * gk * gk;
+      pa[k] -= lr_c * ma[k] / (sqrtf(va[k]) * inv_sqrt_bc2 + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gk = g[i] * gscale;
+    const float mk = b1 * m[i] + omb1 * gk, vk = b2 * v[i] + omb2 * gk * gk;
+    m[i] = mk, v[i] = vk;
+    p[i] -= lr_c * mk / (sqrtf(vk) * inv_sqrt_bc2 + eps);
+  }
+}
+
+extern "C" int b2n_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper3,
+                                 double beta1, double beta2, double eps, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(p && g && m && v && hyper3, "null pointer");
+  B2N_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "buffers must be 16-byte aligned");
+  const int grid = (int)min(div_up(n / 4 + 1, 256), (int64_t)b2n_sm_count() * 8);
+  adam_dev_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper3, (float)beta1, (float)beta2,
+                                                          (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps);
+  B2N_LAUNCH_CHECK();
+}

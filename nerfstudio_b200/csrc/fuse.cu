@@ -1,0 +1,123 @@
+// Glue kernels of the graph-captured nerfacto step: colour-head input assembly (SH ‖ geo features ‖ appearance
+// embedding) forward/backward, and the rgb MSE loss with its gradient.  They replace the torch.cat / expand /
+// embedding / index_put chain of nerfstudio/fields/nerfacto_field.py:234-310 and the MSELoss of
+// models/nerfacto.py:372 so that one optimisation step is a fixed sequence of our own launches.
+#include "common.cuh"
+
+// head_in[n, :] = [ sh[ray(n), 0:n_sh] | base_out[n, 1:1+geo] | emb[cam[ray(n)], 0:n_emb] ]
+__global__ void head_input_fwd_kernel(const float* __restrict__ sh, int n_sh, const float* __restrict__ base_out,
+                                      int base_w, int geo, const float* __restrict__ emb,
+                                      const int64_t* __restrict__ cam, int n_emb, int emb_mode, int64_t n_rays, int S,
+                                      float* __restrict__ out) {
+  const int width = n_sh + geo + n_emb;
+  const int64_t total = n_rays * S * width;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / width;
+    const int c = (int)(idx - n * width);
+    const int64_t r = n / S;
+    float v;
+    if (c < n_sh) v = __ldg(sh + r * n_sh + c);
+    else if (c < n_sh + geo) v = __ldg(base_out + n * base_w + 1 + (c - n_sh));
+    else if (emb_mode == 1) v = __ldg(emb + __ldg(cam + r) * n_emb + (c - n_sh - geo));   // training: per-image row
+    else if (emb_mode == 2) v = __ldg(emb + (c - n_sh - geo));                             // eval: one (mean) row
+    else v = 0.f;                                                                          // eval: zeros
+    out[idx] = v;
+  }
+}
+
+// d_base_out[n, 0] = d_density_pre[n]; d_base_out[n, 1+g] = d_in[n, n_sh+g]; d_emb[cam[ray]] += sum_s d_in[n, n_sh+geo+e]
+__global__ void head_input_bwd_kernel(const float* __restrict__ d_in, int n_sh, int geo, int n_emb,
+                                      const float* __restrict__ d_dens_pre, const int64_t* __restrict__ cam,
+                                      int64_t n_rays, int S, float* __restrict__ d_base_out, int base_w,
+                                      float* __restrict__ d_emb) {
+  const int width = n_sh + geo + n_emb;
+  // part 1: one thread per (sample, base column)
+  const int64_t total1 = n_rays * S * base_w;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = gtid; idx < total1; idx += gsz) {
+    const int64_t n = idx / base_w;
+    const int c = (int)(idx - n * base_w);
+    float v = 0.f;
+    if (c == 0) v = d_dens_pre ? __ldg(d_dens_pre + n) : 0.f;
+    else if (c <= geo) v = __ldg(d_in + n * width + n_sh + c - 1);
+    d_base_out[idx] = v;
+  }
+  // part 2: one thread per (ray, embedding column): reduce over the ray's samples, one atomic per ray
+  if (d_emb != nullptr && n_emb > 0) {
+    const int64_t total2 = n_rays * n_emb;
+    for (int64_t idx = gtid; idx < total2; idx += gsz) {
+      const int64_t r = idx / n_emb;
+      const int e = (int)(idx - r * n_emb);
+      float s = 0.f;
+      const float* p = d_in + (r * S) * width + n_sh + geo + e;
+      for (int i = 0; i < S; ++i) s += __ldg(p + (int64_t)i * width);
+      atomicAdd(d_emb + __ldg(cam + r) * n_emb + e, s);
+    }
+  }
+}
+
+extern "C" int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
+                                  const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
+                                  int32_t n_samples, float* out, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(sh && base_out && out, "null pointer");
+  B2N_REQUIRE(n_emb == 0 || emb_mode == 0 || emb, "embedding table missing");
+  B2N_REQUIRE(emb_mode != 1 || cam, "camera indices missing");
+  B2N_REQUIRE(1 + geo <= base_w, "geo features exceed base width");
+  const int64_t total = n_rays * n_samples * (n_sh + geo + n_emb);
+  const unsigned grid = (unsigned)min(div_up(total, 256), (int64_t)b2n_sm_count() * 32);
+  head_input_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sh, n_sh, base_out, base_w, geo, emb, cam, n_emb,
+                                                                emb_mode, n_rays, n_samples, out);
+  B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_head_input_bwd(const float* d_in, int32_t n_sh, int32_t geo, int32_t n_emb, const float* d_dens_pre,
+                                  const int64_t* cam, int64_t n_rays, int32_t n_samples, float* d_base_out,
+                                  int32_t base_w, float* d_emb, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(d_in && d_base_out, "null pointer");
+  B2N_REQUIRE(d_emb == nullptr || cam, "camera indices missing");
+  const int64_t total = n_rays * n_samples * base_w;
+  const unsigned grid = (unsigned)min(div_up(total, 256), (int64_t)b2n_sm_count() * 32);
+  head_input_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, n_sh, geo, n_emb, d_dens_pre, cam, n_rays,
+                                                                n_samples, d_base_out, base_w, d_emb);
+  B2N_LAUNCH_CHECK();
+}
+
+// loss_out[0] += mean((pred - gt)^2) * 1 ; d_pred = gscale * 2 (pred - gt) / n     (nn.MSELoss, models/nerfacto.py:372)
+__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int64_t n, float gscale,
+                           float* __restrict__ loss_out, float* __restrict__ d_pred) {
+  float s = 0.f;
+  const float inv = 1.f / (float)n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = __ldg(pred + i) - __ldg(gt + i);
+    s = fmaf(d, d, s);
+    if (d_pred) d_pred[i] = gscale * 2.f * d * inv;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0 && loss_out) atomicAdd(loss_out, s * inv);
+}
+
+extern "C" int b2n_mse_fwd_bwd(const float* pred, const float* gt, int64_t n, float gscale, float* loss_out,
+                               float* d_pred, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(pred && gt, "null pointer");
+  const unsigned grid = (unsigned)min(div_up(n, 256), (int64_t)b2n_sm_count() * 4);
+  mse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pred, gt, n, gscale, loss_out, d_pred);
+  B2N_LAUNCH_CHECK();
+}
+
+// out[0] += scale * sum(rows[0..n))      (loss bookkeeping inside the captured step)
+__global__ void sum_rows_kernel(const float* __restrict__ rows, int64_t n, float scale, float* __restrict__ out) {
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += __ldg(rows + i);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s * scale);
+}
+
+extern "C" int b2n_sum_rows(const float* rows, int64_t n, float scale, float* out, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(rows && out, "null pointer");
+  sum_rows_kernel<<<(unsigned)min(div_up(n, 256), (int64_t)64), 256, 0, (cudaStream_t)stream>>>(rows, n, scale, out);
+  B2N_LAUNCH_CHECK();
+}

@@ -69,7 +69,8 @@ extern "C" int b2n_spaced_sample(const float* nears, const float* fars, const fl
 __global__ void __launch_bounds__(PDF_WARPS * 32) pdf_sample_kernel(
     const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ u_base,
     const float* __restrict__ jitter, int jitter_per_bin, const float* __restrict__ nears,
-    const float* __restrict__ fars, int64_t n_rays, int S, int n_out, float anneal, float pad_hist, float eps,
+    const float* __restrict__ fars, int64_t n_rays, int S, int n_out, float anneal_host,
+    const float* __restrict__ anneal_dev, float pad_hist, float eps,
     int spacing, float* __restrict__ new_sbins, float* __restrict__ new_ebins, float* __restrict__ cdf_out,
     int64_t* __restrict__ inds_out) {
   extern __shared__ float sm[];
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) pdf_sample_kernel(
   float* cdf = sm + (size_t)warp * 2 * (S + 1);
   float* eb = cdf + (S + 1);
   const int nb = n_out;  // number of new bin edges = num_samples + 1
+  const float anneal = anneal_dev ? __ldg(anneal_dev) : anneal_host;
   const float* wrow = weights + r * S;
   const float* brow = bins + r * (S + 1);
   const int chunk = (S + 31) / 32;
@@ -144,8 +146,8 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) pdf_sample_kernel(
 
 extern "C" int b2n_pdf_sample(const float* bins, const float* weights, const float* u_base, const float* jitter,
                               int32_t jitter_per_bin, const float* nears, const float* fars, int64_t n_rays,
-                              int32_t n_in, int32_t n_out, float anneal, float histogram_padding, float eps,
-                              int32_t spacing, float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out,
+                              int32_t n_in, int32_t n_out, float anneal, const float* anneal_dev,
+                              float histogram_padding, float eps, int32_t spacing, float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out,
                               void* stream) {
   if (n_rays == 0) return B2N_OK;  // empty batch: nothing to validate or launch
   B2N_REQUIRE(bins && weights && u_base && nears && fars && new_sbins, "null pointer");
@@ -154,7 +156,8 @@ extern "C" int b2n_pdf_sample(const float* bins, const float* weights, const flo
   const size_t smem = sizeof(float) * PDF_WARPS * 2 * (n_in + 1);
   if (smem > 48 * 1024) cudaFuncSetAttribute(pdf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   pdf_sample_kernel<<<(unsigned)div_up(n_rays, PDF_WARPS), PDF_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      bins, weights, u_base, jitter, jitter_per_bin, nears, fars, n_rays, n_in, n_out, anneal, histogram_padding, eps,
+      bins, weights, u_base, jitter, jitter_per_bin, nears, fars, n_rays, n_in, n_out, anneal, anneal_dev,
+      histogram_padding, eps,
       spacing, new_sbins, new_ebins, cdf_out, inds_out);
   B2N_LAUNCH_CHECK();
 }

@@ -1,0 +1,310 @@
+"""Graph-captured nerfacto training step: the B200-native runtime of the hot path.
+
+`Trainer` in nerfacto.py drives the drop-in modules through torch.autograd (dozens of small framework ops and
+Python dispatch per step).  `NerfactoStep` runs the SAME arithmetic — the step of
+nerfstudio/engine/trainer.py:486-530 over models/nerfacto.py:298-391 — as a fixed sequence of our own kernel
+launches on preallocated buffers (forward, losses, hand-written backward, fused Adam), captures that sequence in
+a CUDA graph and replays it: one graph launch per optimisation step, no tracing compiler, no autograd tape, no
+allocation.  Parameters stay the model's own nn.Parameters (views into one flat buffer), so state_dicts and
+evaluation through the module API are unaffected.
+
+Per-step scalars that change (Adam bias corrections, proposal-weight anneal exponent, lr schedule) live in a tiny
+device buffer refreshed with one 16-byte copy before each replay.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, Dict, Optional
+
+import torch
+from torch import Tensor
+
+from . import functional as F
+from . import lib
+from .lib import B2nMlpGrad, call, ptr, stream
+from .nerfacto import NerfactoModel
+from .optim import FlatAdam
+
+NULL = C.c_void_p(0)
+
+
+def _off(t: Tensor, elems: int) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr() + 4 * elems)
+
+
+class _Net:
+    """One hash-grid + MLP network bound to its parameters / gradient views."""
+
+    def __init__(self, encoding, mlp):
+        self.grid = encoding.grid
+        self.table = encoding.hash_table
+        self.spec = mlp.spec
+        self.weights = [l.weight for l in mlp.layers]
+        self.biases = [l.bias for l in mlp.layers]
+
+    def structs(self):
+        m = self.spec.struct(self.weights, self.biases)
+        g = B2nMlpGrad()
+        for i, (w, b) in enumerate(zip(self.weights, self.biases)):
+            g.dw[i], g.db[i] = ptr(w.grad).value, ptr(b.grad).value
+        return m, g
+
+
+class NerfactoStep:
+    def __init__(self, model: NerfactoModel, n_rays: int, lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-15,
+                 lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
+                 always_update_proposals: bool = False) -> None:
+        cfg = model.config
+        if cfg.implementation != "torch":
+            raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
+        if cfg.use_same_proposal_network or cfg.num_proposal_iterations != 2:
+            raise NotImplementedError("captured step: two separate proposal networks (the nerfacto default)")
+        self.model, self.cfg, self.R = model, cfg, n_rays
+        self.optim = FlatAdam(model, lr=lr, betas=betas, eps=eps, lr_schedule=lr_schedule)
+        self.allreduce, self.use_graph = allreduce, use_graph
+        self.always_update = always_update_proposals
+        dev = self.optim.flat.device
+        self.dev = dev
+        self.S = list(cfg.num_proposal_samples_per_ray) + [cfg.num_nerf_samples_per_ray]
+        self.props = [_Net(p.encoding, p.mlp_base[1]) for p in model.proposal_networks]
+        fld = model.field
+        self.base = _Net(fld.mlp_base.model[0], fld.mlp_base.model[1])
+        self.head_spec = fld.mlp_head.spec
+        self.head_w = [l.weight for l in fld.mlp_head.layers]
+        self.head_b = [l.bias for l in fld.mlp_head.layers]
+        self.emb = fld.embedding_appearance.embedding.weight if fld.embedding_appearance is not None else None
+        self.geo, self.n_emb = fld.geo_feat_dim, (fld.appearance_embedding_dim if self.emb is not None else 0)
+        self.contraction = fld.spatial_distortion is not None
+        self.aabb = fld.aabb.flatten().tolist()
+        self.avg = float(cfg.average_init_density)
+        self.spacing = "uniform" if cfg.proposal_initial_sampler == "uniform" else "piecewise"
+        self.bg = cfg.background_color
+        R = n_rays
+        f32 = dict(device=dev, dtype=torch.float32)
+        # ---- static inputs
+        self.origins, self.directions = torch.zeros(R, 3, **f32), torch.zeros(R, 3, **f32)
+        self.cams = torch.zeros(R, device=dev, dtype=torch.int64)
+        self.gt = torch.zeros(R, 3, **f32)
+        self.nears = torch.full((R,), float(cfg.near_plane), **f32)
+        self.fars = torch.full((R,), float(cfg.far_plane), **f32)
+        self.hyper = torch.zeros(4, **f32)  # lr/bc1, 1/sqrt(bc2), grad_scale, anneal
+        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.lin0 = torch.linspace(0.0, 1.0, self.S[0] + 1).to(dev)
+        self.u_base = [torch.linspace(0.0, 1.0 - 1.0 / (s + 1), s + 1).to(dev) for s in self.S[1:]]
+        # ---- per-level buffers
+        self.sb, self.eb, self.x, self.sel, self.enc, self.h, self.hid, self.dens, self.w = [], [], [], [], [], [], [], [], []
+        self.d_w, self.d_dens, self.d_h, self.d_enc = [], [], [], []
+        for lvl, S in enumerate(self.S):
+            N = R * S
+            net = self.props[lvl] if lvl < 2 else self.base
+            width_out = net.spec.out_dims[-1]
+            self.sb.append(torch.zeros(R, S + 1, **f32)), self.eb.append(torch.zeros(R, S + 1, **f32))
+            self.x.append(torch.zeros(N, 3, **f32)), self.sel.append(torch.zeros(N, device=dev, dtype=torch.uint8))
+            self.enc.append(torch.zeros(N, net.grid.out_dim, **f32))
+            self.h.append(torch.zeros(N, width_out, **f32))
+            self.hid.append(torch.zeros(max(net.spec.hidden_width, 1) * N, **f32))
+            self.dens.append(torch.zeros(R, S, **f32)), self.w.append(torch.zeros(R, S, **f32))
+            self.d_w.append(torch.zeros(R, S, **f32)), self.d_dens.append(torch.zeros(R, S, **f32))
+            self.d_h.append(torch.zeros(N, width_out, **f32)), self.d_enc.append(torch.zeros(N, net.grid.out_dim, **f32))
+        N2 = R * self.S[2]
+        self.n_sh = 16
+        self.head_in_w = self.n_sh + self.geo + self.n_emb
+        self.sh = torch.zeros(R, self.n_sh, **f32)
+        self.hin, self.d_hin = torch.zeros(N2, self.head_in_w, **f32), torch.zeros(N2, self.head_in_w, **f32)
+        self.hid_head = torch.zeros(self.head_spec.hidden_width * N2, **f32)
+        self.rgb, self.d_rgb = torch.zeros(N2, 3, **f32), torch.zeros(N2, 3, **f32)
+        self.d_hpre = torch.zeros(N2, **f32)
+        self.d_w_dist = torch.zeros(R, self.S[2], **f32)
+        self.rgb_out, self.d_rgb_out = torch.zeros(R, 3, **f32), torch.zeros(R, 3, **f32)
+        self.acc, self.depth_exp, self.depth_med = torch.zeros(R, **f32), torch.zeros(R, **f32), torch.zeros(R, **f32)
+        self.rows = [torch.zeros(R, **f32) for _ in range(3)]
+        self.losses = torch.zeros(4, **f32)  # rgb, interlevel, distortion, total
+        self.jitter = [torch.zeros(R, 1, **f32) for _ in range(3)]
+        self.step_count = 0
+        self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
+        self._steps_since_update = 0
+        self.fixed_jitter = None
+        if self.bg not in ("last_sample", "white", "black"):
+            raise NotImplementedError("captured step: background_color must be last_sample / white / black")
+
+    # ------------------------------------------------------------------------------------------------
+    def _density_net_fwd(self, lvl: int, net: _Net) -> None:
+        R, S = self.R, self.S[lvl]
+        N = R * S
+        eb = self.eb[lvl]
+        box = lib.host_floats(self.aabb)
+        call("b2n_positions_fwd", ptr(self.origins), ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S,
+             int(self.contraction), C.cast(box, C.c_void_p), ptr(self.x[lvl]), ptr(self.sel[lvl], torch.uint8), stream())
+        call("b2n_hashgrid_fwd", C.byref(net.grid.c), ptr(self.x[lvl]), ptr(net.table), N, ptr(self.enc[lvl]), NULL, stream())
+        m, _ = net.structs()
+        call("b2n_mlp_fwd", C.byref(m), ptr(self.enc[lvl]), N, ptr(self.h[lvl]), ptr(self.hid[lvl]), stream())
+        call("b2n_density_act_fwd", ptr(self.h[lvl]), self.h[lvl].shape[1], ptr(self.sel[lvl], torch.uint8), N, self.avg,
+             ptr(self.dens[lvl]), stream())
+        call("b2n_weights_fwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), R, S, ptr(self.w[lvl]), stream())
+
+    def _density_net_bwd(self, lvl: int, net: _Net, d_hpre: Optional[Tensor]) -> None:
+        """weights -> density -> pre-activation -> MLP -> encoding -> table, for a proposal level."""
+        R, S = self.R, self.S[lvl]
+        N = R * S
+        eb = self.eb[lvl]
+        call("b2n_weights_bwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), ptr(self.d_w[lvl]), R, S,
+             ptr(self.d_dens[lvl]), stream())
+        call("b2n_density_act_bwd", ptr(self.h[lvl]), 1, ptr(self.sel[lvl], torch.uint8), ptr(self.d_dens[lvl]), N, self.avg,
+             ptr(self.d_h[lvl]), 1, stream())
+        m, g = net.structs()
+        call("b2n_mlp_bwd", C.byref(m), C.byref(g), ptr(self.enc[lvl]), ptr(self.h[lvl]), ptr(self.hid[lvl]),
+             ptr(self.d_h[lvl]), N, ptr(self.d_enc[lvl]), stream())
+        call("b2n_hashgrid_bwd", C.byref(net.grid.c), ptr(self.x[lvl]), ptr(net.table), ptr(self.d_enc[lvl]), N,
+             ptr(net.table.grad), NULL, stream())
+
+    def _body(self, update_props: bool) -> None:
+        R, S0, S1, S2 = self.R, *self.S
+        cfg = self.cfg
+        st = stream
+        self.optim.flat_grad.zero_()
+        self.losses.zero_()
+        if self.fixed_jitter is None:
+            for j in self.jitter:
+                j.copy_(torch.rand(R, 1, device=self.dev))
+        else:  # tests: replay recorded stratified draws
+            for j, src in zip(self.jitter, self.fixed_jitter):
+                j.copy_(src)
+        # ---------------- forward: proposal sampling
+        call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), ptr(self.jitter[0]), 0, R, S0,
+             lib.SPACING[self.spacing], ptr(self.sb[0]), ptr(self.eb[0]), st())
+        for lvl in (0, 1):
+            self._density_net_fwd(lvl, self.props[lvl])
+            call("b2n_pdf_sample", ptr(self.sb[lvl]), ptr(self.w[lvl]), ptr(self.u_base[lvl]), ptr(self.jitter[lvl + 1]), 0,
+                 ptr(self.nears), ptr(self.fars), R, self.S[lvl], self.S[lvl + 1] + 1, 1.0, _off(self.hyper, 3), 0.01, 1e-5,
+                 lib.SPACING[self.spacing], ptr(self.sb[lvl + 1]), ptr(self.eb[lvl + 1]), NULL, NULL, st())
+        # ---------------- forward: main field
+        N2 = R * S2
+        eb2 = self.eb[2]
+        box = lib.host_floats(self.aabb)
+        call("b2n_positions_fwd", ptr(self.origins), ptr(self.directions), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2,
+             int(self.contraction), C.cast(box, C.c_void_p), ptr(self.x[2]), ptr(self.sel[2], torch.uint8), st())
+        call("b2n_hashgrid_fwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), N2, ptr(self.enc[2]), NULL, st())
+        mb, gb = self.base.structs()
+        call("b2n_mlp_fwd", C.byref(mb), ptr(self.enc[2]), N2, ptr(self.h[2]), ptr(self.hid[2]), st())
+        bw = self.h[2].shape[1]
+        call("b2n_density_act_fwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), N2, self.avg, ptr(self.dens[2]), st())
+        call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), st())
+        call("b2n_head_input_fwd", ptr(self.sh), self.n_sh, ptr(self.h[2]), bw, self.geo, ptr(self.emb), ptr(self.cams, torch.int64),
+             self.n_emb, 1 if self.emb is not None else 0, R, S2, ptr(self.hin), st())
+        mh = self.head_spec.struct(self.head_w, self.head_b)
+        gh = B2nMlpGrad()
+        for i, (w, b) in enumerate(zip(self.head_w, self.head_b)):
+            gh.dw[i], gh.db[i] = ptr(w.grad).value, ptr(b.grad).value
+        call("b2n_mlp_fwd", C.byref(mh), ptr(self.hin), N2, ptr(self.rgb), ptr(self.hid_head), st())
+        call("b2n_weights_fwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), R, S2, ptr(self.w[2]), st())
+        bg_mode, bg_ptr, _keep = F._bg_args(self.bg)
+        call("b2n_composite_fwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2, bg_mode, bg_ptr, 0,
+             ptr(self.rgb_out), ptr(self.acc), ptr(self.depth_exp), ptr(self.depth_med), NULL, st())
+        # ---------------- losses (+ their gradients)
+        call("b2n_mse_fwd_bwd", ptr(self.rgb_out), ptr(self.gt), 3 * R, 1.0, ptr(self.losses), ptr(self.d_rgb_out), st())
+        il = cfg.interlevel_loss_mult / float(R * S2)
+        for lvl in (0, 1):
+            call("b2n_interlevel_fwd_bwd", ptr(self.sb[2]), ptr(self.w[2]), ptr(self.sb[lvl]), ptr(self.w[lvl]), R, S2,
+                 self.S[lvl], il, ptr(self.rows[lvl]), ptr(self.d_w[lvl]) if update_props else NULL, st())
+            call("b2n_sum_rows", ptr(self.rows[lvl]), R, il, _off(self.losses, 1), st())
+        dm = cfg.distortion_loss_mult / float(R)
+        call("b2n_distortion_fwd_bwd", ptr(self.sb[2]), ptr(self.w[2]), R, S2, dm, ptr(self.rows[2]), ptr(self.d_w_dist), st())
+        call("b2n_sum_rows", ptr(self.rows[2]), R, dm, _off(self.losses, 2), st())
+        # ---------------- backward: main field
+        call("b2n_composite_bwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.d_rgb_out), NULL, NULL,
+             R, S2, bg_mode, bg_ptr, ptr(self.d_rgb), ptr(self.d_w[2]), st())
+        self.d_w[2].add_(self.d_w_dist)
+        call("b2n_weights_bwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), ptr(self.d_w[2]), R, S2, ptr(self.d_dens[2]), st())
+        call("b2n_density_act_bwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), ptr(self.d_dens[2]), N2, self.avg,
+             ptr(self.d_hpre), 1, st())
+        call("b2n_mlp_bwd", C.byref(mh), C.byref(gh), ptr(self.hin), ptr(self.rgb), ptr(self.hid_head), ptr(self.d_rgb), N2,
+             ptr(self.d_hin), st())
+        call("b2n_head_input_bwd", ptr(self.d_hin), self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre), ptr(self.cams, torch.int64),
+             R, S2, ptr(self.d_h[2]), bw, ptr(self.emb.grad) if self.emb is not None else NULL, st())
+        call("b2n_mlp_bwd", C.byref(mb), C.byref(gb), ptr(self.enc[2]), ptr(self.h[2]), ptr(self.hid[2]), ptr(self.d_h[2]), N2,
+             ptr(self.d_enc[2]), st())
+        call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
+             ptr(self.base.table.grad), NULL, st())
+        # ---------------- backward: proposal networks (only the interlevel loss reaches them)
+        if update_props:
+            for lvl in (0, 1):
+                self._density_net_bwd(lvl, self.props[lvl], None)
+        self.losses[3:4].copy_(self.losses[0:3].sum(0, keepdim=True))
+
+    def _adam(self) -> None:
+        o = self.optim
+        call("b2n_adam_step_dev", ptr(o.flat), ptr(o.flat_grad), ptr(o.exp_avg), ptr(o.exp_avg_sq), o.flat.numel(),
+             ptr(self.hyper), float(o.betas[0]), float(o.betas[1]), float(o.eps), stream())
+
+    # ------------------------------------------------------------------------------------------------
+    def set_batch(self, origins: Tensor, directions: Tensor, camera_indices: Tensor, gt_rgb: Tensor) -> None:
+        """Copy one ray batch into the static input buffers (H2D when the sources are pinned host tensors)."""
+        self.origins.copy_(origins, non_blocking=True)
+        self.directions.copy_(directions, non_blocking=True)
+        self.cams.copy_(camera_indices.reshape(-1), non_blocking=True)
+        self.gt.copy_(gt_rgb, non_blocking=True)
+
+    def _anneal(self, step: int) -> float:
+        c = self.cfg
+        if not c.use_proposal_weight_anneal:
+            return 1.0
+        frac = min(max(step / c.proposal_weights_anneal_max_num_iters, 0.0), 1.0)
+        b = c.proposal_weights_anneal_slope
+        return b * frac / ((b - 1) * frac + 1)
+
+    def _update_due(self, step: int) -> bool:
+        if self.always_update:
+            return True
+        return self._steps_since_update > self.model.proposal_sampler.update_sched(step) or step < 10
+
+    def step(self) -> Tensor:
+        """One optimisation step on the batch currently in the static buffers.  Returns the loss vector
+        [rgb, interlevel, distortion, total] (device tensor, valid after the stream is synchronised)."""
+        t = self.step_count
+        o = self.optim
+        lr = o.lr_schedule(t) if o.lr_schedule is not None else o.lr
+        world = getattr(self.allreduce, "world", 1) if self.allreduce is not None else 1
+        self.hyper_host[0] = lr / (1.0 - o.betas[0] ** (t + 1))
+        self.hyper_host[1] = 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1))
+        self.hyper_host[2] = 1.0 / world
+        self.hyper_host[3] = self._anneal(t)
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        update = self._update_due(t)
+        if not self.use_graph:
+            self._body(update)
+            if self.allreduce is not None:
+                self.allreduce(o.flat_grad)
+            self._adam()
+        else:
+            if update not in self._graphs:
+                self._capture(update)
+            self._graphs[update][0].replay()
+            if self.allreduce is not None and world > 1:
+                self.allreduce(o.flat_grad)
+            self._graphs[update][1].replay()
+        if update:
+            self._steps_since_update = 0
+        self._steps_since_update += 1
+        self.step_count += 1
+        o.steps += 1
+        return self.losses
+
+    def _capture(self, update: bool) -> None:
+        """Warm the kernels up on a side stream (loads modules, sizes smem attributes), then capture."""
+        saved = [t.clone() for t in (self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._body(update)
+            self._adam()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for dst, src in zip((self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq), saved):
+            dst.copy_(src)  # the warm-up pass must not count as an optimisation step
+        g_main, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_main):
+            self._body(update)
+        with torch.cuda.graph(g_adam, pool=g_main.pool()):
+            self._adam()
+        self._graphs[update] = (g_main, g_adam)

@@ -392,7 +392,7 @@ def pdf_sample(sbins: Tensor, weights: Tensor, num_samples: int, jitter: Optiona
     cdf = torch.empty(R, S + 1, device=sb.device, dtype=torch.float32) if want_aux else None
     inds = torch.empty(R, nb, device=sb.device, dtype=torch.int64) if want_aux else None
     call("b2n_pdf_sample", ptr(sb), ptr(w), ptr(u_base), ptr(jitter), per_bin, ptr(n), ptr(f), R, S, nb, float(anneal),
-         float(histogram_padding), float(eps), lib.SPACING[spacing], ptr(new_sb), ptr(new_eb), ptr(cdf),
+         C.c_void_p(0), float(histogram_padding), float(eps), lib.SPACING[spacing], ptr(new_sb), ptr(new_eb), ptr(cdf),
          ptr(inds, torch.int64), stream())
     return (new_sb, new_eb, cdf, inds) if want_aux else (new_sb, new_eb)
 

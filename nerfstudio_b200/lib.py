@@ -61,7 +61,7 @@ _SIGNATURES = {
     "b2n_density_act_fwd": [_P, _I64, _P, _I64, _F, _P, _P],
     "b2n_density_act_bwd": [_P, _I64, _P, _P, _I64, _F, _P, _I64, _P],
     "b2n_spaced_sample": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P, _P],
-    "b2n_pdf_sample": [_P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _I32, _F, _F, _F, _I32, _P, _P, _P, _P, _P],
+    "b2n_pdf_sample": [_P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _I32, _F, _P, _F, _F, _I32, _P, _P, _P, _P, _P],
     "b2n_weights_fwd": [_P, _P, _I64, _P, _I64, _I32, _P, _P],
     "b2n_weights_bwd": [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P],
     "b2n_composite_fwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P],
@@ -77,6 +77,11 @@ _SIGNATURES = {
     "b2n_packed_accumulate_bwd": [_P, _P, _I32, _P, _P, _I64, _P, _P, _P],
     "b2n_occgrid_count": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P],
     "b2n_occgrid_fill": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P, _P, _P, _P],
+    "b2n_adam_step_dev": [_P, _P, _P, _P, _I64, _P, C.c_double, C.c_double, C.c_double, _P],
+    "b2n_head_input_fwd": [_P, _I32, _P, _I32, _I32, _P, _P, _I32, _I32, _I64, _I32, _P, _P],
+    "b2n_head_input_bwd": [_P, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _P],
+    "b2n_mse_fwd_bwd": [_P, _P, _I64, _F, _P, _P, _P],
+    "b2n_sum_rows": [_P, _I64, _F, _P, _P],
     "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P],
 }
 _RET = {"b2n_version": C.c_char_p, "b2n_last_error": C.c_char_p}
@@ -123,10 +128,27 @@ def check(code: int, what: str) -> None:
 LAUNCHES = 0  # kernel-launching C-ABI calls made by this process (bench.py reports it as gpu_launches)
 
 
+PROFILE = None  # set to {} to time every C-ABI launch with CUDA events on the launching stream (eager mode only)
+_N_ARG = {"b2n_hashgrid_fwd": 3, "b2n_hashgrid_bwd": 4, "b2n_mlp_fwd": 2, "b2n_mlp_bwd": 6}
+
+
 def call(name: str, *args) -> None:
     global LAUNCHES
     LAUNCHES += 1
+    if PROFILE is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(load(), name)(*args), name)
+    e1.record()
+    key = f"{name}[n={args[_N_ARG[name]]}]" if name in _N_ARG else name
+    PROFILE.setdefault(key, []).append((e0, e1))
+
+
+def profile_summary() -> dict:
+    """key -> (launches, total ms); call after torch.cuda.synchronize()."""
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROFILE or {}).items()}
 
 
 def stream() -> C.c_void_p:

@@ -199,7 +199,7 @@ def run_b200(args) -> None:
         from nerfstudio_b200.engine import NerfactoStep
 
         engine = NerfactoStep(model, RAYS_PER_GPU, allreduce=allreduce, use_graph=(args.engine == "graph"),
-                              always_update_proposals=args.force_proposal_update)
+                              always_update_proposals=args.force_proposal_update, mlp_backend=args.mlp)
         trainer = engine
     D.broadcast_parameters(trainer.optim.flat)
     n_params = trainer.optim.flat.numel()
@@ -316,7 +316,8 @@ def run_b200(args) -> None:
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch_rays": world * RAYS_PER_GPU,
                    "parallelism": f"ray-batch data parallel x{world}, one flat-gradient allreduce/step" if world > 1 else "single GPU",
-                   "precision": "fp32 tables, fp32 SIMT MLPs (1e-4 parity mode)", "optimizer": "fused Adam over one flat buffer", "engine": args.engine,
+                   "precision": ("fp32 tables; MLPs on tcgen05 tensor cores, 3xTF32 split, fp32 accumulate in TMEM (1e-4 parity mode)"
+                                 if (engine is not None and engine.tc) else "fp32 tables, fp32 SIMT MLPs (1e-4 parity mode)"), "optimizer": "fused Adam over one flat buffer", "engine": args.engine,
                    "proposal_update": "every step" if args.force_proposal_update else "reference schedule",
                    "l2": f"per-step working set {4 * 4 * n_params / 1e6:.0f} MB (params+grads+Adam moments) > 126 MB L2",
                    "params": n_params},
@@ -335,6 +336,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mlp", default="auto", choices=["auto", "tc", "simt"],
+                    help="tiny-MLP kernels of the graph/eager engine: tcgen05 3xTF32 (tc) or fp32 SIMT")
     ap.add_argument("--engine", default="graph", choices=["graph", "eager", "autograd"],
                     help="graph: CUDA-graph replay of the hand-written step (default); eager: same launches without a "
                          "graph; autograd: the drop-in modules under torch.autograd")

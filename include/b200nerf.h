@@ -115,6 +115,18 @@ int b2n_mlp_fwd(const B2nMlp* mlp_host, const float* x, int64_t n, float* y, flo
 int b2n_mlp_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, const float* y,
                 const float* hidden, const float* dy, int64_t n, float* dx, void* stream);
 
+/* Tensor-core variant of the same two calls: tcgen05.mma kind::tf32 with the 3xTF32 split (fp32-level accuracy,
+ * ~1e-6 relative), accumulators in TMEM.  Eligible networks: <= 4 layers, every width <= 64, hidden widths a
+ * multiple of 4, ReLU (or no) hidden activation, none/sigmoid/relu output, no skip connections — i.e. all
+ * nerfacto / instant-ngp networks; otherwise B2N_E_UNSUPPORTED (use the SIMT call).  x / dx rows may be padded
+ * (row strides in floats).  `hidden` here is ROW-major per layer: layer i at hidden + N * sum_{j<i} out_j,
+ * laid out [N][out_i] (fwd and bwd of this variant agree; not interchangeable with the SIMT layout). */
+int b2n_mlp_tc_fwd(const B2nMlp* mlp_host, const float* x, int64_t x_stride, int64_t n, float* y, float* hidden,
+                   void* stream);
+int b2n_mlp_tc_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, int64_t x_stride,
+                   const float* y, const float* hidden, const float* dy, int64_t n, float* dx, int64_t dx_stride,
+                   void* stream);
+
 /* ---- K5/K6: direction / frequency encodings ---------------------------------------------------------
  * SHEncoding (encodings.py:752-799, utils/spherical_harmonics.py:24-81): levels in 1..5, out [N,levels^2].
  * remap01 != 0 applies d <- (d+1)/2 first (fields/base_field.py:136-142 fused in). */
@@ -242,13 +254,13 @@ int b2n_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
                       double beta2, double eps, void* stream);
 
 /* ---- glue of the captured nerfacto step (fields/nerfacto_field.py:234-310; models/nerfacto.py:363-391) -----
- * head_in [R*S, n_sh+geo+n_emb] = [ sh[ray] | base_out[n, 1:1+geo] | emb row ]; emb_mode 0 = zeros,
+ * head_in [R*S, out_stride >= n_sh+geo+n_emb] = [ sh[ray] | base_out[n, 1:1+geo] | emb row ]; emb_mode 0 = zeros,
  * 1 = emb[cam[ray]] (training), 2 = emb[0] (a pre-averaged row, eval). */
 int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
                        const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
-                       int32_t n_samples, float* out, void* stream);
+                       int32_t n_samples, float* out, int32_t out_stride, void* stream);
 /* d_base_out [R*S, base_w] (col 0 = d_dens_pre, cols 1..geo from d_in) is overwritten; d_emb rows are ACCUMULATED. */
-int b2n_head_input_bwd(const float* d_in, int32_t n_sh, int32_t geo, int32_t n_emb, const float* d_dens_pre,
+int b2n_head_input_bwd(const float* d_in, int32_t in_stride, int32_t n_sh, int32_t geo, int32_t n_emb, const float* d_dens_pre,
                        const int64_t* cam, int64_t n_rays, int32_t n_samples, float* d_base_out, int32_t base_w,
                        float* d_emb, void* stream);
 /* loss_out[0] += mean((pred-gt)^2); d_pred = gscale * 2 (pred-gt)/n  (either output may be NULL) */
@@ -256,6 +268,13 @@ int b2n_mse_fwd_bwd(const float* pred, const float* gt, int64_t n, float gscale,
                     void* stream);
 /* out[0] += scale * sum(rows[0..n)) */
 int b2n_sum_rows(const float* rows, int64_t n, float scale, float* out, void* stream);
+
+/* ---- tcgen05 self-test (diagnostic; pins the tensor-core operand/TMEM semantics the MLP kernels rely on) -------
+ * One 128-row tile.  mode 0: D = A[128][k] * B[n][k]^T (K-major x K-major);  mode 1: D = A[128][k] * W[k][n]
+ * (K-major x MN-major);  mode 2: D = A[128][m]^T * B[128][n] (MN-major x MN-major, reduction over the 128 rows).
+ * three_pass: 3xTF32 (hi*hi + lo*hi + hi*lo).  out receives the raw TMEM image [128 lanes][n columns]. */
+int b2n_tc_selftest(int32_t mode, int32_t three_pass, const float* a, int32_t a_rows, int32_t a_cols, const float* b,
+                    int32_t b_rows, int32_t b_cols, int32_t m, int32_t n, int32_t k, float* out128xn, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@
 __global__ void head_input_fwd_kernel(const float* __restrict__ sh, int n_sh, const float* __restrict__ base_out,
                                       int base_w, int geo, const float* __restrict__ emb,
                                       const int64_t* __restrict__ cam, int n_emb, int emb_mode, int64_t n_rays, int S,
-                                      float* __restrict__ out) {
+                                      float* __restrict__ out, int out_stride) {
   const int width = n_sh + geo + n_emb;
   const int64_t total = n_rays * S * width;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -21,16 +21,16 @@ __global__ void head_input_fwd_kernel(const float* __restrict__ sh, int n_sh, co
     else if (emb_mode == 1) v = __ldg(emb + __ldg(cam + r) * n_emb + (c - n_sh - geo));   // training: per-image row
     else if (emb_mode == 2) v = __ldg(emb + (c - n_sh - geo));                             // eval: one (mean) row
     else v = 0.f;                                                                          // eval: zeros
-    out[idx] = v;
+    out[n * out_stride + c] = v;
   }
 }
 
 // d_base_out[n, 0] = d_density_pre[n]; d_base_out[n, 1+g] = d_in[n, n_sh+g]; d_emb[cam[ray]] += sum_s d_in[n, n_sh+geo+e]
-__global__ void head_input_bwd_kernel(const float* __restrict__ d_in, int n_sh, int geo, int n_emb,
+__global__ void head_input_bwd_kernel(const float* __restrict__ d_in, int in_stride, int n_sh, int geo, int n_emb,
                                       const float* __restrict__ d_dens_pre, const int64_t* __restrict__ cam,
                                       int64_t n_rays, int S, float* __restrict__ d_base_out, int base_w,
                                       float* __restrict__ d_emb) {
-  const int width = n_sh + geo + n_emb;
+  const int width = in_stride;
   // part 1: one thread per (sample, base column)
   const int64_t total1 = n_rays * S * base_w;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
@@ -58,28 +58,31 @@ __global__ void head_input_bwd_kernel(const float* __restrict__ d_in, int n_sh, 
 
 extern "C" int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
                                   const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
-                                  int32_t n_samples, float* out, void* stream) {
+                                  int32_t n_samples, float* out, int32_t out_stride, void* stream) {
   if (n_rays == 0) return B2N_OK;
   B2N_REQUIRE(sh && base_out && out, "null pointer");
   B2N_REQUIRE(n_emb == 0 || emb_mode == 0 || emb, "embedding table missing");
   B2N_REQUIRE(emb_mode != 1 || cam, "camera indices missing");
   B2N_REQUIRE(1 + geo <= base_w, "geo features exceed base width");
+  B2N_REQUIRE(out_stride >= n_sh + geo + n_emb, "out_stride too small");
   const int64_t total = n_rays * n_samples * (n_sh + geo + n_emb);
   const unsigned grid = (unsigned)min(div_up(total, 256), (int64_t)b2n_sm_count() * 32);
   head_input_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sh, n_sh, base_out, base_w, geo, emb, cam, n_emb,
-                                                                emb_mode, n_rays, n_samples, out);
+                                                                emb_mode, n_rays, n_samples, out, out_stride);
   B2N_LAUNCH_CHECK();
 }
 
-extern "C" int b2n_head_input_bwd(const float* d_in, int32_t n_sh, int32_t geo, int32_t n_emb, const float* d_dens_pre,
+extern "C" int b2n_head_input_bwd(const float* d_in, int32_t in_stride, int32_t n_sh, int32_t geo, int32_t n_emb,
+                                  const float* d_dens_pre,
                                   const int64_t* cam, int64_t n_rays, int32_t n_samples, float* d_base_out,
                                   int32_t base_w, float* d_emb, void* stream) {
   if (n_rays == 0) return B2N_OK;
   B2N_REQUIRE(d_in && d_base_out, "null pointer");
   B2N_REQUIRE(d_emb == nullptr || cam, "camera indices missing");
+  B2N_REQUIRE(in_stride >= n_sh + geo + n_emb, "in_stride too small");
   const int64_t total = n_rays * n_samples * base_w;
   const unsigned grid = (unsigned)min(div_up(total, 256), (int64_t)b2n_sm_count() * 32);
-  head_input_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, n_sh, geo, n_emb, d_dens_pre, cam, n_rays,
+  head_input_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, in_stride, n_sh, geo, n_emb, d_dens_pre, cam, n_rays,
                                                                 n_samples, d_base_out, base_w, d_emb);
   B2N_LAUNCH_CHECK();
 }

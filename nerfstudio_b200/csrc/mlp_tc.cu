@@ -1,0 +1,480 @@
+// K3 on tensor cores — fused tiny MLP forward/backward with tcgen05.mma (kind::tf32), accumulators in TMEM.
+//
+// Replaces the same reference rows as mlp.cu (nerfstudio/field_components/mlp.py:110-114,160-184) for the networks
+// of the nerfacto hot path (every width <= 64: base 32->64->16, head 63->64->64->3, proposal 10->16->1), keeping
+// fp32-level accuracy: every product is formed as hi*hi + lo*hi + hi*lo with hi = top 19 bits of the fp32 value
+// (exactly a tf32) and lo = a - hi ("3xTF32"), accumulated in fp32 in TMEM — measured 1e-6 relative against fp64,
+// so the 1e-4 parity bar holds.  The tensor pipe is nowhere near its limit on K,N <= 64; what the kernel buys is
+// that the 2.1 ms/step the SIMT kernels spend in FFMA disappears into operand staging.
+//
+// Structure (one persistent CTA of 256 threads per SM; threads t and t+128 own row t&127 of the 128-row tile
+// (== TMEM lane) and split its columns in halves — warps w and w+4 share TMEM quarter w&3):
+//   forward  : x row -> hi/lo -> smem (K-major canonical, float4 stores) -> per layer: thread 0 issues the MMAs,
+//              tcgen05.commit -> mbarrier; everyone tcgen05.ld's their row, bias + activation, saves the hidden
+//              row (row-major) for backward, writes the next layer's operand.
+//   backward : per layer  dA = dZ W      A = dZ tile (K-major), B = W^T copy (K-major)            -> TMEM -> regs
+//                         dW += dZ^T A   operands are the transposed tiles (feature x point), written by scalar
+//                                        conflict-free stores; hi and lo of dZ^T are STACKED along M (rows 0-63 /
+//                                        64-127) so one M=128 MMA yields both partial products; a row of ones
+//                                        appended to A^T makes the same GEMM produce db.  dW/db stay resident in
+//                                        TMEM across all tiles of the CTA and are flushed once with REDs.
+// MN-major tf32 operands would need the SWIZZLE_128B_BASE32B layout (probed: the interleaved layout returns zeros),
+// hence the explicit transposed copies.
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#define TC_MAXL 4
+#define TC_ROWS 128
+#define TC_CS_A 2048u                 // [128][64] K-major tile: column-group stride
+#define TC_TILE_BYTES (16u * TC_CS_A)  // 64 cols
+#define TC_CS_TZ (128u * 16u + 16u)    // stacked dZ^T [128 feature rows][64 points], padded against bank conflicts
+#define TC_CS_TA (80u * 16u + 16u)     // A^T [<=80 rows][64 points]
+#define TC_TZ_BYTES (16u * TC_CS_TZ)
+#define TC_TA_BYTES (16u * TC_CS_TA)
+
+struct TcParams {
+  int n_layers, in_dim, in_pad, hidden_act, out_act;
+  int K[TC_MAXL], N[TC_MAXL];          // padded input / output widths (K % 16 == 0, N % 16 == 0, <= 64)
+  int kr[TC_MAXL], nr[TC_MAXL];        // real widths
+  const float* w[TC_MAXL];
+  const float* b[TC_MAXL];
+  float* dw[TC_MAXL];
+  float* db[TC_MAXL];
+  uint32_t w_off[TC_MAXL];             // byte offset of the layer's hi weight tile in the weight region (lo follows)
+  uint32_t w_bytes[TC_MAXL];           // bytes of one (hi or lo) weight tile
+  uint32_t bias_off[TC_MAXL];          // float offset in the bias region
+  long long hid_off[TC_MAXL];          // feature offset (sum of previous real widths) of the saved activations
+  uint32_t w_total;                    // bytes of the whole weight region
+};
+
+__device__ __forceinline__ float tc_act(int act, float v) {
+  if (act == B2N_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == B2N_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+__device__ __forceinline__ float tc_act_grad(int act, float y) {
+  if (act == B2N_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == B2N_ACT_SIGMOID) return y * (1.f - y);
+  return 1.f;
+}
+
+#define TC_THREADS 256  // 8 warps: warp w and w+4 share TMEM quarter w&3 and split the tile's columns in halves
+#define TC_HALF 32
+
+// write this thread's half row (32 columns starting at c0; zero beyond width_pad) as hi/lo into a K-major tile pair
+__device__ __forceinline__ void store_half_hilo(uint8_t* hi, uint8_t* lo, int r, int c0, const float (&v)[TC_HALF],
+                                                int width_pad) {
+#pragma unroll
+  for (int c = 0; c < TC_HALF; c += 4) {
+    if (c0 + c < width_pad) {
+      float4 h, l;
+      tc::split_tf32(v[c], h.x, l.x), tc::split_tf32(v[c + 1], h.y, l.y);
+      tc::split_tf32(v[c + 2], h.z, l.z), tc::split_tf32(v[c + 3], h.w, l.w);
+      const uint32_t off = tc::canon_off(r, c0 + c, TC_CS_A);
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  }
+}
+
+// this thread's half of its TMEM row: columns [col + c0, col + c0 + 32) ∩ [col, col + width); warp-uniform control flow
+__device__ __forceinline__ void load_half(uint32_t tmem, int quarter, int col, int c0, int width, float (&v)[TC_HALF]) {
+#pragma unroll
+  for (int c = 0; c < TC_HALF; c += 16) {
+    if (c0 + c < width) {
+      float t[16];
+      tc::ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(col + c0 + c), t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[c + i] = t[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[c + i] = 0.f;
+    }
+  }
+}
+
+// this thread's half of a global row (row-major, `real` valid columns), zero padded
+__device__ __forceinline__ void load_global_half(const float* __restrict__ src, bool live, bool vec, int c0, int real,
+                                                 int pad, float (&v)[TC_HALF]) {
+#pragma unroll
+  for (int c = 0; c < TC_HALF; c += 4) {
+    if (c0 + c < pad) {
+      if (live && vec && c0 + c + 4 <= real) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(src + c0 + c));
+        v[c] = q.x, v[c + 1] = q.y, v[c + 2] = q.z, v[c + 3] = q.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[c + i] = (live && c0 + c + i < real) ? __ldg(src + c0 + c + i) : 0.f;
+      }
+    } else {
+      v[c] = v[c + 1] = v[c + 2] = v[c + 3] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_constant__ TcParams p,
+                                                                  const float* __restrict__ x, int64_t x_stride,
+                                                                  int64_t n, float* __restrict__ y,
+                                                                  float* __restrict__ hidden) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* Ah = smem;
+  uint8_t* Al = smem + TC_TILE_BYTES;
+  uint8_t* Wr = smem + 2 * TC_TILE_BYTES;                       // weight region
+  float* bias = reinterpret_cast<float*>(Wr + p.w_total);        // [sum N]
+  const int t = threadIdx.x, warp = t >> 5, quarter = warp & 3;
+  const int r = t & (TC_ROWS - 1), c0 = (t >> 7) * TC_HALF;
+
+  for (int l = 0; l < p.n_layers; ++l) {  // stage W hi/lo as K-major canonical [N rows][K cols]
+    const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
+    uint8_t* wh = Wr + p.w_off[l];
+    uint8_t* wl = wh + p.w_bytes[l];
+    const uint32_t cs = (uint32_t)N * 16u;
+    for (int idx = t; idx < N * K; idx += TC_THREADS) {
+      const int j = idx / K, k = idx - j * K;
+      const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
+      float h, lo;
+      tc::split_tf32(v, h, lo);
+      const uint32_t off = tc::canon_off(j, k, cs);
+      *reinterpret_cast<float*>(wh + off) = h;
+      *reinterpret_cast<float*>(wl + off) = lo;
+    }
+    for (int j = t; j < N; j += TC_THREADS) bias[p.bias_off[l] + j] = (j < nr && p.b[l]) ? __ldg(p.b[l] + j) : 0.f;
+  }
+  if (t == 0) tc::mbar_init(&bar, 1);
+  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  uint32_t phase = 0;
+  const bool xvec = ((x_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+
+  const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * TC_ROWS + r;
+    const bool live = row < n;
+    float v[TC_HALF];
+    load_global_half(x + row * x_stride, live, xvec, c0, p.in_dim, p.in_pad, v);
+    store_half_hilo(Ah, Al, r, c0, v, p.in_pad);
+    for (int l = 0; l < p.n_layers; ++l) {
+      const int N = p.N[l], K = p.K[l];
+      tc::fence_smem_to_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      tc::fence_after_sync();
+      if (t == 0) {
+        const uint32_t idesc = tc::make_idesc_tf32(TC_ROWS, N, false, false);
+        const uint32_t cs = (uint32_t)N * 16u;
+        const uint32_t wh = tc::smem_u32(Wr + p.w_off[l]), wl = wh + p.w_bytes[l];
+        const uint32_t ah = tc::smem_u32(Ah), al = tc::smem_u32(Al);
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a0 = (pass == 1) ? al : ah, b0 = (pass == 2) ? wl : wh;
+          for (int s = 0; s < K / 8; ++s) {
+            tc::mma_tf32(tmem, tc::make_desc(a0 + s * 2 * TC_CS_A, TC_CS_A, 128), tc::make_desc(b0 + s * 2 * cs, cs, 128),
+                         idesc, acc);
+            acc = 1;
+          }
+        }
+        tc::commit(&bar);
+      }
+      tc::mbar_wait(&bar, phase);
+      phase ^= 1;
+      tc::fence_after_sync();
+      load_half(tmem, quarter, 0, c0, N, v);
+      const bool last = (l == p.n_layers - 1);
+      const int act = last ? p.out_act : p.hidden_act;
+      const float* bl = bias + p.bias_off[l];
+      const int nr = p.nr[l];
+#pragma unroll
+      for (int c = 0; c < TC_HALF; ++c) v[c] = (c0 + c < nr) ? tc_act(act, v[c] + bl[c0 + c]) : 0.f;
+      if (!last) {
+        if (hidden != nullptr && live) {
+          float* h = hidden + p.hid_off[l] * n + row * nr;
+#pragma unroll
+          for (int c = 0; c < TC_HALF; c += 4)
+            if (c0 + c < nr) *reinterpret_cast<float4*>(h + c0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+        store_half_hilo(Ah, Al, r, c0, v, N);  // this layer's MMAs have completed: the operand tile is free
+      } else if (live) {
+        float* yr = y + row * nr;
+#pragma unroll
+        for (int c = 0; c < TC_HALF; ++c)
+          if (c0 + c < nr) yr[c0 + c] = v[c];
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();  // all TMEM reads of this tile done before the next tile's first MMA overwrites D
+    tc::fence_after_sync();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<64>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_constant__ TcParams p,
+                                                                  const float* __restrict__ x, int64_t x_stride,
+                                                                  const float* __restrict__ y,
+                                                                  const float* __restrict__ hidden,
+                                                                  const float* __restrict__ dy, int64_t n,
+                                                                  float* __restrict__ dx, int64_t dx_stride) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* Zh = smem;                                   // dZ tile, K-major [128][64]
+  uint8_t* Zl = Zh + TC_TILE_BYTES;
+  uint8_t* TZ = Zl + TC_TILE_BYTES;                     // stacked dZ^T: rows 0-63 hi, 64-127 lo; 64 point columns
+  uint8_t* TAh = TZ + TC_TZ_BYTES;                      // A^T hi (+ ones row)
+  uint8_t* TAl = TAh + TC_TA_BYTES;                     // A^T lo
+  uint8_t* Wr = TAl + TC_TA_BYTES;                      // W^T hi/lo per layer: K-major [K rows][N cols]
+  const int t = threadIdx.x, warp = t >> 5, quarter = warp & 3;
+  const int r = t & (TC_ROWS - 1), c0 = (t >> 7) * TC_HALF;
+  const int L = p.n_layers;
+
+  for (int l = 0; l < L; ++l) {
+    const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
+    uint8_t* wh = Wr + p.w_off[l];
+    uint8_t* wl = wh + p.w_bytes[l];
+    const uint32_t cs = (uint32_t)K * 16u;
+    for (int idx = t; idx < N * K; idx += TC_THREADS) {
+      const int j = idx / K, k = idx - j * K;
+      const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
+      float h, lo;
+      tc::split_tf32(v, h, lo);
+      const uint32_t off = tc::canon_off(k, j, cs);  // transposed: row = input index, col = output index
+      *reinterpret_cast<float*>(wh + off) = h;
+      *reinterpret_cast<float*>(wl + off) = lo;
+    }
+  }
+  if (t == 0) tc::mbar_init(&bar, 1);
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  uint32_t phase = 0;
+  uint32_t dw_started = 0;  // bit l: the layer's dW accumulator has been written once (thread 0 only)
+  const int DW_COL0 = 64, DW_COLS = 80;
+  const bool xvec = ((x_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+
+  const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row = tile * TC_ROWS + r;
+    const bool live = row < n;
+    float dz[TC_HALF], a[TC_HALF];
+    {  // dZ of the last layer = dy * act'(y)   (this thread's column half)
+      const int nr = p.nr[L - 1];
+#pragma unroll
+      for (int c = 0; c < TC_HALF; ++c) {
+        float g = 0.f;
+        if (c0 + c < nr && live) g = __ldg(dy + row * nr + c0 + c) * tc_act_grad(p.out_act, __ldg(y + row * nr + c0 + c));
+        dz[c] = g;
+      }
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const int N = p.N[l], K = p.K[l], kr = p.kr[l];
+      if (l == 0) load_global_half(x + row * x_stride, live, xvec, c0, kr, K, a);
+      else load_global_half(hidden + p.hid_off[l - 1] * n + row * (int64_t)kr, live, (kr & 3) == 0, c0, kr, K, a);
+      const bool need_da = (l > 0) || (dx != nullptr);
+      if (need_da) store_half_hilo(Zh, Zl, r, c0, dz, N);
+      // ---- dW_l += dZ^T A over the two 64-point halves of the tile
+      for (int ph = 0; ph < 2; ++ph) {
+        if ((r >> 6) == ph) {
+          const int pc = r & 63;  // point column inside the half
+#pragma unroll
+          for (int j = 0; j < TC_HALF; ++j) {
+            float h = 0.f, lo = 0.f;
+            if (c0 + j < N) tc::split_tf32(dz[j], h, lo);
+            *reinterpret_cast<float*>(TZ + tc::canon_off(c0 + j, pc, TC_CS_TZ)) = h;
+            *reinterpret_cast<float*>(TZ + tc::canon_off(64 + c0 + j, pc, TC_CS_TZ)) = lo;
+          }
+#pragma unroll
+          for (int k = 0; k < TC_HALF; ++k) {
+            if (c0 + k < K) {
+              float h, lo;
+              tc::split_tf32(a[k], h, lo);
+              *reinterpret_cast<float*>(TAh + tc::canon_off(c0 + k, pc, TC_CS_TA)) = h;
+              *reinterpret_cast<float*>(TAl + tc::canon_off(c0 + k, pc, TC_CS_TA)) = lo;
+            }
+          }
+          if (c0 == 0) {  // ones row (-> bias gradient) and zero padding rows K..K+15
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              *reinterpret_cast<float*>(TAh + tc::canon_off(K + k, pc, TC_CS_TA)) = (k == 0 && live) ? 1.f : 0.f;
+              *reinterpret_cast<float*>(TAl + tc::canon_off(K + k, pc, TC_CS_TA)) = 0.f;
+            }
+          }
+        }
+        tc::fence_smem_to_async();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (t == 0) {
+          const uint32_t idesc = tc::make_idesc_tf32(TC_ROWS, K + 16, false, false);
+          const uint32_t tz = tc::smem_u32(TZ), tah = tc::smem_u32(TAh), tal = tc::smem_u32(TAl);
+          const uint32_t dcol = tmem + (uint32_t)(DW_COL0 + DW_COLS * l);
+          uint32_t acc = (dw_started >> l) & 1u;
+#pragma unroll 1
+          for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t b0 = pass ? tal : tah;
+            for (int s = 0; s < 8; ++s) {
+              tc::mma_tf32(dcol, tc::make_desc(tz + s * 2 * TC_CS_TZ, TC_CS_TZ, 128),
+                           tc::make_desc(b0 + s * 2 * TC_CS_TA, TC_CS_TA, 128), idesc, acc);
+              acc = 1;
+            }
+          }
+          dw_started |= 1u << l;
+          if (ph == 1 && need_da) {  // dA = dZ W : issued right behind, one commit covers both
+            const uint32_t idx = tc::make_idesc_tf32(TC_ROWS, K, false, false);
+            const uint32_t cs = (uint32_t)K * 16u;
+            const uint32_t wh = tc::smem_u32(Wr + p.w_off[l]), wl = wh + p.w_bytes[l];
+            const uint32_t zh = tc::smem_u32(Zh), zl = tc::smem_u32(Zl);
+            uint32_t acc2 = 0;
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t a0 = (pass == 1) ? zl : zh, b0 = (pass == 2) ? wl : wh;
+              for (int s = 0; s < N / 8; ++s) {
+                tc::mma_tf32(tmem, tc::make_desc(a0 + s * 2 * TC_CS_A, TC_CS_A, 128), tc::make_desc(b0 + s * 2 * cs, cs, 128),
+                             idx, acc2);
+                acc2 = 1;
+              }
+            }
+          }
+          tc::commit(&bar);
+        }
+        tc::mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+      }
+      // ---- dA half row -> next dZ (or dx)
+      if (need_da) {
+        float da[TC_HALF];
+        load_half(tmem, quarter, 0, c0, K, da);
+        if (l > 0) {
+#pragma unroll
+          for (int c = 0; c < TC_HALF; ++c) dz[c] = (c0 + c < kr) ? da[c] * tc_act_grad(p.hidden_act, a[c]) : 0.f;
+        } else if (live) {
+          float* dr = dx + row * dx_stride;
+#pragma unroll
+          for (int c = 0; c < TC_HALF; ++c)
+            if (c0 + c < p.in_dim) dr[c0 + c] = da[c];
+        }
+        tc::fence_before_sync();
+        __syncthreads();  // D (columns 0..63) fully read before the next layer's dA MMA overwrites it
+        tc::fence_after_sync();
+      }
+    }
+  }
+  // ---- flush dW / db: lanes 0-63 hold dZ_hi^T [A_hi + A_lo], lanes 64-127 the dZ_lo^T part
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  for (int l = 0; l < L; ++l) {
+    if (p.dw[l] == nullptr && p.db[l] == nullptr) continue;
+    const int K = p.K[l], kr = p.kr[l], nr = p.nr[l];
+    const int j = r & 63;
+    const bool started = blockIdx.x < n_tiles;
+    for (int cc = c0 ? 48 : 0; cc < (c0 ? K + 16 : min(48, K + 16)); cc += 16) {  // warp-uniform column ranges
+      float v[16];
+      tc::ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(DW_COL0 + DW_COLS * l + cc), v);
+      if (!started || j >= nr) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = cc + i;
+        if (k < kr && p.dw[l]) atomicAdd(p.dw[l] + (size_t)j * kr + k, v[i]);
+        else if (k == K && p.db[l]) atomicAdd(p.db[l] + j, v[i]);
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int tc_build(const B2nMlp* m, const B2nMlpGrad* g, TcParams& p, bool transposed) {
+  memset(&p, 0, sizeof(p));
+  if (m->n_layers < 1 || m->n_layers > TC_MAXL || m->in_dim < 1 || m->in_dim > 64) return -1;
+  if (m->hidden_act != B2N_ACT_RELU && m->hidden_act != B2N_ACT_NONE) return -1;
+  if (m->out_act != B2N_ACT_NONE && m->out_act != B2N_ACT_SIGMOID && m->out_act != B2N_ACT_RELU) return -1;
+  p.n_layers = m->n_layers, p.in_dim = m->in_dim, p.in_pad = (m->in_dim + 15) & ~15;
+  p.hidden_act = m->hidden_act, p.out_act = m->out_act;
+  int prev = m->in_dim;
+  uint32_t off = 0, boff = 0;
+  long long hid = 0;
+  for (int l = 0; l < m->n_layers; ++l) {
+    const int out = m->out_dims[l];
+    if (m->skip[l] || out < 1 || out > 64 || m->w[l] == nullptr) return -1;
+    if (l < m->n_layers - 1 && (out & 3)) return -1;  // hidden rows are saved with float4 stores
+    p.kr[l] = prev, p.nr[l] = out;
+    p.K[l] = (prev + 15) & ~15, p.N[l] = (out + 15) & ~15;
+    p.w[l] = m->w[l], p.b[l] = m->b[l];
+    p.dw[l] = g ? g->dw[l] : nullptr, p.db[l] = g ? g->db[l] : nullptr;
+    p.w_bytes[l] = (uint32_t)(p.K[l] / 4) * (uint32_t)((transposed ? p.K[l] : p.N[l]) * 16);
+    if (transposed) p.w_bytes[l] = (uint32_t)(p.N[l] / 4) * (uint32_t)(p.K[l] * 16);
+    p.w_off[l] = off;
+    off += 2 * p.w_bytes[l];
+    p.bias_off[l] = boff;
+    boff += p.N[l];
+    p.hid_off[l] = hid;
+    hid += out;
+    prev = out;
+  }
+  p.w_total = off;
+  return 0;
+}
+
+static int tc_smem_limit() {
+  static int lim = 0;
+  if (!lim) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || lim <= 0) lim = 232448;
+  }
+  return lim;
+}
+
+extern "C" int b2n_mlp_tc_fwd(const B2nMlp* mlp_host, const float* x, int64_t x_stride, int64_t n, float* y,
+                              float* hidden, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(mlp_host && x && y, "null pointer");
+  TcParams p;
+  B2N_UNSUPPORTED(tc_build(mlp_host, nullptr, p, false) != 0,
+                  "tensor-core MLP: needs <= 4 layers, widths <= 64 (hidden % 4 == 0), ReLU hidden, no skips");
+  B2N_REQUIRE(x_stride >= mlp_host->in_dim, "x_stride smaller than in_dim");
+  const size_t smem = 2 * TC_TILE_BYTES + p.w_total + 4 * 64 * TC_MAXL + 1024;
+  B2N_UNSUPPORTED(smem > (size_t)tc_smem_limit(), "tensor-core MLP: shared memory");
+  cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = (int)min(div_up(n, TC_ROWS), (int64_t)b2n_sm_count());
+  mlp_tc_fwd_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, x, x_stride, n, y, hidden);
+  B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_mlp_tc_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, int64_t x_stride,
+                              const float* y, const float* hidden, const float* dy, int64_t n, float* dx,
+                              int64_t dx_stride, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(mlp_host && grad_host && x && y && dy, "null pointer");
+  B2N_REQUIRE(mlp_host->n_layers == 1 || hidden != nullptr, "hidden activations required");
+  TcParams p;
+  B2N_UNSUPPORTED(tc_build(mlp_host, grad_host, p, true) != 0,
+                  "tensor-core MLP: needs <= 4 layers, widths <= 64 (hidden % 4 == 0), ReLU hidden, no skips");
+  B2N_REQUIRE(dx == nullptr || dx_stride >= mlp_host->in_dim, "dx_stride smaller than in_dim");
+  const size_t smem = 2 * TC_TILE_BYTES + TC_TZ_BYTES + 2 * TC_TA_BYTES + p.w_total + 1024;
+  B2N_UNSUPPORTED(smem > (size_t)tc_smem_limit(), "tensor-core MLP: shared memory");
+  cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = (int)min(div_up(n, TC_ROWS), (int64_t)b2n_sm_count());
+  mlp_tc_bwd_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, x, x_stride, y, hidden, dy, n, dx, dx_stride);
+  B2N_LAUNCH_CHECK();
+}

@@ -54,7 +54,7 @@ class _Net:
 class NerfactoStep:
     def __init__(self, model: NerfactoModel, n_rays: int, lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-15,
                  lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
-                 always_update_proposals: bool = False) -> None:
+                 always_update_proposals: bool = False, mlp_backend: str = "auto") -> None:
         cfg = model.config
         if cfg.implementation != "torch":
             raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
@@ -75,6 +75,18 @@ class NerfactoStep:
         self.head_b = [l.bias for l in fld.mlp_head.layers]
         self.emb = fld.embedding_appearance.embedding.weight if fld.embedding_appearance is not None else None
         self.geo, self.n_emb = fld.geo_feat_dim, (fld.appearance_embedding_dim if self.emb is not None else 0)
+        specs = [p_.spec for p_ in self.props] + [self.base.spec, self.head_spec]
+        if mlp_backend == "tc" and not all(F.mlp_tc_supported(sp) for sp in specs):
+            raise NotImplementedError("a network of this model is outside the tensor-core MLP's shape range")
+
+        def use_tc(sp) -> bool:
+            if mlp_backend == "simt" or not F.mlp_tc_supported(sp):
+                return False
+            # auto: tensor cores pay off once a layer is >= 32 wide; the 10->16->1 proposal nets stay on FFMA
+            return mlp_backend == "tc" or max(sp.out_dims) >= 32
+
+        self.tc_net = {id(sp): use_tc(sp) for sp in specs}
+        self.tc = use_tc(self.head_spec)
         self.contraction = fld.spatial_distortion is not None
         self.aabb = fld.aabb.flatten().tolist()
         self.avg = float(cfg.average_init_density)
@@ -110,8 +122,9 @@ class NerfactoStep:
         N2 = R * self.S[2]
         self.n_sh = 16
         self.head_in_w = self.n_sh + self.geo + self.n_emb
+        self.hin_stride = (self.head_in_w + 3) // 4 * 4 if self.tc else self.head_in_w  # padded rows: 128-bit loads
         self.sh = torch.zeros(R, self.n_sh, **f32)
-        self.hin, self.d_hin = torch.zeros(N2, self.head_in_w, **f32), torch.zeros(N2, self.head_in_w, **f32)
+        self.hin, self.d_hin = torch.zeros(N2, self.hin_stride, **f32), torch.zeros(N2, self.hin_stride, **f32)
         self.hid_head = torch.zeros(self.head_spec.hidden_width * N2, **f32)
         self.rgb, self.d_rgb = torch.zeros(N2, 3, **f32), torch.zeros(N2, 3, **f32)
         self.d_hpre = torch.zeros(N2, **f32)
@@ -129,6 +142,20 @@ class NerfactoStep:
             raise NotImplementedError("captured step: background_color must be last_sample / white / black")
 
     # ------------------------------------------------------------------------------------------------
+    def _mlp_fwd(self, m, x: Tensor, x_stride: int, n: int, y: Tensor, hidden: Tensor, spec=None) -> None:
+        if self.tc_net[id(spec)]:
+            call("b2n_mlp_tc_fwd", C.byref(m), ptr(x), x_stride, n, ptr(y), ptr(hidden), stream())
+        else:
+            call("b2n_mlp_fwd", C.byref(m), ptr(x), n, ptr(y), ptr(hidden), stream())
+
+    def _mlp_bwd(self, m, g, x: Tensor, x_stride: int, y: Tensor, hidden: Tensor, dy: Tensor, n: int, dx: Tensor,
+                 dx_stride: int, spec=None) -> None:
+        if self.tc_net[id(spec)]:
+            call("b2n_mlp_tc_bwd", C.byref(m), C.byref(g), ptr(x), x_stride, ptr(y), ptr(hidden), ptr(dy), n, ptr(dx),
+                 dx_stride, stream())
+        else:
+            call("b2n_mlp_bwd", C.byref(m), C.byref(g), ptr(x), ptr(y), ptr(hidden), ptr(dy), n, ptr(dx), stream())
+
     def _density_net_fwd(self, lvl: int, net: _Net) -> None:
         R, S = self.R, self.S[lvl]
         N = R * S
@@ -138,7 +165,7 @@ class NerfactoStep:
              int(self.contraction), C.cast(box, C.c_void_p), ptr(self.x[lvl]), ptr(self.sel[lvl], torch.uint8), stream())
         call("b2n_hashgrid_fwd", C.byref(net.grid.c), ptr(self.x[lvl]), ptr(net.table), N, ptr(self.enc[lvl]), NULL, stream())
         m, _ = net.structs()
-        call("b2n_mlp_fwd", C.byref(m), ptr(self.enc[lvl]), N, ptr(self.h[lvl]), ptr(self.hid[lvl]), stream())
+        self._mlp_fwd(m, self.enc[lvl], self.enc[lvl].shape[1], N, self.h[lvl], self.hid[lvl], net.spec)
         call("b2n_density_act_fwd", ptr(self.h[lvl]), self.h[lvl].shape[1], ptr(self.sel[lvl], torch.uint8), N, self.avg,
              ptr(self.dens[lvl]), stream())
         call("b2n_weights_fwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), R, S, ptr(self.w[lvl]), stream())
@@ -153,8 +180,8 @@ class NerfactoStep:
         call("b2n_density_act_bwd", ptr(self.h[lvl]), 1, ptr(self.sel[lvl], torch.uint8), ptr(self.d_dens[lvl]), N, self.avg,
              ptr(self.d_h[lvl]), 1, stream())
         m, g = net.structs()
-        call("b2n_mlp_bwd", C.byref(m), C.byref(g), ptr(self.enc[lvl]), ptr(self.h[lvl]), ptr(self.hid[lvl]),
-             ptr(self.d_h[lvl]), N, ptr(self.d_enc[lvl]), stream())
+        self._mlp_bwd(m, g, self.enc[lvl], self.enc[lvl].shape[1], self.h[lvl], self.hid[lvl], self.d_h[lvl], N,
+                      self.d_enc[lvl], self.d_enc[lvl].shape[1], net.spec)
         call("b2n_hashgrid_bwd", C.byref(net.grid.c), ptr(self.x[lvl]), ptr(net.table), ptr(self.d_enc[lvl]), N,
              ptr(net.table.grad), NULL, stream())
 
@@ -186,17 +213,17 @@ class NerfactoStep:
              int(self.contraction), C.cast(box, C.c_void_p), ptr(self.x[2]), ptr(self.sel[2], torch.uint8), st())
         call("b2n_hashgrid_fwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), N2, ptr(self.enc[2]), NULL, st())
         mb, gb = self.base.structs()
-        call("b2n_mlp_fwd", C.byref(mb), ptr(self.enc[2]), N2, ptr(self.h[2]), ptr(self.hid[2]), st())
+        self._mlp_fwd(mb, self.enc[2], self.enc[2].shape[1], N2, self.h[2], self.hid[2], self.base.spec)
         bw = self.h[2].shape[1]
         call("b2n_density_act_fwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), N2, self.avg, ptr(self.dens[2]), st())
         call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), st())
         call("b2n_head_input_fwd", ptr(self.sh), self.n_sh, ptr(self.h[2]), bw, self.geo, ptr(self.emb), ptr(self.cams, torch.int64),
-             self.n_emb, 1 if self.emb is not None else 0, R, S2, ptr(self.hin), st())
+             self.n_emb, 1 if self.emb is not None else 0, R, S2, ptr(self.hin), self.hin_stride, st())
         mh = self.head_spec.struct(self.head_w, self.head_b)
         gh = B2nMlpGrad()
         for i, (w, b) in enumerate(zip(self.head_w, self.head_b)):
             gh.dw[i], gh.db[i] = ptr(w.grad).value, ptr(b.grad).value
-        call("b2n_mlp_fwd", C.byref(mh), ptr(self.hin), N2, ptr(self.rgb), ptr(self.hid_head), st())
+        self._mlp_fwd(mh, self.hin, self.hin_stride, N2, self.rgb, self.hid_head, self.head_spec)
         call("b2n_weights_fwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), R, S2, ptr(self.w[2]), st())
         bg_mode, bg_ptr, _keep = F._bg_args(self.bg)
         call("b2n_composite_fwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2, bg_mode, bg_ptr, 0,
@@ -218,12 +245,12 @@ class NerfactoStep:
         call("b2n_weights_bwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), ptr(self.d_w[2]), R, S2, ptr(self.d_dens[2]), st())
         call("b2n_density_act_bwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), ptr(self.d_dens[2]), N2, self.avg,
              ptr(self.d_hpre), 1, st())
-        call("b2n_mlp_bwd", C.byref(mh), C.byref(gh), ptr(self.hin), ptr(self.rgb), ptr(self.hid_head), ptr(self.d_rgb), N2,
-             ptr(self.d_hin), st())
-        call("b2n_head_input_bwd", ptr(self.d_hin), self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre), ptr(self.cams, torch.int64),
+        self._mlp_bwd(mh, gh, self.hin, self.hin_stride, self.rgb, self.hid_head, self.d_rgb, N2, self.d_hin, self.hin_stride,
+                      self.head_spec)
+        call("b2n_head_input_bwd", ptr(self.d_hin), self.hin_stride, self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre), ptr(self.cams, torch.int64),
              R, S2, ptr(self.d_h[2]), bw, ptr(self.emb.grad) if self.emb is not None else NULL, st())
-        call("b2n_mlp_bwd", C.byref(mb), C.byref(gb), ptr(self.enc[2]), ptr(self.h[2]), ptr(self.hid[2]), ptr(self.d_h[2]), N2,
-             ptr(self.d_enc[2]), st())
+        self._mlp_bwd(mb, gb, self.enc[2], self.enc[2].shape[1], self.h[2], self.hid[2], self.d_h[2], N2, self.d_enc[2],
+                      self.d_enc[2].shape[1], self.base.spec)
         call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
              ptr(self.base.table.grad), NULL, st())
         # ---------------- backward: proposal networks (only the interlevel loss reaches them)

@@ -209,6 +209,36 @@ def mlp_backward(spec: MlpSpec, x, y, hidden, dy, weights, biases, dws, dbs, wan
     return dx
 
 
+def mlp_tc_supported(spec: MlpSpec) -> bool:
+    """Eligibility of the tensor-core (tcgen05, 3xTF32) kernels — mirrors mlp_tc.cu:tc_build."""
+    return (len(spec.out_dims) <= 4 and spec.in_dim <= 64 and not spec.skip and max(spec.out_dims) <= 64
+            and all(o % 4 == 0 for o in spec.out_dims[:-1]) and spec.hidden_act in ("relu", "none")
+            and spec.out_act in ("none", "sigmoid", "relu"))
+
+
+def mlp_tc_forward(spec: MlpSpec, x: Tensor, weights, biases, save_hidden: bool, x_stride: Optional[int] = None):
+    """Tensor-core forward.  x [N, >=in_dim] row-major (row stride x_stride floats)."""
+    x = _c(x)
+    n = x.shape[0]
+    y = torch.empty(n, spec.out_dims[-1], device=x.device, dtype=torch.float32)
+    hidden = torch.empty(max(spec.hidden_width, 1) * n, device=x.device, dtype=torch.float32) if save_hidden else None
+    m = spec.struct([_c(w) for w in weights], [None if b is None else _c(b) for b in biases])
+    call("b2n_mlp_tc_fwd", C.byref(m), ptr(x), x_stride or x.shape[1], n, ptr(y), ptr(hidden), stream())
+    return y, hidden
+
+
+def mlp_tc_backward(spec: MlpSpec, x, y, hidden, dy, weights, biases, dws, dbs, want_dx: bool):
+    m = spec.struct(weights, biases)
+    g = B2nMlpGrad()
+    for i in range(len(spec.out_dims)):
+        g.dw[i] = ptr(dws[i]).value if dws[i] is not None else None
+        g.db[i] = ptr(dbs[i]).value if dbs[i] is not None else None
+    dx = torch.empty(x.shape[0], spec.in_dim, device=x.device, dtype=torch.float32) if want_dx else None
+    call("b2n_mlp_tc_bwd", C.byref(m), C.byref(g), ptr(x), x.shape[1], ptr(y), ptr(hidden), ptr(_c(dy)), x.shape[0],
+         ptr(dx), spec.in_dim, stream())
+    return dx
+
+
 class _MlpFn(torch.autograd.Function):
     @staticmethod
     @_fwd

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "b2n_hashgrid_bwd": [C.POINTER(B2nGrid), _P, _P, _P, _I64, _P, _P, _P],
     "b2n_mlp_fwd": [C.POINTER(B2nMlp), _P, _I64, _P, _P, _P],
     "b2n_mlp_bwd": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _I64, _P, _P],
+    "b2n_mlp_tc_fwd": [C.POINTER(B2nMlp), _P, _I64, _I64, _P, _P, _P],
+    "b2n_mlp_tc_bwd": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _I64, _P, _P, _P, _I64, _P, _I64, _P],
     "b2n_sh_fwd": [_P, _I64, _I32, _I32, _P, _P],
     "b2n_freq_fwd": [_P, _I64, _I32, _P, _I32, _I32, _P, _P],
     "b2n_freq_bwd": [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P],
@@ -77,9 +79,10 @@ _SIGNATURES = {
     "b2n_packed_accumulate_bwd": [_P, _P, _I32, _P, _P, _I64, _P, _P, _P],
     "b2n_occgrid_count": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P],
     "b2n_occgrid_fill": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P, _P, _P, _P],
+    "b2n_tc_selftest": [_I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b2n_adam_step_dev": [_P, _P, _P, _P, _I64, _P, C.c_double, C.c_double, C.c_double, _P],
-    "b2n_head_input_fwd": [_P, _I32, _P, _I32, _I32, _P, _P, _I32, _I32, _I64, _I32, _P, _P],
-    "b2n_head_input_bwd": [_P, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _P],
+    "b2n_head_input_fwd": [_P, _I32, _P, _I32, _I32, _P, _P, _I32, _I32, _I64, _I32, _P, _I32, _P],
+    "b2n_head_input_bwd": [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _P],
     "b2n_mse_fwd_bwd": [_P, _P, _I64, _F, _P, _P, _P],
     "b2n_sum_rows": [_P, _I64, _F, _P, _P],
     "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P],
@@ -129,7 +132,8 @@ LAUNCHES = 0  # kernel-launching C-ABI calls made by this process (bench.py repo
 
 
 PROFILE = None  # set to {} to time every C-ABI launch with CUDA events on the launching stream (eager mode only)
-_N_ARG = {"b2n_hashgrid_fwd": 3, "b2n_hashgrid_bwd": 4, "b2n_mlp_fwd": 2, "b2n_mlp_bwd": 6}
+_N_ARG = {"b2n_hashgrid_fwd": 3, "b2n_hashgrid_bwd": 4, "b2n_mlp_fwd": 2, "b2n_mlp_bwd": 6, "b2n_mlp_tc_fwd": 3,
+          "b2n_mlp_tc_bwd": 7}
 
 
 def call(name: str, *args) -> None:

@@ -47,3 +47,18 @@ def assert_close(a, b, rel=1e-4, name=""):
     scale = float(b.abs().max().clamp_min(1e-30))
     err = float((a - b).abs().max())
     assert err <= rel * scale, f"{name}: max abs err {err:.3e} > {rel:g} * {scale:.3e}"
+
+
+def assert_grad_close(a, b, name="", rel=1e-4, sparse_switching=False):
+    """Gradient comparison.  `sparse_switching=True` is for gradients that are sums of terms which switch on and
+    off with the sample positions (hash-table rows picked by floor/ceil of a position, clip(w - w_outer, 0) of the
+    interlevel loss): a 1e-5 shift of a sample legitimately changes individual entries by far more than 1e-4, so
+    those are compared by direction (cosine) and norm; everything else entry-wise at `rel` of the max-norm."""
+    a = a.detach().cpu() if isinstance(a, torch.Tensor) else torch.as_tensor(a)
+    b = b.detach().cpu() if isinstance(b, torch.Tensor) else torch.as_tensor(b)
+    if not sparse_switching:
+        return assert_close(a, b, rel, name)
+    x, y = a.double().flatten(), b.double().flatten()
+    cos = float((x @ y) / (x.norm() * y.norm()).clamp_min(1e-300))
+    ratio = float(x.norm() / y.norm().clamp_min(1e-300))
+    assert cos > 0.999 and abs(ratio - 1) < 2e-2, f"{name}: cosine {cos:.6f}, norm ratio {ratio:.5f}"

@@ -186,6 +186,9 @@ def run_b200(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib.load()
+    for kv in filter(None, args.tune.split(",")):
+        k, v = kv.split("=")
+        assert lib.tune(k, int(v)), f"unknown tuning key {k}"
     torch.manual_seed(0)  # identical initial weights on every rank
     cfg = NerfactoModelConfig(implementation="torch", average_init_density=0.01)
     model = NerfactoModel(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_train_data=NUM_IMAGES).to(dev)
@@ -199,7 +202,8 @@ def run_b200(args) -> None:
         from nerfstudio_b200.engine import NerfactoStep
 
         engine = NerfactoStep(model, RAYS_PER_GPU, allreduce=allreduce, use_graph=(args.engine == "graph"),
-                              always_update_proposals=args.force_proposal_update, mlp_backend=args.mlp)
+                              always_update_proposals=args.force_proposal_update, mlp_backend=args.mlp,
+                              fused_proposals=not args.unfused_proposals)
         trainer = engine
     D.broadcast_parameters(trainer.optim.flat)
     n_params = trainer.optim.flat.numel()
@@ -338,6 +342,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mlp", default="auto", choices=["auto", "tc", "simt"],
                     help="tiny-MLP kernels of the graph/eager engine: tcgen05 3xTF32 (tc) or fp32 SIMT")
+    ap.add_argument("--unfused-proposals", action="store_true", help="proposal networks as separate grid/MLP launches")
+    ap.add_argument("--tune", default="", help="comma separated key=value launch-geometry knobs (lib.tune)")
     ap.add_argument("--engine", default="graph", choices=["graph", "eager", "autograd"],
                     help="graph: CUDA-graph replay of the hand-written step (default); eager: same launches without a "
                          "graph; autograd: the drop-in modules under torch.autograd")

@@ -269,6 +269,22 @@ int b2n_mse_fwd_bwd(const float* pred, const float* gt, int64_t n, float gscale,
 /* out[0] += scale * sum(rows[0..n)) */
 int b2n_sum_rows(const float* rows, int64_t n, float scale, float* out, void* stream);
 
+/* ---- fused proposal density field (fields/density_fields.py:94-117) ---------------------------
+ * ray sample -> unit cube -> hash grid (F=2, <= 8 levels) -> MLP in->16->1 (ReLU) -> avg_init * trunc_exp * selector,
+ * ONE launch; the network is read from the device pointers in mlp_host (w[0] [16][in], b[0], w[1] [1][16], b[1]).
+ * Ray form: origins/directions [R,3], starts/ends [R,S] (row stride bin_stride); point form: directions NULL and
+ * origins = positions [R,3].  density [R*S].  Other shapes: B2N_E_UNSUPPORTED (use the unfused calls). */
+int b2n_density_field_fwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, const float* table, const float* origins,
+                          const float* directions, const float* starts, const float* ends, int64_t bin_stride,
+                          int64_t n_rays, int32_t n_samples, int32_t contraction, const float* aabb_host6,
+                          float avg_init, float* density, void* stream);
+/* backward from d_density [R*S]: recomputes the forward, ACCUMULATES into dtable and grad_host->dw/db[0..1]. */
+int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                          const float* table, const float* origins, const float* directions, const float* starts,
+                          const float* ends, int64_t bin_stride, int64_t n_rays, int32_t n_samples,
+                          int32_t contraction, const float* aabb_host6, float avg_init, const float* d_density,
+                          float* dtable, void* stream);
+
 /* ---- tcgen05 self-test (diagnostic; pins the tensor-core operand/TMEM semantics the MLP kernels rely on) -------
  * One 128-row tile.  mode 0: D = A[128][k] * B[n][k]^T (K-major x K-major);  mode 1: D = A[128][k] * W[k][n]
  * (K-major x MN-major);  mode 2: D = A[128][m]^T * B[128][n] (MN-major x MN-major, reduction over the 128 rows).

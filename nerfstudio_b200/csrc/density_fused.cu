@@ -1,0 +1,373 @@
+// Fused proposal density field: ray sample -> unit cube -> hash grid (L levels, F=2) -> 2-layer MLP (H hidden, 1 out)
+// -> trunc_exp density, forward and backward, one kernel each.
+//
+// Replaces HashMLPDensityField.get_density (nerfstudio/fields/density_fields.py:94-117) — the 1.44 M points per
+// 4096-ray step that go through the two proposal networks are the largest point count on the path.
+// Unfused, each level of the proposal sampler costs 4 forward + 3 backward launches and round-trips the [N,10]
+// encoding and [N,16] hidden activations through HBM; the 10->16->1 network is far too small for either the tiled
+// SIMT kernel (10 of 256 threads busy in its dW phase) or the tensor cores.  Here one thread owns a sample: the 40
+// corner features are gathered straight into registers, the network (193 weights, staged once per CTA in shared
+// memory and read as warp-uniform 128-bit broadcasts) is evaluated in FFMA, and nothing but the density leaves the SM.
+//
+// Backward recomputes the forward from the ray (re-gathering is cheaper than storing), forms d(encoding) in
+// registers, scatters it with the run-length accumulation of hashgrid.cu (a thread walks CH consecutive samples of
+// a ray and flushes its 8 corner accumulators only when the cell changes), and reduces the weight gradients
+// dW1 = dZ1^T Enc through a shared-memory staging tile: thread (j,c) of the CTA sums its product over the CTA's
+// samples, keeps the running total in a register across all tiles and issues ONE atomic at the end.
+#include <string.h>
+
+#include "hashgrid.cuh"
+#include "positions.cuh"
+
+#define DF_MAXL 8
+#define DF_H 16
+#define DF_MAXIN (2 * DF_MAXL)
+#define DF_THREADS 256
+#define DF_CH 4  // consecutive samples per thread in the backward kernel
+
+#define DF_W1S 16  // padded row stride of w1 in shared memory (>= 2*DF_MAXL, multiple of 4)
+
+// device pointers to the network of HashMLPDensityField.mlp_base[1] (nn.Linear layout) — they change every
+// optimiser step and the launch may be replayed from a CUDA graph, so they are read on the device
+struct DensityNet {
+  const float* w1;  // [H][in]
+  const float* b1;  // [H]
+  const float* w2;  // [1][H]
+  const float* b2;  // [1]
+  float avg_init;
+  int in_dim;
+};
+
+// shared-memory image: w1 [H][DF_W1S] | b1 [H] | w2 [H] | b2
+#define DF_NET_FLOATS (DF_H * DF_W1S + 2 * DF_H + 4)
+
+__device__ __forceinline__ void stage_net(const DensityNet& net, float* ws) {
+  for (int idx = threadIdx.x; idx < DF_H * DF_W1S; idx += blockDim.x) {
+    const int j = idx / DF_W1S, c = idx - j * DF_W1S;
+    ws[idx] = c < net.in_dim ? __ldg(net.w1 + j * net.in_dim + c) : 0.f;
+  }
+  if (threadIdx.x < DF_H) {
+    ws[DF_H * DF_W1S + threadIdx.x] = net.b1 ? __ldg(net.b1 + threadIdx.x) : 0.f;
+    ws[DF_H * DF_W1S + DF_H + threadIdx.x] = __ldg(net.w2 + threadIdx.x);
+  }
+  if (threadIdx.x == 0) ws[DF_H * DF_W1S + 2 * DF_H] = net.b2 ? __ldg(net.b2) : 0.f;
+}
+
+struct RayGeom {
+  const float* origins;     // [R,3]
+  const float* directions;  // [R,3] or nullptr (point form: origins = positions [N,3], S = 1)
+  const float* starts;      // [R,S] with row stride
+  const float* ends;
+  int64_t bin_stride;
+  int64_t n_rays;
+  int n_samples;
+};
+
+template <int L>
+struct Sample {
+  float x[3];
+  bool sel;
+  float enc[2 * L];
+};
+
+template <int L, int MODE>
+__device__ __forceinline__ void encode_sample(const GridParams& gp, const PosParams& pp, const RayGeom& rg,
+                                              const float* __restrict__ table, int64_t i, Sample<L>& sm) {
+  const int64_t r = i / rg.n_samples;
+  const int s = (int)(i - r * rg.n_samples);
+  if (rg.directions != nullptr)
+    frustum_centre(rg.origins + 3 * r, rg.directions + 3 * r, __ldg(rg.starts + r * rg.bin_stride + s),
+                   __ldg(rg.ends + r * rg.bin_stride + s), sm.x);
+  else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) sm.x[a] = __ldg(rg.origins + 3 * i + a);
+  }
+  sm.sel = unit_cube_point(pp, sm.x);
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const Corners c = corners_of<MODE>(gp, l, sm.x[0], sm.x[1], sm.x[2]);
+    Vec<2> f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = ldg_row<2>(table, c.row[k]);
+    const float ox = c.ox, oy = c.oy, oz = c.oz, rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float f03 = f[0].v[j] * ox + f[3].v[j] * rx, f12 = f[1].v[j] * ox + f[2].v[j] * rx;
+      const float f56 = f[5].v[j] * ox + f[6].v[j] * rx, f47 = f[4].v[j] * ox + f[7].v[j] * rx;
+      sm.enc[2 * l + j] = (f03 * oy + f12 * ry) * oz + (f47 * oy + f56 * ry) * rz;
+    }
+  }
+}
+
+template <int L>
+__device__ __forceinline__ float mlp_forward(const float* __restrict__ ws, const float (&enc)[2 * L], float (&z1)[DF_H]) {
+  constexpr int IN = 2 * L;
+  float z2 = ws[DF_H * DF_W1S + 2 * DF_H];
+#pragma unroll
+  for (int j = 0; j < DF_H; ++j) {
+    float a = ws[DF_H * DF_W1S + j];
+    const float4* wr = reinterpret_cast<const float4*>(ws + j * DF_W1S);
+#pragma unroll
+    for (int q = 0; q < (IN + 3) / 4; ++q) {
+      const float4 w = wr[q];
+      if (4 * q + 0 < IN) a = fmaf(w.x, enc[4 * q + 0 < IN ? 4 * q + 0 : 0], a);
+      if (4 * q + 1 < IN) a = fmaf(w.y, enc[4 * q + 1 < IN ? 4 * q + 1 : 0], a);
+      if (4 * q + 2 < IN) a = fmaf(w.z, enc[4 * q + 2 < IN ? 4 * q + 2 : 0], a);
+      if (4 * q + 3 < IN) a = fmaf(w.w, enc[4 * q + 3 < IN ? 4 * q + 3 : 0], a);
+    }
+    z1[j] = a;
+    z2 = fmaf(ws[DF_H * DF_W1S + DF_H + j], fmaxf(a, 0.f), z2);
+  }
+  return z2;
+}
+
+template <int L, int MODE>
+__global__ void __launch_bounds__(DF_THREADS) density_fused_fwd_kernel(const __grid_constant__ GridParams gp,
+                                                                       const __grid_constant__ PosParams pp,
+                                                                       const __grid_constant__ DensityNet net,
+                                                                       const __grid_constant__ RayGeom rg,
+                                                                       const float* __restrict__ table,
+                                                                       float* __restrict__ density) {
+  __shared__ __align__(16) float ws[DF_NET_FLOATS];
+  stage_net(net, ws);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rg.n_rays * rg.n_samples) return;
+  Sample<L> sm;
+  encode_sample<L, MODE>(gp, pp, rg, table, i, sm);
+  float z1[DF_H];
+  const float z2 = mlp_forward<L>(ws, sm.enc, z1);
+  density[i] = mul_rn(mul_rn(net.avg_init, expf(z2)), sm.sel ? 1.f : 0.f);
+}
+
+template <int L, int MODE>
+__global__ void __launch_bounds__(DF_THREADS) density_fused_bwd_kernel(const __grid_constant__ GridParams gp,
+                                                                       const __grid_constant__ PosParams pp,
+                                                                       const __grid_constant__ DensityNet net,
+                                                                       const __grid_constant__ RayGeom rg,
+                                                                       const float* __restrict__ table,
+                                                                       const float* __restrict__ d_density,
+                                                                       float* __restrict__ dtable, float* __restrict__ dw1,
+                                                                       float* __restrict__ db1, float* __restrict__ dw2,
+                                                                       float* __restrict__ db2) {
+  constexpr int IN = 2 * L;
+  constexpr int SW = DF_H + IN + 1;             // staging row: z1[16] | enc[IN] | dz2   (odd stride: conflict-free)
+  constexpr int DW = DF_CH * IN + 1;            // per-thread d(encoding) row in shared memory (odd stride)
+  extern __shared__ __align__(16) float dyn_smem[];
+  float* stage = dyn_smem;                       // [DF_THREADS][SW]
+  float* denc = dyn_smem + DF_THREADS * SW;      // [DF_THREADS][DW]
+  __shared__ __align__(16) float ws[DF_NET_FLOATS];
+  stage_net(net, ws);
+  const int t = threadIdx.x;
+  const int64_t n = rg.n_rays * rg.n_samples;
+  const int64_t n_tiles = (n + DF_THREADS * DF_CH - 1) / (DF_THREADS * DF_CH);
+  // weight-gradient owners (one register accumulator each, kept across all tiles of the CTA):
+  //   t in [0, H*IN)            dW1[j][c],   then H threads db1[j], then H threads dW2[j], then one thread db2
+  const int oj = t / IN, oc = t - oj * IN;
+  const int role = t < DF_H * IN ? 0 : t < DF_H * IN + DF_H ? 1 : t < DF_H * IN + 2 * DF_H ? 2 : t == DF_H * IN + 2 * DF_H ? 3 : 4;
+  float own_acc = 0.f;
+  __syncthreads();
+  float* my_denc = denc + t * DW;
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t i0 = (tile * DF_THREADS + t) * DF_CH;
+    float xs[DF_CH][3];
+#pragma unroll
+    for (int s = 0; s < DF_CH; ++s) {
+      const int64_t i = i0 + s;
+      float* row = stage + t * SW;
+      float dz2 = 0.f;
+      if (i < n) {
+        Sample<L> sm;
+        encode_sample<L, MODE>(gp, pp, rg, table, i, sm);
+        float z1[DF_H];
+        const float z2 = mlp_forward<L>(ws, sm.enc, z1);
+        const float g = __ldg(d_density + i);
+        // density = avg * exp(z2) * sel ; trunc_exp backward clamps the exponent (activations.py:36-41)
+        if (sm.sel && g != 0.f) dz2 = g * net.avg_init * expf(fminf(fmaxf(z2, -15.f), 15.f));
+        float de[IN];
+#pragma unroll
+        for (int c = 0; c < IN; ++c) de[c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DF_H; ++j) {
+          row[j] = z1[j];
+          const float d = z1[j] > 0.f ? dz2 * ws[DF_H * DF_W1S + DF_H + j] : 0.f;
+          const float4* wr = reinterpret_cast<const float4*>(ws + j * DF_W1S);
+#pragma unroll
+          for (int q = 0; q < (IN + 3) / 4; ++q) {
+            const float4 w = wr[q];
+            if (4 * q + 0 < IN) de[4 * q + 0 < IN ? 4 * q + 0 : 0] = fmaf(d, w.x, de[4 * q + 0 < IN ? 4 * q + 0 : 0]);
+            if (4 * q + 1 < IN) de[4 * q + 1 < IN ? 4 * q + 1 : 0] = fmaf(d, w.y, de[4 * q + 1 < IN ? 4 * q + 1 : 0]);
+            if (4 * q + 2 < IN) de[4 * q + 2 < IN ? 4 * q + 2 : 0] = fmaf(d, w.z, de[4 * q + 2 < IN ? 4 * q + 2 : 0]);
+            if (4 * q + 3 < IN) de[4 * q + 3 < IN ? 4 * q + 3 : 0] = fmaf(d, w.w, de[4 * q + 3 < IN ? 4 * q + 3 : 0]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < IN; ++c) row[DF_H + c] = sm.enc[c], my_denc[s * IN + c] = de[c];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xs[s][a] = sm.x[a];
+      } else {
+#pragma unroll
+        for (int c = 0; c < IN; ++c) my_denc[s * IN + c] = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) xs[s][a] = 0.f;
+      }
+      row[DF_H + IN] = dz2;
+      __syncthreads();
+      // ---- the owners reduce their product over this round's 256 staged samples
+      if (role == 0) {
+        const float w2j = ws[DF_H * DF_W1S + DF_H + oj];
+        float a = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < DF_THREADS; ++q) {
+          const float* r_ = stage + q * SW;
+          const float d = r_[oj] > 0.f ? r_[DF_H + IN] * w2j : 0.f;
+          a = fmaf(d, r_[DF_H + oc], a);
+        }
+        own_acc += a;
+      } else if (role == 1) {
+        const int j = t - DF_H * IN;
+        const float w2j = ws[DF_H * DF_W1S + DF_H + j];
+        float a = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < DF_THREADS; ++q) a += stage[q * SW + j] > 0.f ? stage[q * SW + DF_H + IN] * w2j : 0.f;
+        own_acc += a;
+      } else if (role == 2) {
+        const int j = t - DF_H * IN - DF_H;
+        float a = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < DF_THREADS; ++q) a = fmaf(stage[q * SW + DF_H + IN], fmaxf(stage[q * SW + j], 0.f), a);
+        own_acc += a;
+      } else if (role == 3) {
+        float a = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < DF_THREADS; ++q) a += stage[q * SW + DF_H + IN];
+        own_acc += a;
+      }
+      __syncthreads();
+    }
+    // ---- scatter d_enc into the table: per level, run-length accumulation over this thread's CH samples
+#pragma unroll 1
+    for (int l = 0; l < L; ++l) {
+      uint32_t rows[8];
+      float acc[8][2];
+      bool have = false;
+#pragma unroll
+      for (int s = 0; s < DF_CH; ++s) {
+        const float ga = my_denc[s * IN + 2 * l], gb = my_denc[s * IN + 2 * l + 1];
+        if (ga == 0.f && gb == 0.f) continue;
+        const Corners c = corners_of<MODE>(gp, l, xs[s][0], xs[s][1], xs[s][2]);
+        bool same = have;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) same &= (c.row[k] == rows[k]);
+        if (!same) {
+          if (have) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) red_row<2>(dtable, rows[k], acc[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) rows[k] = c.row[k], acc[k][0] = 0.f, acc[k][1] = 0.f;
+          have = true;
+        }
+        const float ox = c.ox, oy = c.oy, oz = c.oz, rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
+        const float w[8] = {ox * oy * oz, ox * ry * oz, rx * ry * oz, rx * oy * oz,
+                            ox * oy * rz, ox * ry * rz, rx * ry * rz, rx * oy * rz};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k][0] = fmaf(w[k], ga, acc[k][0]), acc[k][1] = fmaf(w[k], gb, acc[k][1]);
+      }
+      if (have) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red_row<2>(dtable, rows[k], acc[k]);
+      }
+    }
+  }
+  // ---- flush the weight gradients: one atomic per entry per CTA
+  if (role == 0 && dw1) atomicAdd(dw1 + oj * IN + oc, own_acc);
+  if (role == 1 && db1) atomicAdd(db1 + (t - DF_H * IN), own_acc);
+  if (role == 2 && dw2) atomicAdd(dw2 + (t - DF_H * IN - DF_H), own_acc);
+  if (role == 3 && db2) atomicAdd(db2, own_acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_shape(const B2nGrid* g, const B2nMlp* m) {
+  if (g->n_features != 2 || g->n_levels < 1 || g->n_levels > DF_MAXL) return -1;
+  if (m->n_layers != 2 || m->in_dim != 2 * g->n_levels || m->out_dims[0] != DF_H || m->out_dims[1] != 1) return -1;
+  if (m->hidden_act != B2N_ACT_RELU || m->out_act != B2N_ACT_NONE || m->skip[0] || m->skip[1]) return -1;
+  if (!m->w[0] || !m->w[1]) return -1;
+  return 0;
+}
+
+template <int L, int MODE>
+static void launch_fused_bwd(unsigned grid, cudaStream_t st, const GridParams& gp, const PosParams& pp, const DensityNet& net,
+                             const RayGeom& rg, const float* table, const float* d_density, float* dtable, float* dw1,
+                             float* db1, float* dw2, float* db2) {
+  constexpr size_t smem = sizeof(float) * DF_THREADS * ((DF_H + 2 * L + 1) + (DF_CH * 2 * L + 1));
+  auto kernel = density_fused_bwd_kernel<L, MODE>;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, dtable, dw1, db1, dw2, db2);
+}
+
+#define DF_DISPATCH(KERNEL, ...)                                                          \
+  do {                                                                                    \
+    const bool torch_mode = gp.mode == B2N_GRID_TORCH;                                    \
+    switch (gp.n_levels) {                                                                \
+      case 1: if (torch_mode) KERNEL<1, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<1, B2N_GRID_TCNN> __VA_ARGS__; break; \
+      case 2: if (torch_mode) KERNEL<2, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<2, B2N_GRID_TCNN> __VA_ARGS__; break; \
+      case 3: if (torch_mode) KERNEL<3, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<3, B2N_GRID_TCNN> __VA_ARGS__; break; \
+      case 4: if (torch_mode) KERNEL<4, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<4, B2N_GRID_TCNN> __VA_ARGS__; break; \
+      case 5: if (torch_mode) KERNEL<5, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<5, B2N_GRID_TCNN> __VA_ARGS__; break; \
+      case 6: if (torch_mode) KERNEL<6, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<6, B2N_GRID_TCNN> __VA_ARGS__; break; \
+      case 7: if (torch_mode) KERNEL<7, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<7, B2N_GRID_TCNN> __VA_ARGS__; break; \
+      default: if (torch_mode) KERNEL<8, B2N_GRID_TORCH> __VA_ARGS__; else KERNEL<8, B2N_GRID_TCNN> __VA_ARGS__; break; \
+    }                                                                                     \
+  } while (0)
+
+extern "C" int b2n_density_field_fwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, const float* table,
+                                     const float* origins, const float* directions, const float* starts,
+                                     const float* ends, int64_t bin_stride, int64_t n_rays, int32_t n_samples,
+                                     int32_t contraction, const float* aabb_host6, float avg_init, float* density,
+                                     void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(grid_host && mlp_host && table && origins && density, "null pointer");
+  B2N_REQUIRE(directions == nullptr || (starts && ends), "ray form needs starts/ends");
+  B2N_REQUIRE(contraction || aabb_host6, "aabb required without contraction");
+  B2N_UNSUPPORTED(check_shape(grid_host, mlp_host) != 0,
+                  "fused density field: F=2, <= 8 levels, MLP in->16->1 with ReLU (the nerfacto proposal networks)");
+  GridParams gp;
+  B2N_REQUIRE(fill_params(grid_host, gp) == 0, "bad grid description");
+  PosParams pp;
+  fill_pos_params(pp, contraction, aabb_host6);
+  DensityNet net{mlp_host->w[0], mlp_host->b[0], mlp_host->w[1], mlp_host->b[1], avg_init, mlp_host->in_dim};
+  RayGeom rg{origins, directions, starts, ends, bin_stride, n_rays, directions ? n_samples : 1};
+  const int64_t n = rg.n_rays * rg.n_samples;
+  const unsigned grid = (unsigned)div_up(n, DF_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  DF_DISPATCH(density_fused_fwd_kernel, <<<grid, DF_THREADS, 0, st>>>(gp, pp, net, rg, table, density));
+  B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                                     const float* table, const float* origins, const float* directions,
+                                     const float* starts, const float* ends, int64_t bin_stride, int64_t n_rays,
+                                     int32_t n_samples, int32_t contraction, const float* aabb_host6, float avg_init,
+                                     const float* d_density, float* dtable, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(grid_host && mlp_host && grad_host && table && origins && d_density && dtable, "null pointer");
+  B2N_REQUIRE(directions == nullptr || (starts && ends), "ray form needs starts/ends");
+  B2N_REQUIRE(contraction || aabb_host6, "aabb required without contraction");
+  B2N_UNSUPPORTED(check_shape(grid_host, mlp_host) != 0,
+                  "fused density field: F=2, <= 8 levels, MLP in->16->1 with ReLU (the nerfacto proposal networks)");
+  GridParams gp;
+  B2N_REQUIRE(fill_params(grid_host, gp) == 0, "bad grid description");
+  PosParams pp;
+  fill_pos_params(pp, contraction, aabb_host6);
+  DensityNet net{mlp_host->w[0], mlp_host->b[0], mlp_host->w[1], mlp_host->b[1], avg_init, mlp_host->in_dim};
+  RayGeom rg{origins, directions, starts, ends, bin_stride, n_rays, directions ? n_samples : 1};
+  const int64_t n = rg.n_rays * rg.n_samples;
+  const int64_t tiles = div_up(n, (int64_t)DF_THREADS * DF_CH);
+  const unsigned grid = (unsigned)min(tiles, (int64_t)b2n_sm_count() * 3);
+  cudaStream_t st = (cudaStream_t)stream;
+  DF_DISPATCH(launch_fused_bwd, (grid, st, gp, pp, net, rg, table, d_density, dtable, grad_host->dw[0], grad_host->db[0],
+                                 grad_host->dw[1], grad_host->db[1]));
+  B2N_LAUNCH_CHECK();
+}

@@ -1,5 +1,6 @@
 // K5/K6 + a8-a10/a14 — SH / frequency encodings, sample positions -> unit cube, density activation.
 #include "common.cuh"
+#include "positions.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Spherical harmonics, positive-sign basis (nerfstudio/utils/spherical_harmonics.py:24-81)
@@ -162,11 +163,6 @@ extern "C" int b2n_freq_bwd(const float* x, const float* dout, int64_t n, int32_
 // positions: o + d*(s+e)/2 -> L-inf contraction -> (p+2)/4 | aabb normalise -> selector
 // every op separately rounded like the reference's chain of torch kernels (the result feeds floor()/ceil()).
 // ---------------------------------------------------------------------------------------------
-struct PosParams {
-  int contraction;
-  float lo[3], len[3];
-};
-
 __global__ void positions_fwd_kernel(const __grid_constant__ PosParams pp, const float* __restrict__ origins,
                                      const float* __restrict__ directions, const float* __restrict__ starts,
                                      const float* __restrict__ ends, int64_t bin_stride, int64_t n_rays, int n_samples,
@@ -177,31 +173,14 @@ __global__ void positions_fwd_kernel(const __grid_constant__ PosParams pp, const
   const int s = (int)(idx - r * n_samples);
   float p[3];
   if (directions != nullptr) {
-    const float t = add_rn(__ldg(starts + r * bin_stride + s), __ldg(ends + r * bin_stride + s));
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-      p[a] = add_rn(__ldg(origins + 3 * r + a), div_rn(mul_rn(__ldg(directions + 3 * r + a), t), 2.f));
+    frustum_centre(origins + 3 * r, directions + 3 * r, __ldg(starts + r * bin_stride + s), __ldg(ends + r * bin_stride + s), p);
   } else {
 #pragma unroll
     for (int a = 0; a < 3; ++a) p[a] = __ldg(origins + 3 * idx + a);
   }
-  if (pp.contraction) {
-    const float mag = fmaxf(fabsf(p[0]), fmaxf(fabsf(p[1]), fabsf(p[2])));
-    if (!(mag < 1.f)) {
-      const float k = sub_rn(2.f, div_rn(1.f, mag));
+  const bool sel = unit_cube_point(pp, p);
 #pragma unroll
-      for (int a = 0; a < 3; ++a) p[a] = mul_rn(k, div_rn(p[a], mag));
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) p[a] = div_rn(add_rn(p[a], 2.f), 4.f);
-  } else {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) p[a] = div_rn(sub_rn(p[a], pp.lo[a]), pp.len[a]);
-  }
-  const bool sel = p[0] > 0.f && p[0] < 1.f && p[1] > 0.f && p[1] < 1.f && p[2] > 0.f && p[2] < 1.f;
-  const float m = sel ? 1.f : 0.f;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) x_out[3 * idx + a] = mul_rn(p[a], m);  // NaN * 0 = NaN, as in the reference
+  for (int a = 0; a < 3; ++a) x_out[3 * idx + a] = p[a];
   if (sel_out) sel_out[idx] = sel ? 1 : 0;
 }
 
@@ -215,11 +194,7 @@ extern "C" int b2n_positions_fwd(const float* origins, const float* directions, 
   B2N_REQUIRE(contraction || aabb_host6, "aabb required without contraction");
   B2N_REQUIRE(n_samples >= 1, "n_samples");
   PosParams pp;
-  pp.contraction = contraction;
-  for (int a = 0; a < 3; ++a) {
-    pp.lo[a] = aabb_host6 ? aabb_host6[a] : 0.f;
-    pp.len[a] = aabb_host6 ? aabb_host6[3 + a] - aabb_host6[a] : 1.f;
-  }
+  fill_pos_params(pp, contraction, aabb_host6);
   const int64_t total = n_rays * n_samples;
   if (total == 0) return B2N_OK;
   positions_fwd_kernel<<<(unsigned)div_up(total, 256), 256, 0, (cudaStream_t)stream>>>(

@@ -14,123 +14,11 @@
 
 #include "common.cuh"
 
-struct GridParams {
-  int n_levels, log2_T, mode;
-  float scale[B2N_MAX_LEVELS];
-  uint32_t resolution[B2N_MAX_LEVELS];
-  uint32_t offset[B2N_MAX_LEVELS];
-  uint32_t size[B2N_MAX_LEVELS];
-  uint32_t hashed[B2N_MAX_LEVELS];
-};
+#include "hashgrid.cuh"
 
 static int g_levels_per_block_fwd = 0;  // 0 = all levels in one thread
 static int g_levels_per_block_bwd = 1;
-
-template <int F>
-struct Vec;
-template <>
-struct Vec<1> {
-  float v[1];
-};
-template <>
-struct alignas(8) Vec<2> {
-  float v[2];
-};
-template <>
-struct alignas(16) Vec<4> {
-  float v[4];
-};
-template <>
-struct alignas(16) Vec<8> {
-  float v[8];
-};
-
-template <int F>
-__device__ __forceinline__ Vec<F> ldg_row(const float* __restrict__ table, uint32_t row) {
-  Vec<F> r;
-  const float* p = table + (size_t)row * F;
-  if constexpr (F == 1) {
-    r.v[0] = __ldg(p);
-  } else if constexpr (F == 2) {
-    float2 t = __ldg(reinterpret_cast<const float2*>(p));
-    r.v[0] = t.x, r.v[1] = t.y;
-  } else if constexpr (F == 4) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    r.v[0] = t.x, r.v[1] = t.y, r.v[2] = t.z, r.v[3] = t.w;
-  } else {
-    float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w;
-    r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
-  }
-  return r;
-}
-
-template <int F>
-__device__ __forceinline__ void red_row(float* table, uint32_t row, const float* g) {
-  float* p = table + (size_t)row * F;
-  if constexpr (F == 1) {
-    atomicAdd(p, g[0]);
-  } else if constexpr (F == 2) {
-    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(g[0]), "f"(g[1]) : "memory");
-  } else {
-#pragma unroll
-    for (int i = 0; i < F; i += 4)
-      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + i), "f"(g[i]), "f"(g[i + 1]),
-                   "f"(g[i + 2]), "f"(g[i + 3])
-                   : "memory");
-  }
-}
-
-// corner rows + lerp weights of one (point, level)
-struct Corners {
-  uint32_t row[8];
-  float ox, oy, oz;  // torch: weight of the ceil corner; tcnn: weight of the +1 corner
-};
-
-template <int MODE>
-__device__ __forceinline__ Corners corners_of(const GridParams& gp, int l, float x, float y, float z) {
-  Corners c;
-  if constexpr (MODE == B2N_GRID_TORCH) {
-    const float s = gp.scale[l];
-    const float sx = mul_rn(x, s), sy = mul_rn(y, s), sz = mul_rn(z, s);
-    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
-    const uint32_t xf = (uint32_t)(int)fx, yf = (uint32_t)(int)fy * 2654435761u, zf = (uint32_t)(int)fz * 805459861u;
-    const uint32_t xc = (uint32_t)(int)ceilf(sx), yc = (uint32_t)(int)ceilf(sy) * 2654435761u,
-                   zc = (uint32_t)(int)ceilf(sz) * 805459861u;
-    c.ox = sx - fx, c.oy = sy - fy, c.oz = sz - fz;
-    const uint32_t mask = (1u << gp.log2_T) - 1u, off = gp.offset[l];
-    c.row[0] = ((xc ^ yc ^ zc) & mask) + off;
-    c.row[1] = ((xc ^ yf ^ zc) & mask) + off;
-    c.row[2] = ((xf ^ yf ^ zc) & mask) + off;
-    c.row[3] = ((xf ^ yc ^ zc) & mask) + off;
-    c.row[4] = ((xc ^ yc ^ zf) & mask) + off;
-    c.row[5] = ((xc ^ yf ^ zf) & mask) + off;
-    c.row[6] = ((xf ^ yf ^ zf) & mask) + off;
-    c.row[7] = ((xf ^ yc ^ zf) & mask) + off;
-  } else {
-    const float s = gp.scale[l];
-    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
-    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-    c.ox = px - fx, c.oy = py - fy, c.oz = pz - fz;
-    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
-    const uint32_t size = gp.size[l], off = gp.offset[l], res = gp.resolution[l];
-    const bool hashed = gp.hashed[l] != 0;
-    // same corner order as torch mode with c = +1 corner, f = base corner
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int dx = (k == 0 || k == 1 || k == 4 || k == 5), dy = (k == 0 || k == 3 || k == 4 || k == 7), dz = (k < 4);
-      const uint32_t cx = gx + dx, cy = gy + dy, cz = gz + dz;
-      uint32_t idx;
-      if (hashed)
-        idx = (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) % size;
-      else
-        idx = (cx + cy * res + cz * res * res) % size;
-      c.row[k] = idx + off;
-    }
-  }
-  return c;
-}
+static int g_bwd_chunk = 8;  // samples per thread of the run-length backward kernel (0 = one sample per thread)
 
 template <int F, int MODE>
 __global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const __grid_constant__ GridParams gp,
@@ -244,19 +132,68 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(const __grid_constant
   }
 }
 
-static int fill_params(const B2nGrid* g, GridParams& gp) {
-  if (g->n_levels < 1 || g->n_levels > B2N_MAX_LEVELS) return -1;
-  if (g->log2_hashmap_size < 1 || g->log2_hashmap_size > 31) return -1;
-  gp.n_levels = g->n_levels, gp.log2_T = g->log2_hashmap_size, gp.mode = g->mode;
-  for (int l = 0; l < g->n_levels; ++l) {
-    gp.scale[l] = g->scale[l];
-    gp.resolution[l] = g->resolution[l];
-    gp.offset[l] = g->offset[l];
-    gp.size[l] = g->size[l] ? g->size[l] : 1u;
-    gp.hashed[l] = g->hashed[l];
+// Run-length variant of the scatter: a thread walks CH consecutive samples of one level.  Consecutive samples along a
+// ray stay in the same grid cell for many steps at the coarse levels, so the 8 corner contributions are accumulated in
+// registers while the cell does not change and flushed with one vector RED per corner when it does — this removes
+// most of the same-address atomic serialisation at L2 that dominates the proposal-grid backward once gradients
+// become dense (measured 0.60 ms -> see profiles/).
+template <int F, int MODE, int CH>
+__global__ void __launch_bounds__(256) hashgrid_bwd_runs_kernel(const __grid_constant__ GridParams gp,
+                                                                const float* __restrict__ x,
+                                                                const float* __restrict__ dy, int64_t n,
+                                                                float* __restrict__ dtable) {
+  const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i0 = chunk * CH;
+  if (i0 >= n) return;
+  const int l = blockIdx.y;
+  const int LF = gp.n_levels * F;
+  uint32_t rows[8];
+  float acc[8][F];
+  bool have = false;
+#pragma unroll 1
+  for (int s = 0; s < CH; ++s) {
+    const int64_t i = i0 + s;
+    if (i >= n) break;
+    float g[F];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      g[j] = __ldg(dy + i * LF + l * F + j);
+      any |= (g[j] != 0.f);
+    }
+    if (!any) continue;
+    const Corners c = corners_of<MODE>(gp, l, __ldg(x + 3 * i), __ldg(x + 3 * i + 1), __ldg(x + 3 * i + 2));
+    bool same = have;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) same &= (c.row[k] == rows[k]);
+    if (!same) {
+      if (have) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red_row<F>(dtable, rows[k], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        rows[k] = c.row[k];
+#pragma unroll
+        for (int j = 0; j < F; ++j) acc[k][j] = 0.f;
+      }
+      have = true;
+    }
+    const float ox = c.ox, oy = c.oy, oz = c.oz;
+    const float rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
+    const float w[8] = {ox * oy * oz, ox * ry * oz, rx * ry * oz, rx * oy * oz,
+                        ox * oy * rz, ox * ry * rz, rx * ry * rz, rx * oy * rz};
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int j = 0; j < F; ++j) acc[k][j] = fmaf(w[k], g[j], acc[k][j]);
   }
-  return 0;
+  if (have) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red_row<F>(dtable, rows[k], acc[k]);
+  }
 }
+
 
 template <int F>
 static void launch_fwd(const GridParams& gp, const float* x, const float* table, int64_t n, float* y, int64_t* idx,
@@ -269,9 +206,24 @@ static void launch_fwd(const GridParams& gp, const float* x, const float* table,
     hashgrid_fwd_kernel<F, B2N_GRID_TCNN><<<grid, 256, 0, st>>>(gp, x, table, n, y, idx, lpb);
 }
 
+template <int F, int CH>
+static void launch_bwd_runs(const GridParams& gp, const float* x, const float* dy, int64_t n, float* dtable, cudaStream_t st) {
+  dim3 grid((unsigned)div_up(div_up(n, CH), 256), (unsigned)gp.n_levels);
+  if (gp.mode == B2N_GRID_TORCH)
+    hashgrid_bwd_runs_kernel<F, B2N_GRID_TORCH, CH><<<grid, 256, 0, st>>>(gp, x, dy, n, dtable);
+  else
+    hashgrid_bwd_runs_kernel<F, B2N_GRID_TCNN, CH><<<grid, 256, 0, st>>>(gp, x, dy, n, dtable);
+}
+
 template <int F, bool DX>
 static void launch_bwd(const GridParams& gp, const float* x, const float* table, const float* dy, int64_t n,
                        float* dtable, float* dx, cudaStream_t st) {
+  if (!DX && g_bwd_chunk > 0) {
+    if (g_bwd_chunk >= 16) launch_bwd_runs<F, 16>(gp, x, dy, n, dtable, st);
+    else if (g_bwd_chunk >= 8) launch_bwd_runs<F, 8>(gp, x, dy, n, dtable, st);
+    else launch_bwd_runs<F, 4>(gp, x, dy, n, dtable, st);
+    return;
+  }
   int lpb = g_levels_per_block_bwd > 0 ? g_levels_per_block_bwd : gp.n_levels;
   dim3 grid((unsigned)div_up(n, 256), (unsigned)div_up(gp.n_levels, lpb));
   if (DX && grid.y > 1) cudaMemsetAsync(dx, 0, sizeof(float) * 3 * n, st);
@@ -330,5 +282,6 @@ extern "C" int b2n_hashgrid_bwd(const B2nGrid* grid_host, const float* x, const 
 int b2n_tune_hashgrid(const char* key, int value) {
   if (!strcmp(key, "hash_levels_per_block_fwd")) { g_levels_per_block_fwd = value; return 1; }
   if (!strcmp(key, "hash_levels_per_block_bwd")) { g_levels_per_block_bwd = value; return 1; }
+  if (!strcmp(key, "hash_bwd_chunk")) { g_bwd_chunk = value; return 1; }
   return 0;
 }

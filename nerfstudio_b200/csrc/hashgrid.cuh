@@ -1,0 +1,133 @@
+// Device helpers of the multiresolution hash grid shared by hashgrid.cu and the fused density-field kernels.
+#pragma once
+#include "common.cuh"
+
+struct GridParams {
+  int n_levels, log2_T, mode;
+  float scale[B2N_MAX_LEVELS];
+  uint32_t resolution[B2N_MAX_LEVELS];
+  uint32_t offset[B2N_MAX_LEVELS];
+  uint32_t size[B2N_MAX_LEVELS];
+  uint32_t hashed[B2N_MAX_LEVELS];
+};
+
+template <int F>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+};
+template <>
+struct alignas(8) Vec<2> {
+  float v[2];
+};
+template <>
+struct alignas(16) Vec<4> {
+  float v[4];
+};
+template <>
+struct alignas(16) Vec<8> {
+  float v[8];
+};
+
+template <int F>
+__device__ __forceinline__ Vec<F> ldg_row(const float* __restrict__ table, uint32_t row) {
+  Vec<F> r;
+  const float* p = table + (size_t)row * F;
+  if constexpr (F == 1) {
+    r.v[0] = __ldg(p);
+  } else if constexpr (F == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x, r.v[1] = t.y;
+  } else if constexpr (F == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x, r.v[1] = t.y, r.v[2] = t.z, r.v[3] = t.w;
+  } else {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w;
+    r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
+  }
+  return r;
+}
+
+template <int F>
+__device__ __forceinline__ void red_row(float* table, uint32_t row, const float* g) {
+  float* p = table + (size_t)row * F;
+  if constexpr (F == 1) {
+    atomicAdd(p, g[0]);
+  } else if constexpr (F == 2) {
+    asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(g[0]), "f"(g[1]) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < F; i += 4)
+      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + i), "f"(g[i]), "f"(g[i + 1]),
+                   "f"(g[i + 2]), "f"(g[i + 3])
+                   : "memory");
+  }
+}
+
+// corner rows + lerp weights of one (point, level)
+struct Corners {
+  uint32_t row[8];
+  float ox, oy, oz;  // torch: weight of the ceil corner; tcnn: weight of the +1 corner
+};
+
+template <int MODE>
+__device__ __forceinline__ Corners corners_of(const GridParams& gp, int l, float x, float y, float z) {
+  Corners c;
+  if constexpr (MODE == B2N_GRID_TORCH) {
+    const float s = gp.scale[l];
+    const float sx = mul_rn(x, s), sy = mul_rn(y, s), sz = mul_rn(z, s);
+    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    const uint32_t xf = (uint32_t)(int)fx, yf = (uint32_t)(int)fy * 2654435761u, zf = (uint32_t)(int)fz * 805459861u;
+    const uint32_t xc = (uint32_t)(int)ceilf(sx), yc = (uint32_t)(int)ceilf(sy) * 2654435761u,
+                   zc = (uint32_t)(int)ceilf(sz) * 805459861u;
+    c.ox = sx - fx, c.oy = sy - fy, c.oz = sz - fz;
+    const uint32_t mask = (1u << gp.log2_T) - 1u, off = gp.offset[l];
+    c.row[0] = ((xc ^ yc ^ zc) & mask) + off;
+    c.row[1] = ((xc ^ yf ^ zc) & mask) + off;
+    c.row[2] = ((xf ^ yf ^ zc) & mask) + off;
+    c.row[3] = ((xf ^ yc ^ zc) & mask) + off;
+    c.row[4] = ((xc ^ yc ^ zf) & mask) + off;
+    c.row[5] = ((xc ^ yf ^ zf) & mask) + off;
+    c.row[6] = ((xf ^ yf ^ zf) & mask) + off;
+    c.row[7] = ((xf ^ yc ^ zf) & mask) + off;
+  } else {
+    const float s = gp.scale[l];
+    const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
+    const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    c.ox = px - fx, c.oy = py - fy, c.oz = pz - fz;
+    const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    const uint32_t size = gp.size[l], off = gp.offset[l], res = gp.resolution[l];
+    const bool hashed = gp.hashed[l] != 0;
+    // same corner order as torch mode with c = +1 corner, f = base corner
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int dx = (k == 0 || k == 1 || k == 4 || k == 5), dy = (k == 0 || k == 3 || k == 4 || k == 7), dz = (k < 4);
+      const uint32_t cx = gx + dx, cy = gy + dy, cz = gz + dz;
+      uint32_t idx;
+      if (hashed)
+        idx = (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) % size;
+      else
+        idx = (cx + cy * res + cz * res * res) % size;
+      c.row[k] = idx + off;
+    }
+  }
+  return c;
+}
+
+
+static inline int fill_params(const B2nGrid* g, GridParams& gp) {
+  if (g->n_levels < 1 || g->n_levels > B2N_MAX_LEVELS) return -1;
+  if (g->log2_hashmap_size < 1 || g->log2_hashmap_size > 31) return -1;
+  gp.n_levels = g->n_levels, gp.log2_T = g->log2_hashmap_size, gp.mode = g->mode;
+  for (int l = 0; l < g->n_levels; ++l) {
+    gp.scale[l] = g->scale[l];
+    gp.resolution[l] = g->resolution[l];
+    gp.offset[l] = g->offset[l];
+    gp.size[l] = g->size[l] ? g->size[l] : 1u;
+    gp.hashed[l] = g->hashed[l];
+  }
+  return 0;
+}

@@ -54,7 +54,8 @@ class _Net:
 class NerfactoStep:
     def __init__(self, model: NerfactoModel, n_rays: int, lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-15,
                  lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
-                 always_update_proposals: bool = False, mlp_backend: str = "auto") -> None:
+                 always_update_proposals: bool = False, mlp_backend: str = "auto",
+                 fused_proposals: bool = True) -> None:
         cfg = model.config
         if cfg.implementation != "torch":
             raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
@@ -86,6 +87,7 @@ class NerfactoStep:
             return mlp_backend == "tc" or max(sp.out_dims) >= 32
 
         self.tc_net = {id(sp): use_tc(sp) for sp in specs}
+        self.fused_props = fused_proposals and all(F.density_field_supported(p_.grid, p_.spec) for p_ in self.props)
         self.tc = use_tc(self.head_spec)
         self.contraction = fld.spatial_distortion is not None
         self.aabb = fld.aabb.flatten().tolist()
@@ -161,6 +163,13 @@ class NerfactoStep:
         N = R * S
         eb = self.eb[lvl]
         box = lib.host_floats(self.aabb)
+        if self.fused_props:
+            m, _ = net.structs()
+            call("b2n_density_field_fwd", C.byref(net.grid.c), C.byref(m), ptr(net.table), ptr(self.origins),
+                 ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
+                 self.avg, ptr(self.dens[lvl]), stream())
+            call("b2n_weights_fwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), R, S, ptr(self.w[lvl]), stream())
+            return
         call("b2n_positions_fwd", ptr(self.origins), ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S,
              int(self.contraction), C.cast(box, C.c_void_p), ptr(self.x[lvl]), ptr(self.sel[lvl], torch.uint8), stream())
         call("b2n_hashgrid_fwd", C.byref(net.grid.c), ptr(self.x[lvl]), ptr(net.table), N, ptr(self.enc[lvl]), NULL, stream())
@@ -177,6 +186,13 @@ class NerfactoStep:
         eb = self.eb[lvl]
         call("b2n_weights_bwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), ptr(self.d_w[lvl]), R, S,
              ptr(self.d_dens[lvl]), stream())
+        if self.fused_props:
+            m, g = net.structs()
+            box = lib.host_floats(self.aabb)
+            call("b2n_density_field_bwd", C.byref(net.grid.c), C.byref(m), C.byref(g), ptr(net.table), ptr(self.origins),
+                 ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
+                 self.avg, ptr(self.d_dens[lvl]), ptr(net.table.grad), stream())
+            return
         call("b2n_density_act_bwd", ptr(self.h[lvl]), 1, ptr(self.sel[lvl], torch.uint8), ptr(self.d_dens[lvl]), N, self.avg,
              ptr(self.d_h[lvl]), 1, stream())
         m, g = net.structs()

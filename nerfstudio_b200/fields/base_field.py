@@ -34,6 +34,10 @@ def unit_cube_points(ray_samples, spatial_distortion, aabb: Tensor) -> Tuple[Ten
     return x, sel, iv.R, iv.S
 
 
+def is_linf_contraction(mod) -> bool:
+    return (isinstance(mod, SceneContraction) and mod.is_linf) or _is_reference_linf(mod)
+
+
 def _is_reference_linf(mod) -> bool:
     """nerfstudio's own SceneContraction(order=inf) instance (when our fields run inside unmodified models)."""
     return type(mod).__name__ == "SceneContraction" and getattr(mod, "order", None) is not None \

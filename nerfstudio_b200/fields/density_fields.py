@@ -14,7 +14,8 @@ from torch import Tensor, nn
 from .. import functional as F
 from ..field_components.encodings import HashEncoding
 from ..field_components.mlp import MLP
-from .base_field import Field, unit_cube_points
+from ..cameras.rays import ray_form
+from .base_field import Field, is_linf_contraction, unit_cube_points
 
 
 class HashMLPDensityField(Field):
@@ -42,7 +43,22 @@ class HashMLPDensityField(Field):
         else:
             self.linear = torch.nn.Linear(self.encoding.get_out_dim(), 1)
 
+    def _fused_ok(self) -> bool:
+        if self.use_linear or self.encoding.tcnn_encoding is not None:
+            return False
+        net = self.mlp_base[1]
+        linf = self.spatial_distortion is None or is_linf_contraction(self.spatial_distortion)
+        return linf and getattr(net, "_fused", False) and F.density_field_supported(self.encoding.grid, net.spec)
+
     def get_density(self, ray_samples) -> Tuple[Tensor, None]:
+        if self._fused_ok():  # one launch: samples -> unit cube -> grid -> 10->16->1 MLP -> trunc_exp
+            o, d, iv = ray_form(ray_samples)
+            net = self.mlp_base[1]
+            contraction = self.spatial_distortion is not None
+            density = F.density_field(self.encoding.grid, net.spec, self.encoding.hash_table,
+                                      [l.weight for l in net.layers], [l.bias for l in net.layers], o, d, iv, contraction,
+                                      None if contraction else self.aabb.flatten().tolist(), self.average_init_density)
+            return density.view(*ray_samples.frustums.shape, 1), None
         x, sel, R, S = unit_cube_points(ray_samples, self.spatial_distortion, self.aabb)
         if not self.use_linear:
             h = self.mlp_base(x)

@@ -372,6 +372,78 @@ def density_activation(h: Tensor, sel: Optional[Tensor], avg_init: float) -> Ten
 
 
 # ----------------------------------------------------------------------------------------
+# fused proposal density field
+# ----------------------------------------------------------------------------------------
+def density_field_supported(grid: GridSpec, spec: MlpSpec) -> bool:
+    """Shape family of the fused kernel (density_fused.cu:check_shape): F=2, <= 8 levels, MLP in->16->1, ReLU."""
+    return (grid.n_features == 2 and grid.n_levels <= 8 and spec.in_dim == 2 * grid.n_levels
+            and spec.out_dims == [16, 1] and not spec.skip and spec.hidden_act == "relu" and spec.out_act == "none")
+
+
+def _geom(origins, directions, iv):
+    o = _c(origins.float())
+    if directions is None:
+        return o, None, C.c_void_p(0), C.c_void_p(0), 0, o.shape[0], 1
+    return o, _c(directions.float()), iv.p_starts, iv.p_ends, iv.stride, iv.R, iv.S
+
+
+def density_field_forward(grid: GridSpec, spec: MlpSpec, table, weights, biases, origins, directions, iv, contraction,
+                          aabb, avg_init: float) -> Tensor:
+    """One launch: ray samples (or raw positions when directions is None) -> density [R*S]."""
+    o, d, ps, pe, stride, R, S = _geom(origins, directions, iv)
+    m = spec.struct([_c(w) for w in weights], [None if b is None else _c(b) for b in biases])
+    box = host_floats(aabb) if aabb is not None else None
+    dens = torch.empty(R * S, device=o.device, dtype=torch.float32)
+    call("b2n_density_field_fwd", C.byref(grid.c), C.byref(m), ptr(_c(table)), ptr(o), ptr(d), ps, pe, stride, R, S,
+         int(contraction), C.cast(box, C.c_void_p) if box is not None else C.c_void_p(0), float(avg_init), ptr(dens),
+         stream())
+    return dens
+
+
+def density_field_backward(grid: GridSpec, spec: MlpSpec, table, weights, biases, origins, directions, iv, contraction,
+                           aabb, avg_init: float, d_density: Tensor, dtable: Tensor, dws, dbs) -> None:
+    o, d, ps, pe, stride, R, S = _geom(origins, directions, iv)
+    m = spec.struct(weights, biases)
+    g = B2nMlpGrad()
+    for i in range(2):
+        g.dw[i] = ptr(dws[i]).value if dws[i] is not None else None
+        g.db[i] = ptr(dbs[i]).value if dbs[i] is not None else None
+    box = host_floats(aabb) if aabb is not None else None
+    call("b2n_density_field_bwd", C.byref(grid.c), C.byref(m), C.byref(g), ptr(_c(table)), ptr(o), ptr(d), ps, pe, stride,
+         R, S, int(contraction), C.cast(box, C.c_void_p) if box is not None else C.c_void_p(0), float(avg_init),
+         ptr(_c(d_density.float())), ptr(dtable), stream())
+
+
+class _DensityFieldFn(torch.autograd.Function):
+    @staticmethod
+    @_fwd
+    def forward(ctx, meta, table, w1, b1, w2, b2):
+        grid, spec, origins, directions, iv, contraction, aabb, avg = meta
+        table, w1, b1, w2, b2 = _c(table), _c(w1), _c(b1), _c(w2), _c(b2)
+        ctx.meta = meta
+        ctx.save_for_backward(table, w1, b1, w2, b2)
+        return density_field_forward(grid, spec, table, [w1, w2], [b1, b2], origins, directions, iv, contraction, aabb, avg)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, d_density):
+        grid, spec, origins, directions, iv, contraction, aabb, avg = ctx.meta
+        table, w1, b1, w2, b2 = ctx.saved_tensors
+        dtable = torch.zeros_like(table)
+        dws, dbs = [torch.zeros_like(w1), torch.zeros_like(w2)], [torch.zeros_like(b1), torch.zeros_like(b2)]
+        density_field_backward(grid, spec, table, [w1, w2], [b1, b2], origins, directions, iv, contraction, aabb, avg,
+                               d_density, dtable, dws, dbs)
+        return None, dtable, dws[0], dbs[0], dws[1], dbs[1]
+
+
+def density_field(grid, spec, table, weights, biases, origins, directions, iv, contraction, aabb, avg_init) -> Tensor:
+    """Differentiable (w.r.t. table and network) fused density field; density [R*S]."""
+    meta = (grid, spec, origins.detach(), None if directions is None else directions.detach(), iv, contraction, aabb,
+            float(avg_init))
+    return _DensityFieldFn.apply(meta, table, weights[0], biases[0], weights[1], biases[1])
+
+
+# ----------------------------------------------------------------------------------------
 # samplers
 # ----------------------------------------------------------------------------------------
 _LINSPACE_CACHE = {}

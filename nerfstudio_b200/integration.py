@@ -1,0 +1,123 @@
+"""Drop the B200 core in behind an importable nerfstudio — models run unmodified.
+
+    import nerfstudio_b200.integration as b200
+    b200.install()            # before nerfstudio models are constructed
+    # ns-train nerfacto ... / instant-ngp ... now build their fields, samplers and renderers from this package
+
+What `install()` does (each step is the binding a nerfstudio maintainer would otherwise write by hand):
+
+1. registers `nerfstudio_b200.shims.nerfacc` / `.tinycudann` as the modules `nerfacc` / `tinycudann` when the real
+   packages are not importable — nerfstudio imports `nerfacc` at module import time
+   (model_components/ray_samplers.py:24, renderers.py:34) and gates its tcnn path on `import tinycudann`
+   (utils/external.py:38-58);
+2. replaces the hot-path classes inside the reference's own modules, and re-binds the names the model files
+   imported from them (`from nerfstudio.fields.nerfacto_field import NerfactoField` binds at import time):
+   HashEncoding / SHEncoding / NeRFEncoding, MLP / MLPWithHashEncoding, trunc_exp, NerfactoField,
+   HashMLPDensityField, the samplers, RGB / accumulation / depth renderers, interlevel / distortion losses;
+3. patches `RaySamples.get_weights` (cameras/rays.py:129-152) to the warp-scan kernel.
+
+Everything replaced keeps the reference's constructor signature, attributes and state_dict keys, so configs and
+checkpoints are untouched.  `uninstall()` restores the originals.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+from typing import Dict, List, Tuple
+
+_ORIGINALS: List[Tuple[object, str, object]] = []
+
+# reference module -> {attribute: (our module, our attribute)}
+_REPLACEMENTS: Dict[str, Dict[str, Tuple[str, str]]] = {
+    "nerfstudio.field_components.encodings": {
+        "HashEncoding": ("nerfstudio_b200.field_components.encodings", "HashEncoding"),
+        "SHEncoding": ("nerfstudio_b200.field_components.encodings", "SHEncoding"),
+        "NeRFEncoding": ("nerfstudio_b200.field_components.encodings", "NeRFEncoding"),
+    },
+    "nerfstudio.field_components.mlp": {
+        "MLP": ("nerfstudio_b200.field_components.mlp", "MLP"),
+        "MLPWithHashEncoding": ("nerfstudio_b200.field_components.mlp", "MLPWithHashEncoding"),
+    },
+    "nerfstudio.field_components.activations": {
+        "trunc_exp": ("nerfstudio_b200.field_components.activations", "trunc_exp"),
+    },
+    "nerfstudio.fields.nerfacto_field": {"NerfactoField": ("nerfstudio_b200.fields.nerfacto_field", "NerfactoField")},
+    "nerfstudio.fields.density_fields": {
+        "HashMLPDensityField": ("nerfstudio_b200.fields.density_fields", "HashMLPDensityField")},
+    "nerfstudio.model_components.ray_samplers": {
+        k: ("nerfstudio_b200.model_components.ray_samplers", k)
+        for k in ("UniformSampler", "LinearDisparitySampler", "SqrtSampler", "LogSampler",
+                  "UniformLinDispPiecewiseSampler", "PDFSampler", "ProposalNetworkSampler", "VolumetricSampler")},
+    "nerfstudio.model_components.renderers": {
+        k: ("nerfstudio_b200.model_components.renderers", k)
+        for k in ("RGBRenderer", "AccumulationRenderer", "DepthRenderer")},
+    "nerfstudio.model_components.losses": {
+        k: ("nerfstudio_b200.model_components.losses", k) for k in ("interlevel_loss", "distortion_loss")},
+}
+# modules that did `from <reference module> import <name>` and therefore hold their own binding
+_REBIND_IN = ("nerfstudio.models.nerfacto", "nerfstudio.models.instant_ngp", "nerfstudio.models.vanilla_nerf",
+              "nerfstudio.models.depth_nerfacto", "nerfstudio.fields.nerfacto_field", "nerfstudio.fields.density_fields",
+              "nerfstudio.fields.vanilla_nerf_field", "nerfstudio.field_components.mlp")
+
+
+def _importable(name: str) -> bool:
+    try:
+        importlib.import_module(name)
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def _set(obj, attr: str, value) -> None:
+    _ORIGINALS.append((obj, attr, getattr(obj, attr, None)))
+    setattr(obj, attr, value)
+
+
+def install(shim_third_party: bool = True, patch_get_weights: bool = True) -> List[str]:
+    """Returns the list of `module.attribute` names that were replaced."""
+    from . import lib
+
+    lib.load()  # fail loudly if the CUDA library is not built: there is nothing to fall back to
+    done: List[str] = []
+    if shim_third_party:
+        for name, ours in (("nerfacc", "nerfstudio_b200.shims.nerfacc"), ("tinycudann", "nerfstudio_b200.shims.tinycudann")):
+            if name not in sys.modules and not _importable(name):
+                sys.modules[name] = importlib.import_module(ours)
+                done.append(f"sys.modules[{name!r}]")
+    for ref_mod_name, attrs in _REPLACEMENTS.items():
+        ref_mod = importlib.import_module(ref_mod_name)
+        for attr, (our_mod_name, our_attr) in attrs.items():
+            ours = getattr(importlib.import_module(our_mod_name), our_attr)
+            original = getattr(ref_mod, attr)
+            _set(ref_mod, attr, ours)
+            done.append(f"{ref_mod_name}.{attr}")
+            for holder_name in _REBIND_IN:
+                holder = sys.modules.get(holder_name)
+                if holder is None and _importable(holder_name):
+                    holder = sys.modules.get(holder_name)
+                if holder is not None and holder is not ref_mod and getattr(holder, attr, None) is original:
+                    _set(holder, attr, ours)
+                    done.append(f"{holder_name}.{attr}")
+    if patch_get_weights:
+        from .cameras.rays import RaySamples as OurSamples
+
+        rays = importlib.import_module("nerfstudio.cameras.rays")
+        _set(rays.RaySamples, "get_weights", OurSamples.get_weights)
+        done.append("nerfstudio.cameras.rays.RaySamples.get_weights")
+    return done
+
+
+def uninstall() -> None:
+    while _ORIGINALS:
+        obj, attr, value = _ORIGINALS.pop()
+        if value is None:
+            try:
+                delattr(obj, attr)
+            except AttributeError:
+                pass
+        else:
+            setattr(obj, attr, value)
+    for name in ("nerfacc", "tinycudann"):
+        mod = sys.modules.get(name)
+        if mod is not None and getattr(mod, "__name__", "").startswith("nerfstudio_b200.shims"):
+            del sys.modules[name]

@@ -1,0 +1,65 @@
+"""CPU, world_size 2 over gloo: the host logic of the ray-batch data-parallel path (flat gradient all-reduce,
+parameter broadcast, rank-0-only reference arm).  No CUDA calls."""
+import os
+import socket
+import subprocess
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from nerfstudio_b200 import distributed as D
+
+    r, l, w = D.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    flat = torch.full((1000,), float(rank + 1))
+    scale = D.FlatGradAllReduce()(flat)
+    params = torch.full((10,), float(rank))
+    D.broadcast_parameters(params, src=0)
+    out[rank] = (float(flat[0]), scale, float(params[0]))
+    dist.destroy_process_group()
+
+
+def test_flat_grad_allreduce_and_broadcast_world2():
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    for rank in (0, 1):
+        total, scale, p0 = out[rank]
+        assert total == 3.0      # 1 + 2: summed over ranks
+        assert scale == 0.5      # the mean is taken inside the fused Adam kernel (grad_scale)
+        assert p0 == 0.0         # every replica starts from rank 0's weights
+
+
+def test_single_process_allreduce_is_identity():
+    sys.path.insert(0, ROOT)
+    from nerfstudio_b200.distributed import FlatGradAllReduce
+
+    g = torch.arange(8.0)
+    assert FlatGradAllReduce()(g) == 1.0
+    assert torch.equal(g, torch.arange(8.0))
+
+
+def test_reference_arm_runs_on_rank0_only():
+    """`bench.py --impl reference` under a 2-rank launch: rank 0 prints the JSON line, rank 1 exits 0 silently."""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""

@@ -292,6 +292,9 @@ int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, cons
 int b2n_tc_selftest(int32_t mode, int32_t three_pass, const float* a, int32_t a_rows, int32_t a_cols, const float* b,
                     int32_t b_rows, int32_t b_cols, int32_t m, int32_t n, int32_t k, float* out128xn, void* stream);
 
+/* diagnostic: average cycles {issue, issue->completion} of n_mma back-to-back 128 x n x 8 tf32 MMAs (one CTA) */
+int b2n_tc_timing(int32_t n_mma, int32_t n, int32_t reps, long long* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(DF_THREADS) density_fused_fwd_kernel(const __g
 }
 
 template <int L, int MODE>
-__global__ void __launch_bounds__(DF_THREADS) density_fused_bwd_kernel(const __grid_constant__ GridParams gp,
+__global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const __grid_constant__ GridParams gp,
                                                                        const __grid_constant__ PosParams pp,
                                                                        const __grid_constant__ DensityNet net,
                                                                        const __grid_constant__ RayGeom rg,
@@ -151,21 +151,27 @@ __global__ void __launch_bounds__(DF_THREADS) density_fused_bwd_kernel(const __g
                                                                        float* __restrict__ db1, float* __restrict__ dw2,
                                                                        float* __restrict__ db2) {
   constexpr int IN = 2 * L;
-  constexpr int SW = DF_H + IN + 1;             // staging row: z1[16] | enc[IN] | dz2   (odd stride: conflict-free)
+  constexpr int SC = DF_H + IN;                 // staging columns: dz1[16] | enc[IN], stored column-major
+  constexpr int CSW = DF_THREADS + 4;           // column stride (+16 B: columns read together sit in different banks)
   constexpr int DW = DF_CH * IN + 1;            // per-thread d(encoding) row in shared memory (odd stride)
   extern __shared__ __align__(16) float dyn_smem[];
-  float* stage = dyn_smem;                       // [DF_THREADS][SW]
-  float* denc = dyn_smem + DF_THREADS * SW;      // [DF_THREADS][DW]
+  float* stage = dyn_smem;                       // [SC][CSW]
+  float* denc = dyn_smem + SC * CSW;             // [DF_THREADS][DW]
   __shared__ __align__(16) float ws[DF_NET_FLOATS];
+  __shared__ float red2[DF_H + 1];
   stage_net(net, ws);
   const int t = threadIdx.x;
   const int64_t n = rg.n_rays * rg.n_samples;
   const int64_t n_tiles = (n + DF_THREADS * DF_CH - 1) / (DF_THREADS * DF_CH);
   // weight-gradient owners (one register accumulator each, kept across all tiles of the CTA):
-  //   t in [0, H*IN)            dW1[j][c],   then H threads db1[j], then H threads dW2[j], then one thread db2
+  //   t in [0, H*IN) owns dW1[j][c], the next H threads own db1[j]; dW2 / db2 are accumulated per thread
   const int oj = t / IN, oc = t - oj * IN;
-  const int role = t < DF_H * IN ? 0 : t < DF_H * IN + DF_H ? 1 : t < DF_H * IN + 2 * DF_H ? 2 : t == DF_H * IN + 2 * DF_H ? 3 : 4;
+  const int role = t < DF_H * IN ? 0 : t < DF_H * IN + DF_H ? 1 : 2;
   float own_acc = 0.f;
+  float g2[DF_H + 1];
+#pragma unroll
+  for (int j = 0; j <= DF_H; ++j) g2[j] = 0.f;
+  if (t <= DF_H) red2[t] = 0.f;
   __syncthreads();
   float* my_denc = denc + t * DW;
 
@@ -175,23 +181,25 @@ __global__ void __launch_bounds__(DF_THREADS) density_fused_bwd_kernel(const __g
 #pragma unroll
     for (int s = 0; s < DF_CH; ++s) {
       const int64_t i = i0 + s;
-      float* row = stage + t * SW;
       float dz2 = 0.f;
-      if (i < n) {
+      // samples that receive no gradient (outside the selector, or d_density == 0: most of a ray under the
+      // interlevel loss) contribute exact zeros everywhere: skip their gather and network evaluation
+      const float g = (i < n) ? __ldg(d_density + i) : 0.f;
+      if (g != 0.f) {
         Sample<L> sm;
         encode_sample<L, MODE>(gp, pp, rg, table, i, sm);
         float z1[DF_H];
         const float z2 = mlp_forward<L>(ws, sm.enc, z1);
-        const float g = __ldg(d_density + i);
         // density = avg * exp(z2) * sel ; trunc_exp backward clamps the exponent (activations.py:36-41)
-        if (sm.sel && g != 0.f) dz2 = g * net.avg_init * expf(fminf(fmaxf(z2, -15.f), 15.f));
+        if (sm.sel) dz2 = g * net.avg_init * expf(fminf(fmaxf(z2, -15.f), 15.f));
         float de[IN];
 #pragma unroll
         for (int c = 0; c < IN; ++c) de[c] = 0.f;
 #pragma unroll
         for (int j = 0; j < DF_H; ++j) {
-          row[j] = z1[j];
+          g2[j] = fmaf(dz2, fmaxf(z1[j], 0.f), g2[j]);
           const float d = z1[j] > 0.f ? dz2 * ws[DF_H * DF_W1S + DF_H + j] : 0.f;
+          stage[j * CSW + t] = d;
           const float4* wr = reinterpret_cast<const float4*>(ws + j * DF_W1S);
 #pragma unroll
           for (int q = 0; q < (IN + 3) / 4; ++q) {
@@ -202,46 +210,39 @@ __global__ void __launch_bounds__(DF_THREADS) density_fused_bwd_kernel(const __g
             if (4 * q + 3 < IN) de[4 * q + 3 < IN ? 4 * q + 3 : 0] = fmaf(d, w.w, de[4 * q + 3 < IN ? 4 * q + 3 : 0]);
           }
         }
+        g2[DF_H] += dz2;
 #pragma unroll
-        for (int c = 0; c < IN; ++c) row[DF_H + c] = sm.enc[c], my_denc[s * IN + c] = de[c];
+        for (int c = 0; c < IN; ++c) stage[(DF_H + c) * CSW + t] = sm.enc[c], my_denc[s * IN + c] = de[c];
 #pragma unroll
         for (int a = 0; a < 3; ++a) xs[s][a] = sm.x[a];
       } else {
+#pragma unroll
+        for (int j = 0; j < SC; ++j) stage[j * CSW + t] = 0.f;
 #pragma unroll
         for (int c = 0; c < IN; ++c) my_denc[s * IN + c] = 0.f;
 #pragma unroll
         for (int a = 0; a < 3; ++a) xs[s][a] = 0.f;
       }
-      row[DF_H + IN] = dz2;
       __syncthreads();
-      // ---- the owners reduce their product over this round's 256 staged samples
+      // ---- the owners reduce their product over this round's 256 staged samples (128-bit column reads)
       if (role == 0) {
-        const float w2j = ws[DF_H * DF_W1S + DF_H + oj];
+        const float4* zc = reinterpret_cast<const float4*>(stage + oj * CSW);
+        const float4* ec = reinterpret_cast<const float4*>(stage + (DF_H + oc) * CSW);
         float a = 0.f;
 #pragma unroll 8
-        for (int q = 0; q < DF_THREADS; ++q) {
-          const float* r_ = stage + q * SW;
-          const float d = r_[oj] > 0.f ? r_[DF_H + IN] * w2j : 0.f;
-          a = fmaf(d, r_[DF_H + oc], a);
+        for (int q = 0; q < DF_THREADS / 4; ++q) {
+          const float4 z = zc[q], e = ec[q];
+          a = fmaf(z.x, e.x, a), a = fmaf(z.y, e.y, a), a = fmaf(z.z, e.z, a), a = fmaf(z.w, e.w, a);
         }
         own_acc += a;
       } else if (role == 1) {
-        const int j = t - DF_H * IN;
-        const float w2j = ws[DF_H * DF_W1S + DF_H + j];
+        const float4* zc = reinterpret_cast<const float4*>(stage + (t - DF_H * IN) * CSW);
         float a = 0.f;
 #pragma unroll 8
-        for (int q = 0; q < DF_THREADS; ++q) a += stage[q * SW + j] > 0.f ? stage[q * SW + DF_H + IN] * w2j : 0.f;
-        own_acc += a;
-      } else if (role == 2) {
-        const int j = t - DF_H * IN - DF_H;
-        float a = 0.f;
-#pragma unroll 8
-        for (int q = 0; q < DF_THREADS; ++q) a = fmaf(stage[q * SW + DF_H + IN], fmaxf(stage[q * SW + j], 0.f), a);
-        own_acc += a;
-      } else if (role == 3) {
-        float a = 0.f;
-#pragma unroll 8
-        for (int q = 0; q < DF_THREADS; ++q) a += stage[q * SW + DF_H + IN];
+        for (int q = 0; q < DF_THREADS / 4; ++q) {
+          const float4 z = zc[q];
+          a += (z.x + z.y) + (z.z + z.w);
+        }
         own_acc += a;
       }
       __syncthreads();
@@ -284,8 +285,14 @@ __global__ void __launch_bounds__(DF_THREADS) density_fused_bwd_kernel(const __g
   // ---- flush the weight gradients: one atomic per entry per CTA
   if (role == 0 && dw1) atomicAdd(dw1 + oj * IN + oc, own_acc);
   if (role == 1 && db1) atomicAdd(db1 + (t - DF_H * IN), own_acc);
-  if (role == 2 && dw2) atomicAdd(dw2 + (t - DF_H * IN - DF_H), own_acc);
-  if (role == 3 && db2) atomicAdd(db2, own_acc);
+#pragma unroll
+  for (int j = 0; j <= DF_H; ++j) {
+    const float v = warp_sum(g2[j]);
+    if ((t & 31) == 0) atomicAdd(&red2[j], v);
+  }
+  __syncthreads();
+  if (t < DF_H && dw2) atomicAdd(dw2 + t, red2[t]);
+  if (t == DF_H && db2) atomicAdd(db2, red2[DF_H]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -301,7 +308,7 @@ template <int L, int MODE>
 static void launch_fused_bwd(unsigned grid, cudaStream_t st, const GridParams& gp, const PosParams& pp, const DensityNet& net,
                              const RayGeom& rg, const float* table, const float* d_density, float* dtable, float* dw1,
                              float* db1, float* dw2, float* db2) {
-  constexpr size_t smem = sizeof(float) * DF_THREADS * ((DF_H + 2 * L + 1) + (DF_CH * 2 * L + 1));
+  constexpr size_t smem = sizeof(float) * ((DF_H + 2 * L) * (DF_THREADS + 4) + DF_THREADS * (DF_CH * 2 * L + 1));
   auto kernel = density_fused_bwd_kernel<L, MODE>;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, dtable, dw1, db1, dw2, db2);

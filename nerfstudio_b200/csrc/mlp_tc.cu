@@ -7,8 +7,8 @@
 // so the 1e-4 parity bar holds.  The tensor pipe is nowhere near its limit on K,N <= 64; what the kernel buys is
 // that the 2.1 ms/step the SIMT kernels spend in FFMA disappears into operand staging.
 //
-// Structure (one persistent CTA of 256 threads per SM; threads t and t+128 own row t&127 of the 128-row tile
-// (== TMEM lane) and split its columns in halves — warps w and w+4 share TMEM quarter w&3):
+// Structure (one persistent CTA of 512 threads per SM; threads t, t+128, t+256, t+384 own row t&127 of the tile
+// (== TMEM lane) and its columns are split 4 ways — warps w, w+4, w+8, w+12 share TMEM quarter w&3 (16 warps/SM):
 //   forward  : x row -> hi/lo -> smem (K-major canonical, float4 stores) -> per layer: thread 0 issues the MMAs,
 //              tcgen05.commit -> mbarrier; everyone tcgen05.ld's their row, bias + activation, saves the hidden
 //              row (row-major) for backward, writes the next layer's operand.
@@ -60,8 +60,8 @@ __device__ __forceinline__ float tc_act_grad(int act, float y) {
   return 1.f;
 }
 
-#define TC_THREADS 256  // 8 warps: warp w and w+4 share TMEM quarter w&3 and split the tile's columns in halves
-#define TC_HALF 32
+#define TC_THREADS 512  // 16 warps: warps w, w+4, w+8, w+12 share TMEM quarter w&3 and split the tile's 64 columns
+#define TC_HALF 16     // columns per thread
 
 // write this thread's half row (32 columns starting at c0; zero beyond width_pad) as hi/lo into a K-major tile pair
 __device__ __forceinline__ void store_half_hilo(uint8_t* hi, uint8_t* lo, int r, int c0, const float (&v)[TC_HALF],
@@ -174,13 +174,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
         const uint32_t cs = (uint32_t)N * 16u;
         const uint32_t wh = tc::smem_u32(Wr + p.w_off[l]), wl = wh + p.w_bytes[l];
         const uint32_t ah = tc::smem_u32(Ah), al = tc::smem_u32(Al);
+        // descriptors differ between k-steps only in the start-address field (bits 0-13, units of 16 B)
+        const uint64_t da = (uint64_t)((2 * TC_CS_A) >> 4), db = (uint64_t)((2 * cs) >> 4);
         uint32_t acc = 0;
-#pragma unroll 1
+#pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = (pass == 1) ? al : ah, b0 = (pass == 2) ? wl : wh;
+          uint64_t ad = tc::make_desc((pass == 1) ? al : ah, TC_CS_A, 128), bd = tc::make_desc((pass == 2) ? wl : wh, cs, 128);
+#pragma unroll 2
           for (int s = 0; s < K / 8; ++s) {
-            tc::mma_tf32(tmem, tc::make_desc(a0 + s * 2 * TC_CS_A, TC_CS_A, 128), tc::make_desc(b0 + s * 2 * cs, cs, 128),
-                         idesc, acc);
+            tc::mma_tf32(tmem, ad, bd, idesc, acc);
+            ad += da, bd += db;
             acc = 1;
           }
         }
@@ -325,12 +328,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
           const uint32_t tz = tc::smem_u32(TZ), tah = tc::smem_u32(TAh), tal = tc::smem_u32(TAl);
           const uint32_t dcol = tmem + (uint32_t)(DW_COL0 + DW_COLS * l);
           uint32_t acc = (dw_started >> l) & 1u;
-#pragma unroll 1
+#pragma unroll
           for (int pass = 0; pass < 2; ++pass) {
-            const uint32_t b0 = pass ? tal : tah;
+            uint64_t ad = tc::make_desc(tz, TC_CS_TZ, 128), bd = tc::make_desc(pass ? tal : tah, TC_CS_TA, 128);
+#pragma unroll
             for (int s = 0; s < 8; ++s) {
-              tc::mma_tf32(dcol, tc::make_desc(tz + s * 2 * TC_CS_TZ, TC_CS_TZ, 128),
-                           tc::make_desc(b0 + s * 2 * TC_CS_TA, TC_CS_TA, 128), idesc, acc);
+              tc::mma_tf32(dcol, ad, bd, idesc, acc);
+              ad += (uint64_t)((2 * TC_CS_TZ) >> 4), bd += (uint64_t)((2 * TC_CS_TA) >> 4);
               acc = 1;
             }
           }
@@ -341,12 +345,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
             const uint32_t wh = tc::smem_u32(Wr + p.w_off[l]), wl = wh + p.w_bytes[l];
             const uint32_t zh = tc::smem_u32(Zh), zl = tc::smem_u32(Zl);
             uint32_t acc2 = 0;
-#pragma unroll 1
+#pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
-              const uint32_t a0 = (pass == 1) ? zl : zh, b0 = (pass == 2) ? wl : wh;
+              uint64_t ad = tc::make_desc((pass == 1) ? zl : zh, TC_CS_A, 128), bd = tc::make_desc((pass == 2) ? wl : wh, cs, 128);
+#pragma unroll 2
               for (int s = 0; s < N / 8; ++s) {
-                tc::mma_tf32(tmem, tc::make_desc(a0 + s * 2 * TC_CS_A, TC_CS_A, 128), tc::make_desc(b0 + s * 2 * cs, cs, 128),
-                             idx, acc2);
+                tc::mma_tf32(tmem, ad, bd, idx, acc2);
+                ad += (uint64_t)((2 * TC_CS_A) >> 4), bd += (uint64_t)((2 * cs) >> 4);
                 acc2 = 1;
               }
             }
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
     const int K = p.K[l], kr = p.kr[l], nr = p.nr[l];
     const int j = r & 63;
     const bool started = blockIdx.x < n_tiles;
-    for (int cc = c0 ? 48 : 0; cc < (c0 ? K + 16 : min(48, K + 16)); cc += 16) {  // warp-uniform column ranges
+    for (int cc = c0; cc < K + 16; cc += 64) {  // warp-uniform: column group c0/16 takes chunks c0, c0+64
       float v[16];
       tc::ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(DW_COL0 + DW_COLS * l + cc), v);
       if (!started || j >= nr) continue;

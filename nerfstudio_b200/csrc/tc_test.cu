@@ -101,3 +101,57 @@ extern "C" int b2n_tc_selftest(int32_t mode, int32_t three_pass, const float* a,
                                                              out128xn);
   B2N_LAUNCH_CHECK();
 }
+
+// Timing probe: cycles from the first tcgen05.mma issue to the mbarrier completion for `n_mma` back-to-back
+// M=128 x N x K=8 tf32 MMAs on zeroed operands (development aid for the MLP kernels' pipeline model).
+__global__ void __launch_bounds__(128) tc_timing_kernel(int n_mma, int N, int reps, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  for (int i = t; i < 2 * 16 * 2048 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
+  if (t == 0) tc::mbar_init(&bar, 1);
+  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  tc::fence_smem_to_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  uint32_t phase = 0;
+  long long issue = 0, total = 0;
+  for (int rep = 0; rep < reps; ++rep) {
+    __syncthreads();
+    const long long t0 = clock64();
+    long long t1 = t0;
+    if (t == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(128, N, false, false);
+      const uint32_t a = tc::smem_u32(smem), b = a + 16 * 2048;
+      uint64_t ad = tc::make_desc(a, 2048, 128), bd = tc::make_desc(b, 1024, 128);
+#pragma unroll 2
+      for (int j = 0; j < n_mma; ++j) {
+        tc::mma_tf32(tmem, ad, bd, idesc, j > 0);
+        ad += ((j & 7) == 7) ? (uint64_t)0 - 7 * ((2 * 2048) >> 4) : (uint64_t)((2 * 2048) >> 4);
+        bd += ((j & 7) == 7) ? (uint64_t)0 - 7 * ((2 * 1024) >> 4) : (uint64_t)((2 * 1024) >> 4);
+      }
+      tc::commit(&bar);
+      t1 = clock64();
+    }
+    tc::mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+    const long long t2 = clock64();
+    if (rep > 0) issue += t1 - t0, total += t2 - t0;
+  }
+  if (t == 0) out[0] = issue / (reps - 1), out[1] = total / (reps - 1);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<64>(tmem);
+}
+
+extern "C" int b2n_tc_timing(int32_t n_mma, int32_t n, int32_t reps, long long* out2, void* stream) {
+  B2N_REQUIRE(out2 && n_mma >= 1 && reps >= 2 && n % 16 == 0 && n >= 16 && n <= 64, "bad arguments");
+  const size_t smem = 2 * 16 * 2048;
+  cudaFuncSetAttribute(tc_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, n, reps, out2);
+  B2N_LAUNCH_CHECK();
+}

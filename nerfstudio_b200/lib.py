@@ -83,6 +83,7 @@ _SIGNATURES = {
     "b2n_density_field_bwd": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _P, _I64, _I64,
                               _I32, _I32, _P, _F, _P, _P, _P],
     "b2n_tc_selftest": [_I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _P],
+    "b2n_tc_timing": [_I32, _I32, _I32, _P, _P],
     "b2n_adam_step_dev": [_P, _P, _P, _P, _I64, _P, C.c_double, C.c_double, C.c_double, _P],
     "b2n_head_input_fwd": [_P, _I32, _P, _I32, _I32, _P, _P, _I32, _I32, _I64, _I32, _P, _I32, _P],
     "b2n_head_input_bwd": [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _P],

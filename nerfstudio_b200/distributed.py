@@ -38,6 +38,20 @@ class FlatGradAllReduce:
             dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
         return 1.0 / self.world
 
+    def start(self, segment: torch.Tensor):
+        """Launch the sum of one contiguous segment asynchronously (NCCL runs it on its own stream, ordered after
+        the work already enqueued on the current stream) so that it overlaps whatever is enqueued next."""
+        if self.world <= 1:
+            return None
+        return dist.all_reduce(segment, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    @staticmethod
+    def finish(*handles) -> None:
+        """Make the current stream wait for the collectives started with `start`."""
+        for h in handles:
+            if h is not None:
+                h.wait()
+
 
 def broadcast_parameters(flat_params: torch.Tensor, src: int = 0, group=None) -> None:
     """Make every replica start from rank `src`'s weights (what DDP's constructor does)."""

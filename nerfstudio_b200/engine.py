@@ -64,6 +64,12 @@ class NerfactoStep:
         self.model, self.cfg, self.R = model, cfg, n_rays
         self.optim = FlatAdam(model, lr=lr, betas=betas, eps=eps, lr_schedule=lr_schedule)
         self.allreduce, self.use_graph = allreduce, use_graph
+        prop_ids = {id(p) for p in model.proposal_networks.parameters()}
+        firsts = [off for p, off in zip(self.optim.params, self.optim.offsets) if id(p) in prop_ids]
+        lasts = [off for p, off in zip(self.optim.params, self.optim.offsets) if id(p) not in prop_ids]
+        # flat layout is [field parameters | proposal parameters] (module registration order); fall back to one
+        # segment if a model orders them differently
+        self.grad_split = min(firsts) if firsts and lasts and min(firsts) > max(lasts) else self.optim.flat.numel()
         self.always_update = always_update_proposals
         dev = self.optim.flat.device
         self.dev = dev
@@ -269,11 +275,13 @@ class NerfactoStep:
                       self.d_enc[2].shape[1], self.base.spec)
         call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
              ptr(self.base.table.grad), NULL, st())
-        # ---------------- backward: proposal networks (only the interlevel loss reaches them)
+        self.losses[3:4].copy_(self.losses[0:3].sum(0, keepdim=True))
+
+    def _body_props(self, update_props: bool) -> None:
+        """backward of the proposal networks (only the interlevel loss reaches them)."""
         if update_props:
             for lvl in (0, 1):
                 self._density_net_bwd(lvl, self.props[lvl], None)
-        self.losses[3:4].copy_(self.losses[0:3].sum(0, keepdim=True))
 
     def _adam(self) -> None:
         o = self.optim
@@ -314,18 +322,26 @@ class NerfactoStep:
         self.hyper_host[3] = self._anneal(t)
         self.hyper.copy_(self.hyper_host, non_blocking=True)
         update = self._update_due(t)
-        if not self.use_graph:
-            self._body(update)
-            if self.allreduce is not None:
-                self.allreduce(o.flat_grad)
-            self._adam()
-        else:
-            if update not in self._graphs:
-                self._capture(update)
-            self._graphs[update][0].replay()
-            if self.allreduce is not None and world > 1:
-                self.allreduce(o.flat_grad)
-            self._graphs[update][1].replay()
+        overlap = self.allreduce is not None and world > 1
+        if self.use_graph and update not in self._graphs:
+            self._capture(update)
+        def run(i: int) -> None:
+            if self.use_graph:
+                g = self._graphs[update][i]
+                if g is not None:
+                    g.replay()
+            else:
+                (self._body, self._body_props, lambda _u: self._adam())[i](update)
+
+        # [forward + losses + main-field backward] -> start summing the field's gradient segment over NVLink while
+        # the [proposal backward] runs -> sum the proposal segment -> [Adam].  One process per GPU, two collectives.
+        run(0)
+        h_field = self.allreduce.start(o.flat_grad[: self.grad_split]) if overlap else None
+        run(1)
+        h_prop = self.allreduce.start(o.flat_grad[self.grad_split:]) if overlap else None
+        if overlap:
+            self.allreduce.finish(h_field, h_prop)
+        run(2)
         if update:
             self._steps_since_update = 0
         self._steps_since_update += 1
@@ -340,14 +356,20 @@ class NerfactoStep:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             self._body(update)
+            self._body_props(update)
             self._adam()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         for dst, src in zip((self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq), saved):
             dst.copy_(src)  # the warm-up pass must not count as an optimisation step
-        g_main, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        g_main, g_props, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_main):
             self._body(update)
+        if update:
+            with torch.cuda.graph(g_props, pool=g_main.pool()):
+                self._body_props(update)
+        else:
+            g_props = None  # nothing to replay when the proposal networks are frozen this step
         with torch.cuda.graph(g_adam, pool=g_main.pool()):
             self._adam()
-        self._graphs[update] = (g_main, g_adam)
+        self._graphs[update] = (g_main, g_props, g_adam)

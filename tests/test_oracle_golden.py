@@ -266,3 +266,26 @@ def test_full_nerfacto_pipeline(golden):
             grads = torch.autograd.grad(out["loss"], list(named.values()))
             for k, gr in zip(named, grads):
                 assert_close(gr, g["g_" + k], 1e-5, "g_" + k)
+
+
+def test_c_restatement_of_hash_indices(golden):
+    """oracle/hash_index.c (plain C, int64 arithmetic) == indices recorded from the reference, bit for bit."""
+    import ctypes
+    import os
+    import subprocess
+
+    import numpy as np
+
+    odir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    subprocess.run(["make", "-s", "-C", odir], check=True)
+    lib = ctypes.CDLL(os.path.join(odir, "libhash_index.so"))
+    g = golden("hash_encoding")
+    for nm in ("small", "f4", "mid"):
+        L, lo, hi, log2T, F = (int(v) for v in g[f"{nm}_cfg"])
+        x = np.ascontiguousarray(g[f"{nm}_x"].numpy(), dtype=np.float32)
+        sc = np.ascontiguousarray(g[f"{nm}_scalings"].numpy(), dtype=np.float32)
+        out = np.zeros((x.shape[0], L, 8), dtype=np.int64)
+        lib.hash_corner_indices(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(x.shape[0]),
+                                sc.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(L), ctypes.c_int32(log2T),
+                                out.ctypes.data_as(ctypes.c_void_p))
+        assert np.array_equal(out, g[f"{nm}_idx"].numpy()), nm

@@ -182,16 +182,14 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
     for (int s = 0; s < DF_CH; ++s) {
       const int64_t i = i0 + s;
       float dz2 = 0.f;
-      // samples that receive no gradient (outside the selector, or d_density == 0: most of a ray under the
-      // interlevel loss) contribute exact zeros everywhere: skip their gather and network evaluation
-      const float g = (i < n) ? __ldg(d_density + i) : 0.f;
-      if (g != 0.f) {
+      if (i < n) {
         Sample<L> sm;
         encode_sample<L, MODE>(gp, pp, rg, table, i, sm);
         float z1[DF_H];
         const float z2 = mlp_forward<L>(ws, sm.enc, z1);
+        const float g = __ldg(d_density + i);
         // density = avg * exp(z2) * sel ; trunc_exp backward clamps the exponent (activations.py:36-41)
-        if (sm.sel) dz2 = g * net.avg_init * expf(fminf(fmaxf(z2, -15.f), 15.f));
+        if (sm.sel && g != 0.f) dz2 = g * net.avg_init * expf(fminf(fmaxf(z2, -15.f), 15.f));
         float de[IN];
 #pragma unroll
         for (int c = 0; c < IN; ++c) de[c] = 0.f;

@@ -157,12 +157,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
   const bool xvec = ((x_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
 
   const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+  float vnext[TC_HALF];  // next tile's input slice, loaded a whole tile ahead so its DRAM latency is never exposed
+  {
+    const int64_t row0 = (int64_t)blockIdx.x * TC_ROWS + r;
+    load_global_half(x + row0 * x_stride, blockIdx.x < n_tiles && row0 < n, xvec, c0, p.in_dim, p.in_pad, vnext);
+  }
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = tile * TC_ROWS + r;
     const bool live = row < n;
     float v[TC_HALF];
-    load_global_half(x + row * x_stride, live, xvec, c0, p.in_dim, p.in_pad, v);
+#pragma unroll
+    for (int c = 0; c < TC_HALF; ++c) v[c] = vnext[c];
     store_half_hilo(Ah, Al, r, c0, v, p.in_pad);
+    {
+      const int64_t nrow = (tile + gridDim.x) * TC_ROWS + r;
+      load_global_half(x + nrow * x_stride, tile + gridDim.x < n_tiles && nrow < n, xvec, c0, p.in_dim, p.in_pad, vnext);
+    }
     for (int l = 0; l < p.n_layers; ++l) {
       const int N = p.N[l], K = p.K[l];
       tc::fence_smem_to_async();
@@ -285,10 +295,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
         dz[c] = g;
       }
     }
+    float a_next[TC_HALF];  // the input row slice of the NEXT layer to be processed (one layer of lookahead)
+    {
+      const int l = L - 1, kr = p.kr[l];
+      if (l == 0) load_global_half(x + row * x_stride, live, xvec, c0, kr, p.K[l], a_next);
+      else load_global_half(hidden + p.hid_off[l - 1] * n + row * (int64_t)kr, live, (kr & 3) == 0, c0, kr, p.K[l], a_next);
+    }
     for (int l = L - 1; l >= 0; --l) {
       const int N = p.N[l], K = p.K[l], kr = p.kr[l];
-      if (l == 0) load_global_half(x + row * x_stride, live, xvec, c0, kr, K, a);
-      else load_global_half(hidden + p.hid_off[l - 1] * n + row * (int64_t)kr, live, (kr & 3) == 0, c0, kr, K, a);
+#pragma unroll
+      for (int c = 0; c < TC_HALF; ++c) a[c] = a_next[c];
+      if (l > 0) {
+        const int l2 = l - 1, kr2 = p.kr[l2];
+        if (l2 == 0) load_global_half(x + row * x_stride, live, xvec, c0, kr2, p.K[l2], a_next);
+        else load_global_half(hidden + p.hid_off[l2 - 1] * n + row * (int64_t)kr2, live, (kr2 & 3) == 0, c0, kr2, p.K[l2], a_next);
+      }
       const bool need_da = (l > 0) || (dx != nullptr);
       if (need_da) store_half_hilo(Zh, Zl, r, c0, dz, N);
       // ---- dW_l += dZ^T A over the two 64-point halves of the tile

@@ -102,16 +102,18 @@ extern "C" int b2n_tc_selftest(int32_t mode, int32_t three_pass, const float* a,
   B2N_LAUNCH_CHECK();
 }
 
-// Timing probe: cycles from the first tcgen05.mma issue to the mbarrier completion for `n_mma` back-to-back
-// M=128 x N x K=8 tf32 MMAs on zeroed operands (development aid for the MLP kernels' pipeline model).
-__global__ void __launch_bounds__(128) tc_timing_kernel(int n_mma, int N, int reps, long long* __restrict__ out) {
+// Timing probe: cycles from the first tcgen05.mma issue to completion for `n_mma` M=128 x N x K=8 tf32 MMAs split
+// over `n_issuers` threads (lane 0 of warps 0..n_issuers-1), each with its own accumulator and mbarrier
+// (development aid for the MLP kernels' pipeline model).
+__global__ void __launch_bounds__(128) tc_timing_kernel(int n_mma, int N, int reps, int n_issuers, long long* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar[4];
   __shared__ uint32_t tmem_slot;
   const int t = threadIdx.x, warp = t >> 5;
   for (int i = t; i < 2 * 16 * 2048 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 1.0f;
-  if (t == 0) tc::mbar_init(&bar, 1);
-  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  if (t == 0)
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bar[i], 1);
+  if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
   tc::fence_smem_to_async();
   tc::fence_before_sync();
   __syncthreads();
@@ -119,24 +121,25 @@ __global__ void __launch_bounds__(128) tc_timing_kernel(int n_mma, int N, int re
   const uint32_t tmem = tmem_slot;
   uint32_t phase = 0;
   long long issue = 0, total = 0;
+  const int per = n_mma / n_issuers;
   for (int rep = 0; rep < reps; ++rep) {
     __syncthreads();
     const long long t0 = clock64();
     long long t1 = t0;
-    if (t == 0) {
+    if ((t & 31) == 0 && warp < n_issuers) {
       const uint32_t idesc = tc::make_idesc_tf32(128, N, false, false);
       const uint32_t a = tc::smem_u32(smem), b = a + 16 * 2048;
       uint64_t ad = tc::make_desc(a, 2048, 128), bd = tc::make_desc(b, 1024, 128);
 #pragma unroll 2
-      for (int j = 0; j < n_mma; ++j) {
-        tc::mma_tf32(tmem, ad, bd, idesc, j > 0);
+      for (int j = 0; j < per; ++j) {
+        tc::mma_tf32(tmem + warp * 64, ad, bd, idesc, j > 0);
         ad += ((j & 7) == 7) ? (uint64_t)0 - 7 * ((2 * 2048) >> 4) : (uint64_t)((2 * 2048) >> 4);
         bd += ((j & 7) == 7) ? (uint64_t)0 - 7 * ((2 * 1024) >> 4) : (uint64_t)((2 * 1024) >> 4);
       }
-      tc::commit(&bar);
+      tc::commit(&bar[warp]);
       t1 = clock64();
     }
-    tc::mbar_wait(&bar, phase);
+    for (int i = 0; i < n_issuers; ++i) tc::mbar_wait(&bar[i], phase);
     phase ^= 1;
     tc::fence_after_sync();
     const long long t2 = clock64();
@@ -145,13 +148,16 @@ __global__ void __launch_bounds__(128) tc_timing_kernel(int n_mma, int N, int re
   if (t == 0) out[0] = issue / (reps - 1), out[1] = total / (reps - 1);
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<64>(tmem);
+  if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
 extern "C" int b2n_tc_timing(int32_t n_mma, int32_t n, int32_t reps, long long* out2, void* stream) {
-  B2N_REQUIRE(out2 && n_mma >= 1 && reps >= 2 && n % 16 == 0 && n >= 16 && n <= 64, "bad arguments");
+  // n_mma's upper byte selects the number of issuing threads (0 -> 1)
+  const int issuers = (n_mma >> 24) ? (n_mma >> 24) : 1;
+  n_mma &= 0xFFFFFF;
+  B2N_REQUIRE(out2 && n_mma >= 1 && reps >= 2 && n % 16 == 0 && n >= 16 && n <= 64 && issuers <= 4, "bad arguments");
   const size_t smem = 2 * 16 * 2048;
   cudaFuncSetAttribute(tc_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, n, reps, out2);
+  tc_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n_mma, n, reps, issuers, out2);
   B2N_LAUNCH_CHECK();
 }

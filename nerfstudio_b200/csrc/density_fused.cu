@@ -86,7 +86,8 @@ __device__ __forceinline__ void encode_sample(const GridParams& gp, const PosPar
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const Corners c = corners_of<MODE>(gp, l, sm.x[0], sm.x[1], sm.x[2]);
-    Vec<2> f[8];
+    Vec<2> f[8];  // plain 64-bit loads: on the coarse proposal grids a warp's corners already share sectors, and the
+                  // paired 128-bit path of hashgrid.cuh only adds divergence here (measured 0.42 -> 0.58 ms backward)
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = ldg_row<2>(table, c.row[k]);
     const float ox = c.ox, oy = c.oy, oz = c.oz, rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;

@@ -16,7 +16,7 @@
 
 #include "hashgrid.cuh"
 
-static int g_levels_per_block_fwd = 0;  // 0 = all levels in one thread
+static int g_levels_per_block_fwd = 4;  // levels looped per thread (blockIdx.y picks the group); 0 = all
 static int g_levels_per_block_bwd = 1;
 static int g_bwd_chunk = 8;  // samples per thread of the run-length backward kernel (0 = one sample per thread)
 
@@ -36,8 +36,12 @@ __global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const __grid_constant
   for (int l = l0; l < l1; ++l) {
     const Corners c = corners_of<MODE>(gp, l, px, py, pz);
     Vec<F> f[8];
+    if constexpr (F == 2) {
+      gather_corners2(table, c, f);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = ldg_row<F>(table, c.row[k]);
+      for (int k = 0; k < 8; ++k) f[k] = ldg_row<F>(table, c.row[k]);
+    }
     if (idx_out != nullptr) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) idx_out[(i * gp.n_levels + l) * 8 + k] = (int64_t)c.row[k];
@@ -149,7 +153,15 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_runs_kernel(const __grid_con
   const int LF = gp.n_levels * F;
   uint32_t rows[8];
   float acc[8][F];
-  bool have = false;
+  bool have = false, pair = false;
+  auto flush = [&]() {
+    if constexpr (F == 2) {
+      scatter_corners2(dtable, rows, pair, acc);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red_row<F>(dtable, rows[k], acc[k]);
+    }
+  };
 #pragma unroll 1
   for (int s = 0; s < CH; ++s) {
     const int64_t i = i0 + s;
@@ -167,17 +179,14 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_runs_kernel(const __grid_con
 #pragma unroll
     for (int k = 0; k < 8; ++k) same &= (c.row[k] == rows[k]);
     if (!same) {
-      if (have) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) red_row<F>(dtable, rows[k], acc[k]);
-      }
+      if (have) flush();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         rows[k] = c.row[k];
 #pragma unroll
         for (int j = 0; j < F; ++j) acc[k][j] = 0.f;
       }
-      have = true;
+      have = true, pair = c.xpair;
     }
     const float ox = c.ox, oy = c.oy, oz = c.oz;
     const float rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
@@ -188,10 +197,7 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_runs_kernel(const __grid_con
 #pragma unroll
       for (int j = 0; j < F; ++j) acc[k][j] = fmaf(w[k], g[j], acc[k][j]);
   }
-  if (have) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) red_row<F>(dtable, rows[k], acc[k]);
-  }
+  if (have) flush();
 }
 
 

@@ -71,6 +71,7 @@ __device__ __forceinline__ void red_row(float* table, uint32_t row, const float*
 struct Corners {
   uint32_t row[8];
   float ox, oy, oz;  // torch: weight of the ceil corner; tcnn: weight of the +1 corner
+  bool xpair;        // the x-neighbours of every (y,z) corner pair sit in adjacent table rows {2m, 2m+1}
 };
 
 template <int MODE>
@@ -84,6 +85,9 @@ __device__ __forceinline__ Corners corners_of(const GridParams& gp, int l, float
     const uint32_t xc = (uint32_t)(int)ceilf(sx), yc = (uint32_t)(int)ceilf(sy) * 2654435761u,
                    zc = (uint32_t)(int)ceilf(sz) * 805459861u;
     c.ox = sx - fx, c.oy = sy - fy, c.oz = sz - fz;
+    // x enters the hash with prime 1: for an even floor coordinate, row(x+1) = row(x) ^ 1 — the two x-neighbours are
+    // one aligned 16-byte pair (level offsets l*T are even), so 4 vector accesses replace 8
+    c.xpair = ((xf & 1u) == 0u) && (xc == xf + 1u);
     const uint32_t mask = (1u << gp.log2_T) - 1u, off = gp.offset[l];
     c.row[0] = ((xc ^ yc ^ zc) & mask) + off;
     c.row[1] = ((xc ^ yf ^ zc) & mask) + off;
@@ -98,6 +102,7 @@ __device__ __forceinline__ Corners corners_of(const GridParams& gp, int l, float
     const float px = fmaf(x, s, 0.5f), py = fmaf(y, s, 0.5f), pz = fmaf(z, s, 0.5f);
     const float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
     c.ox = px - fx, c.oy = py - fy, c.oz = pz - fz;
+    c.xpair = false;
     const uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
     const uint32_t size = gp.size[l], off = gp.offset[l], res = gp.resolution[l];
     const bool hashed = gp.hashed[l] != 0;
@@ -117,6 +122,45 @@ __device__ __forceinline__ Corners corners_of(const GridParams& gp, int l, float
   return c;
 }
 
+
+// the 8 corner feature rows of one (point, level), F = 2: 4 x 128-bit loads when the x-neighbours are paired
+__device__ __forceinline__ void gather_corners2(const float* __restrict__ table, const Corners& c, Vec<2> (&f)[8]) {
+  if (c.xpair) {
+    // (ceil-x corner, floor-x corner) index pairs of the reference's corner order
+    constexpr int pc[4] = {0, 1, 4, 5}, pf[4] = {3, 2, 7, 6};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t rf = c.row[pf[q]];
+      const float4 v = __ldg(reinterpret_cast<const float4*>(table + (size_t)(rf & ~1u) * 2));
+      const bool f_hi = (rf & 1u) != 0u;  // which half of the pair is the floor-x corner
+      f[pf[q]].v[0] = f_hi ? v.z : v.x, f[pf[q]].v[1] = f_hi ? v.w : v.y;
+      f[pc[q]].v[0] = f_hi ? v.x : v.z, f[pc[q]].v[1] = f_hi ? v.y : v.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = ldg_row<2>(table, c.row[k]);
+  }
+}
+
+// scatter counterpart: g[k][0..1] is added to row k; paired x-neighbours go out as one 128-bit RED
+__device__ __forceinline__ void scatter_corners2(float* table, const uint32_t (&row)[8], bool xpair, const float (&g)[8][2]) {
+  if (xpair) {
+    constexpr int pc[4] = {0, 1, 4, 5}, pf[4] = {3, 2, 7, 6};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t rf = row[pf[q]];
+      const bool f_hi = (rf & 1u) != 0u;
+      float* p = table + (size_t)(rf & ~1u) * 2;
+      const float a0 = f_hi ? g[pc[q]][0] : g[pf[q]][0], a1 = f_hi ? g[pc[q]][1] : g[pf[q]][1];
+      const float b0 = f_hi ? g[pf[q]][0] : g[pc[q]][0], b1 = f_hi ? g[pf[q]][1] : g[pc[q]][1];
+      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a0), "f"(a1), "f"(b0), "f"(b1)
+                   : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red_row<2>(table, row[k], g[k]);
+  }
+}
 
 static inline int fill_params(const B2nGrid* g, GridParams& gp) {
   if (g->n_levels < 1 || g->n_levels > B2N_MAX_LEVELS) return -1;

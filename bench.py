@@ -280,8 +280,14 @@ def run_b200(args) -> None:
         prof, lib.PROFILE = lib.profile_summary(), None
         engine.use_graph = was_graph
         S = engine.S
-        hb = {f"b2n_hashgrid_fwd[n={RAYS_PER_GPU * S[i]}]": RAYS_PER_GPU * S[i] * L * 8 * 2 * 4 for i, L in ((0, 5), (1, 5), (2, 16))}
-        hb.update({f"b2n_hashgrid_bwd[n={RAYS_PER_GPU * S[i]}]": 2 * RAYS_PER_GPU * S[i] * L * 8 * 2 * 4 for i, L in ((0, 5), (1, 5), (2, 16))})
+        # algorithmic bytes of every kernel that gathers from / scatters into a hash table: 8 corners x F(2) x 4 B per
+        # (point, level); scatter counted as read + write.  The fused density-field kernels carry the proposal grids.
+        hb = {}
+        for i, L in ((0, 5), (1, 5), (2, 16)):
+            n_pts, b = RAYS_PER_GPU * S[i], RAYS_PER_GPU * S[i] * L * 8 * 2 * 4
+            hb[f"b2n_hashgrid_fwd[n={n_pts}]"], hb[f"b2n_hashgrid_bwd[n={n_pts}]"] = b, 2 * b
+            hb[f"b2n_density_field_fwd[n={n_pts}]"] = b
+            hb[f"b2n_density_field_bwd[n={n_pts}]"] = 3 * b  # re-gather + scatter
         kt = {k: {"launches": c, "ms_total": t, "ms_avg": t / c, "bytes_per_launch": hb[k]} for k, (c, t) in prof.items() if k in hb}
         kernel_table = {k: round(t / n_prof, 4) for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         ms_prof = sum(t for _, t in prof.values()) / n_prof
@@ -303,8 +309,12 @@ def run_b200(args) -> None:
     if dom is not None:
         name, st = dom
         ach = st["bytes_per_launch"] / (st["ms_avg"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")  # dram read+write per launch, ncu --set full
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(name.split("[")[0], {}).get(name)
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "launches_per_step": st["launches"] / n_prof,
+                    "traffic": traffic, "peak_source": peak_src, "launches_per_step": st["launches"] / n_prof,
                     "ms_avg": st["ms_avg"], "share_of_step": st["ms_avg"] * st["launches"] / n_prof / ms_prof,
                     "all_hash_kernels": {k: {"ms_avg": v["ms_avg"], "GBps": v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9,
                                              "launches_per_step": v["launches"] / n_prof} for k, v in kt.items()},

@@ -150,7 +150,12 @@ def call(name: str, *args) -> None:
     e0.record()
     check(getattr(load(), name)(*args), name)
     e1.record()
-    key = f"{name}[n={args[_N_ARG[name]]}]" if name in _N_ARG else name
+    if name == "b2n_density_field_fwd":
+        key = f"{name}[n={args[8] * args[9]}]"
+    elif name == "b2n_density_field_bwd":
+        key = f"{name}[n={args[9] * args[10]}]"
+    else:
+        key = f"{name}[n={args[_N_ARG[name]]}]" if name in _N_ARG else name
     PROFILE.setdefault(key, []).append((e0, e1))
 
 

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict, List, Optional
 
 import torch
 from torch import Tensor
@@ -52,6 +52,8 @@ class _Net:
 
 
 class NerfactoStep:
+    HYPER_SLOTS = 64
+
     def __init__(self, model: NerfactoModel, n_rays: int, lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-15,
                  lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
                  always_update_proposals: bool = False, mlp_backend: str = "auto",
@@ -109,7 +111,10 @@ class NerfactoStep:
         self.nears = torch.full((R,), float(cfg.near_plane), **f32)
         self.fars = torch.full((R,), float(cfg.far_plane), **f32)
         self.hyper = torch.zeros(4, **f32)  # lr/bc1, 1/sqrt(bc2), grad_scale, anneal
-        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        # pinned staging ring for the per-step scalars: a slot is rewritten only after the async H2D copy that read it
+        # has completed (the CPU may run many steps ahead of the stream)
+        self._hyper_ring = torch.zeros(self.HYPER_SLOTS, 4, dtype=torch.float32).pin_memory()
+        self._hyper_events: List[Optional[torch.cuda.Event]] = [None] * self.HYPER_SLOTS
         self.lin0 = torch.linspace(0.0, 1.0, self.S[0] + 1).to(dev)
         self.u_base = [torch.linspace(0.0, 1.0 - 1.0 / (s + 1), s + 1).to(dev) for s in self.S[1:]]
         # ---- per-level buffers
@@ -316,11 +321,18 @@ class NerfactoStep:
         o = self.optim
         lr = o.lr_schedule(t) if o.lr_schedule is not None else o.lr
         world = getattr(self.allreduce, "world", 1) if self.allreduce is not None else 1
-        self.hyper_host[0] = lr / (1.0 - o.betas[0] ** (t + 1))
-        self.hyper_host[1] = 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1))
-        self.hyper_host[2] = 1.0 / world
-        self.hyper_host[3] = self._anneal(t)
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        slot = t % self.HYPER_SLOTS
+        if self._hyper_events[slot] is not None:
+            self._hyper_events[slot].synchronize()
+        host = self._hyper_ring[slot]
+        host[0] = lr / (1.0 - o.betas[0] ** (t + 1))
+        host[1] = 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1))
+        host[2] = 1.0 / world
+        host[3] = self._anneal(t)
+        self.hyper.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_events[slot] = ev
         update = self._update_due(t)
         overlap = self.allreduce is not None and world > 1
         if self.use_graph and update not in self._graphs:

@@ -49,15 +49,86 @@ struct TcParams {
   uint32_t w_total;                    // bytes of the whole weight region
 };
 
-__device__ __forceinline__ float tc_act(int act, float v) {
-  if (act == B2N_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == B2N_ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+// The activation id is warp-uniform: switch once per slice, not per element (the per-element form compiled to a
+// branch ladder of ~12 instructions per value and made the epilogue the longest phase of the kernel).
+__device__ __forceinline__ void bias_act_slice(int act, float (&v)[16], const float* __restrict__ bias16, int n_real) {
+  float b[16];
+#pragma unroll
+  for (int c = 0; c < 16; c += 4) {
+    const float4 q = *reinterpret_cast<const float4*>(bias16 + c);
+    b[c] = q.x, b[c + 1] = q.y, b[c + 2] = q.z, b[c + 3] = q.w;
+  }
+  if (act == B2N_ACT_RELU) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = fmaxf(v[c] + b[c], 0.f);
+  } else if (act == B2N_ACT_SIGMOID) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = (c < n_real) ? 1.f / (1.f + expf(-(v[c] + b[c]))) : 0.f;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] += b[c];
+  }
+}
+// g[c] *= act'(y[c])
+__device__ __forceinline__ void act_grad_slice(int act, float (&g)[16], const float (&y)[16]) {
+  if (act == B2N_ACT_RELU) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) g[c] = y[c] > 0.f ? g[c] : 0.f;
+  } else if (act == B2N_ACT_SIGMOID) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) g[c] *= y[c] * (1.f - y[c]);
+  }
+}
+
+#ifdef B2N_TC_PROF
+// clock64 phase profile (development builds only): per-thread register accumulators, flushed once at kernel end
+__device__ unsigned long long tc_prof[16];
+#define TCP_INIT                  \
+  long long tcp_last = clock64(); \
+  unsigned long long tcp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TCPT(i, tid)                                                  \
+  do {                                                                \
+    if (threadIdx.x == (tid) && blockIdx.x == 0) {                    \
+      const long long now = clock64();                                \
+      tcp_acc[(i) & 7] += (unsigned long long)(now - tcp_last);       \
+      tcp_last = now;                                                 \
+    }                                                                 \
+  } while (0)
+#define TCP(i) TCPT(i, 0)
+#define TCP_FLUSH(tid)                                                \
+  do {                                                                \
+    if (threadIdx.x == (tid) && blockIdx.x == 0) {                    \
+      _Pragma("unroll") for (int q_ = 0; q_ < 8; ++q_) if (tcp_acc[q_]) atomicAdd(&tc_prof[q_], tcp_acc[q_]); \
+    }                                                                 \
+  } while (0)
+extern "C" int b2n_tc_prof_read(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, tc_prof, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(tc_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#else
+#define TCP_INIT
+#define TCP(i)
+#define TCPT(i, tid)
+#define TCP_FLUSH(tid)
+#endif
+
+// Read-only global loads as volatile asm: the compiler otherwise sinks a "prefetch" (a load issued a layer or a tile
+// before its first use) across the barriers down to the use, exposing the full DRAM latency (ncu: 13 % of the
+// forward's stall samples sat on the first use of the prefetched input).
+__device__ __forceinline__ float4 ldg4_early(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ float tc_act_grad(int act, float y) {
-  if (act == B2N_ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == B2N_ACT_SIGMOID) return y * (1.f - y);
-  return 1.f;
+__device__ __forceinline__ float ldg1_early(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
 }
 
 #define TC_THREADS 512  // 16 warps: warps w, w+4, w+8, w+12 share TMEM quarter w&3 and split the tile's 64 columns
@@ -102,16 +173,91 @@ __device__ __forceinline__ void load_global_half(const float* __restrict__ src, 
   for (int c = 0; c < TC_HALF; c += 4) {
     if (c0 + c < pad) {
       if (live && vec && c0 + c + 4 <= real) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(src + c0 + c));
+        const float4 q = ldg4_early(src + c0 + c);
         v[c] = q.x, v[c + 1] = q.y, v[c + 2] = q.z, v[c + 3] = q.w;
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[c + i] = (live && c0 + c + i < real) ? __ldg(src + c0 + c + i) : 0.f;
+        for (int i = 0; i < 4; ++i) v[c + i] = (live && c0 + c + i < real) ? ldg1_early(src + c0 + c + i) : 0.f;
       }
     } else {
       v[c] = v[c + 1] = v[c + 2] = v[c + 3] = 0.f;
     }
   }
+}
+
+
+// ---- warp-cooperative row access ---------------------------------------------------------------------------------
+// A warp owns rows row0..row0+31 of a row-major matrix and, per row, the 16 floats (64 B) starting at column c0.
+// If lane L touched its own row, every access instruction would hit 32 different 128-byte lines (32 LSU cycles per
+// instruction: measured 2-3k cycles per layer and tile).  Instead instruction k lets quad i = L/4 touch row 4i+k with
+// lane j = L%4 on 16-byte chunk j — 8 rows x 64 contiguous bytes per instruction, whole sectors — and a 4x4
+// transpose inside each quad (two shuffle stages) converts between "access order" and "row-owner order".
+__device__ __forceinline__ float4 shfl_xor4(const float4 v, int m) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m),
+                     __shfl_xor_sync(0xffffffffu, v.z, m), __shfl_xor_sync(0xffffffffu, v.w, m));
+}
+// lane j of a quad holds q[k]; afterwards lane j's q[k] is what lane k held in q[j]
+__device__ __forceinline__ void quad_transpose(float4 (&q)[4]) {
+  const int lane = threadIdx.x & 31;
+  {
+    const bool odd = (lane & 1) != 0;
+    const float4 r0 = shfl_xor4(odd ? q[0] : q[1], 1), r1 = shfl_xor4(odd ? q[2] : q[3], 1);
+    if (odd) q[0] = r0, q[2] = r1;
+    else q[1] = r0, q[3] = r1;
+  }
+  {
+    const bool hi = (lane & 2) != 0;
+    const float4 r0 = shfl_xor4(hi ? q[0] : q[2], 2), r1 = shfl_xor4(hi ? q[1] : q[3], 2);
+    if (hi) q[0] = r0, q[1] = r1;
+    else q[2] = r0, q[3] = r1;
+  }
+}
+// v <- columns [c0, c0+16) of row (row0 + lane); rows >= n and columns >= real read as zero.  `stride` % 4 == 0 and a
+// 16-byte aligned base are required (so a chunk that starts below `real` lies inside the row's storage).
+__device__ __forceinline__ void load_rows_quad(const float* __restrict__ base, int64_t stride, int64_t row0, int64_t n,
+                                               int c0, int real, float (&v)[TC_HALF]) {
+  const int lane = threadIdx.x & 31, col = c0 + 4 * (lane & 3);
+  float4 q[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t row = row0 + 4 * (lane >> 2) + k;
+    q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n && col < real) {
+      q[k] = ldg4_early(base + row * stride + col);
+      if (col + 1 >= real) q[k].y = 0.f;
+      if (col + 2 >= real) q[k].z = 0.f;
+      if (col + 3 >= real) q[k].w = 0.f;
+    }
+  }
+  quad_transpose(q);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[4 * k] = q[k].x, v[4 * k + 1] = q[k].y, v[4 * k + 2] = q[k].z, v[4 * k + 3] = q[k].w;
+}
+// columns [c0, c0+16) ∩ [0, real) of row (row0 + lane) <- v   (rows >= n are skipped)
+__device__ __forceinline__ void store_rows_quad(float* __restrict__ base, int64_t stride, int64_t row0, int64_t n, int c0,
+                                                int real, const float (&v)[TC_HALF]) {
+  const int lane = threadIdx.x & 31, col = c0 + 4 * (lane & 3);
+  float4 q[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  quad_transpose(q);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t row = row0 + 4 * (lane >> 2) + k;
+    if (row < n && col < real) {
+      float* dst = base + row * stride + col;
+      if (col + 4 <= real) {
+        *reinterpret_cast<float4*>(dst) = q[k];
+      } else {
+        dst[0] = q[k].x;
+        if (col + 1 < real) dst[1] = q[k].y;
+        if (col + 2 < real) dst[2] = q[k].z;
+      }
+    }
+  }
+}
+__device__ __forceinline__ bool quad_ok(const void* base, int64_t stride) {
+  return ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -133,22 +279,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
 
   for (int l = 0; l < p.n_layers; ++l) {  // stage W hi/lo as K-major canonical [N rows][K cols]
     const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
-    uint8_t* wh = Wr + p.w_off[l];
-    uint8_t* wl = wh + p.w_bytes[l];
-    const uint32_t cs = (uint32_t)N * 16u;
+    // hi and lo halves are STACKED along N (rows 0..N-1 = hi, N..2N-1 = lo): one N'=2N MMA stream then yields
+    // [A_hi W_hi | A_hi W_lo] and a second N'=N stream adds A_lo W_hi onto the first half — 2 streams instead of 3
+    uint8_t* wst = Wr + p.w_off[l];
+    const uint32_t cs = (uint32_t)(2 * N) * 16u;
     for (int idx = t; idx < N * K; idx += TC_THREADS) {
       const int j = idx / K, k = idx - j * K;
       const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
       float h, lo;
       tc::split_tf32(v, h, lo);
-      const uint32_t off = tc::canon_off(j, k, cs);
-      *reinterpret_cast<float*>(wh + off) = h;
-      *reinterpret_cast<float*>(wl + off) = lo;
+      *reinterpret_cast<float*>(wst + tc::canon_off(j, k, cs)) = h;
+      *reinterpret_cast<float*>(wst + tc::canon_off(N + j, k, cs)) = lo;
     }
     for (int j = t; j < N; j += TC_THREADS) bias[p.bias_off[l] + j] = (j < nr && p.b[l]) ? __ldg(p.b[l] + j) : 0.f;
   }
   if (t == 0) tc::mbar_init(&bar, 1);
-  if (warp == 0) tc::tmem_alloc<64>(&tmem_slot);
+  if (warp == 0) tc::tmem_alloc<128>(&tmem_slot);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -180,16 +326,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
       __syncthreads();
       tc::fence_after_sync();
       if (t == 0) {
-        const uint32_t idesc = tc::make_idesc_tf32(TC_ROWS, N, false, false);
-        const uint32_t cs = (uint32_t)N * 16u;
-        const uint32_t wh = tc::smem_u32(Wr + p.w_off[l]), wl = wh + p.w_bytes[l];
-        const uint32_t ah = tc::smem_u32(Ah), al = tc::smem_u32(Al);
+        const uint32_t cs = (uint32_t)(2 * N) * 16u;
+        const uint32_t wst = tc::smem_u32(Wr + p.w_off[l]);
         // descriptors differ between k-steps only in the start-address field (bits 0-13, units of 16 B)
         const uint64_t da = (uint64_t)((2 * TC_CS_A) >> 4), db = (uint64_t)((2 * cs) >> 4);
         uint32_t acc = 0;
 #pragma unroll
-        for (int pass = 0; pass < 3; ++pass) {
-          uint64_t ad = tc::make_desc((pass == 1) ? al : ah, TC_CS_A, 128), bd = tc::make_desc((pass == 2) ? wl : wh, cs, 128);
+        for (int pass = 0; pass < 2; ++pass) {  // pass 0: A_hi x [W_hi; W_lo] (N' = 2N), pass 1: A_lo x W_hi (N' = N)
+          const uint32_t idesc = tc::make_idesc_tf32(TC_ROWS, pass ? N : 2 * N, false, false);
+          uint64_t ad = tc::make_desc(tc::smem_u32(pass ? Al : Ah), TC_CS_A, 128), bd = tc::make_desc(wst, cs, 128);
 #pragma unroll 2
           for (int s = 0; s < K / 8; ++s) {
             tc::mma_tf32(tmem, ad, bd, idesc, acc);
@@ -199,16 +344,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
         }
         tc::commit(&bar);
       }
+      __syncwarp();  // lane 0 issued the MMAs alone: reconverge before the warp-aligned tcgen05 instructions
       tc::mbar_wait(&bar, phase);
+      __syncwarp();
       phase ^= 1;
       tc::fence_after_sync();
-      load_half(tmem, quarter, 0, c0, N, v);
+      {
+        float v2[TC_HALF];
+        load_half(tmem, quarter, 0, c0, N, v);
+        load_half(tmem, quarter, N, c0, N, v2);  // the A_hi W_lo partial product
+#pragma unroll
+        for (int c = 0; c < TC_HALF; ++c) v[c] += v2[c];
+      }
       const bool last = (l == p.n_layers - 1);
       const int act = last ? p.out_act : p.hidden_act;
-      const float* bl = bias + p.bias_off[l];
       const int nr = p.nr[l];
-#pragma unroll
-      for (int c = 0; c < TC_HALF; ++c) v[c] = (c0 + c < nr) ? tc_act(act, v[c] + bl[c0 + c]) : 0.f;
+      // padded columns: zero weights and zero bias give act(0) = 0 for ReLU / identity (sigmoid only ends a network)
+      if (c0 < N) bias_act_slice(act, v, bias + p.bias_off[l] + c0, nr - c0);  // warp-uniform
       if (!last) {
         if (hidden != nullptr && live) {
           float* h = hidden + p.hid_off[l] * n + row * nr;
@@ -230,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<64>(tmem);
+  if (warp == 0) tc::tmem_dealloc<128>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,17 +409,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
 
   for (int l = 0; l < L; ++l) {
     const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
-    uint8_t* wh = Wr + p.w_off[l];
-    uint8_t* wl = wh + p.w_bytes[l];
-    const uint32_t cs = (uint32_t)K * 16u;
+    // transposed (row = input index k, col = output index j), hi rows 0..K-1 and lo rows K..2K-1 stacked along the
+    // MMA's N: dA = [dZ_hi W_hi | dZ_hi W_lo] (N' = 2K) + dZ_lo W_hi (N' = K) in two streams
+    uint8_t* wst = Wr + p.w_off[l];
+    const uint32_t cs = (uint32_t)(2 * K) * 16u;
     for (int idx = t; idx < N * K; idx += TC_THREADS) {
       const int j = idx / K, k = idx - j * K;
       const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
       float h, lo;
       tc::split_tf32(v, h, lo);
-      const uint32_t off = tc::canon_off(k, j, cs);  // transposed: row = input index, col = output index
-      *reinterpret_cast<float*>(wh + off) = h;
-      *reinterpret_cast<float*>(wl + off) = lo;
+      *reinterpret_cast<float*>(wst + tc::canon_off(k, j, cs)) = h;
+      *reinterpret_cast<float*>(wst + tc::canon_off(K + k, j, cs)) = lo;
     }
   }
   if (t == 0) tc::mbar_init(&bar, 1);
@@ -278,40 +430,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
   const uint32_t tmem = tmem_slot;
   uint32_t phase = 0;
   uint32_t dw_started = 0;  // bit l: the layer's dW accumulator has been written once (thread 0 only)
-  const int DW_COL0 = 64, DW_COLS = 80;
-  const bool xvec = ((x_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int DW_COL0 = 128, DW_COLS = 80;  // D (dA, two partial products) occupies columns 0..127
+  const bool xvec = quad_ok(x, x_stride);
+  const bool dxvec = dx != nullptr && quad_ok(dx, dx_stride);
+  const int wrow = 32 * quarter;  // first tile row of this warp
+  // input rows of layer l (x or the saved hidden activations) for this thread's (row, column slice)
+  auto load_a = [&](int l, int64_t tile, int64_t row, bool live, float (&dst)[TC_HALF]) {
+    const int kr = p.kr[l];
+    if (c0 >= p.K[l]) {  // warp-uniform
+#pragma unroll
+      for (int c = 0; c < TC_HALF; ++c) dst[c] = 0.f;
+      return;
+    }
+    if (l == 0) {
+      if (xvec) load_rows_quad(x, x_stride, tile * TC_ROWS + wrow, n, c0, kr, dst);
+      else load_global_half(x + row * x_stride, live, false, c0, kr, p.K[l], dst);
+    } else {
+      const float* hsrc = hidden + p.hid_off[l - 1] * n;
+      if ((kr & 3) == 0 && quad_ok(hsrc, kr)) load_rows_quad(hsrc, kr, tile * TC_ROWS + wrow, n, c0, kr, dst);
+      else load_global_half(hsrc + row * (int64_t)kr, live, false, c0, kr, p.K[l], dst);
+    }
+  };
 
   const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+  TCP_INIT;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = tile * TC_ROWS + r;
     const bool live = row < n;
     float dz[TC_HALF], a[TC_HALF];
     {  // dZ of the last layer = dy * act'(y)   (this thread's column half)
       const int nr = p.nr[L - 1];
+      if (c0 < nr && (nr & 3) == 0 && quad_ok(dy, nr) && quad_ok(y, nr)) {  // warp-uniform
+        float yv[TC_HALF];
+        load_rows_quad(dy, nr, tile * TC_ROWS + wrow, n, c0, nr, dz);
+        load_rows_quad(y, nr, tile * TC_ROWS + wrow, n, c0, nr, yv);
+        act_grad_slice(p.out_act, dz, yv);
+      } else {
+        float yv[TC_HALF];
 #pragma unroll
-      for (int c = 0; c < TC_HALF; ++c) {
-        float g = 0.f;
-        if (c0 + c < nr && live) g = __ldg(dy + row * nr + c0 + c) * tc_act_grad(p.out_act, __ldg(y + row * nr + c0 + c));
-        dz[c] = g;
+        for (int c = 0; c < TC_HALF; ++c) {
+          const bool on = c0 + c < nr && live;
+          dz[c] = on ? __ldg(dy + row * nr + c0 + c) : 0.f;
+          yv[c] = on ? __ldg(y + row * nr + c0 + c) : 0.f;
+        }
+        act_grad_slice(p.out_act, dz, yv);
       }
     }
     float a_next[TC_HALF];  // the input row slice of the NEXT layer to be processed (one layer of lookahead)
-    {
-      const int l = L - 1, kr = p.kr[l];
-      if (l == 0) load_global_half(x + row * x_stride, live, xvec, c0, kr, p.K[l], a_next);
-      else load_global_half(hidden + p.hid_off[l - 1] * n + row * (int64_t)kr, live, (kr & 3) == 0, c0, kr, p.K[l], a_next);
-    }
+    load_a(L - 1, tile, row, live, a_next);
+    TCP(0);
     for (int l = L - 1; l >= 0; --l) {
       const int N = p.N[l], K = p.K[l], kr = p.kr[l];
 #pragma unroll
       for (int c = 0; c < TC_HALF; ++c) a[c] = a_next[c];
-      if (l > 0) {
-        const int l2 = l - 1, kr2 = p.kr[l2];
-        if (l2 == 0) load_global_half(x + row * x_stride, live, xvec, c0, kr2, p.K[l2], a_next);
-        else load_global_half(hidden + p.hid_off[l2 - 1] * n + row * (int64_t)kr2, live, (kr2 & 3) == 0, c0, kr2, p.K[l2], a_next);
-      }
+      if (l > 0) load_a(l - 1, tile, row, live, a_next);
       const bool need_da = (l > 0) || (dx != nullptr);
       if (need_da) store_half_hilo(Zh, Zl, r, c0, dz, N);
+      TCP(1);
       // ---- dW_l += dZ^T A over the two 64-point halves of the tile
       for (int ph = 0; ph < 2; ++ph) {
         if ((r >> 6) == ph) {
@@ -340,10 +515,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
             }
           }
         }
+        TCP(2);
         tc::fence_smem_to_async();
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
+        TCP(3);
         if (t == 0) {
           const uint32_t idesc = tc::make_idesc_tf32(TC_ROWS, K + 16, false, false);
           const uint32_t tz = tc::smem_u32(TZ), tah = tc::smem_u32(TAh), tal = tc::smem_u32(TAl);
@@ -361,14 +538,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
           }
           dw_started |= 1u << l;
           if (ph == 1 && need_da) {  // dA = dZ W : issued right behind, one commit covers both
-            const uint32_t idx = tc::make_idesc_tf32(TC_ROWS, K, false, false);
-            const uint32_t cs = (uint32_t)K * 16u;
-            const uint32_t wh = tc::smem_u32(Wr + p.w_off[l]), wl = wh + p.w_bytes[l];
-            const uint32_t zh = tc::smem_u32(Zh), zl = tc::smem_u32(Zl);
+            const uint32_t cs = (uint32_t)(2 * K) * 16u;
+            const uint32_t wst = tc::smem_u32(Wr + p.w_off[l]);
             uint32_t acc2 = 0;
 #pragma unroll
-            for (int pass = 0; pass < 3; ++pass) {
-              uint64_t ad = tc::make_desc((pass == 1) ? zl : zh, TC_CS_A, 128), bd = tc::make_desc((pass == 2) ? wl : wh, cs, 128);
+            for (int pass = 0; pass < 2; ++pass) {
+              const uint32_t idx = tc::make_idesc_tf32(TC_ROWS, pass ? K : 2 * K, false, false);
+              uint64_t ad = tc::make_desc(tc::smem_u32(pass ? Zl : Zh), TC_CS_A, 128), bd = tc::make_desc(wst, cs, 128);
 #pragma unroll 2
               for (int s = 0; s < N / 8; ++s) {
                 tc::mma_tf32(tmem, ad, bd, idx, acc2);
@@ -379,29 +555,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
           }
           tc::commit(&bar);
         }
+        TCP(4);
+        __syncwarp();  // lane 0 issued the MMAs alone: reconverge before the warp-aligned tcgen05 instructions
         tc::mbar_wait(&bar, phase);
+        __syncwarp();
         phase ^= 1;
         tc::fence_after_sync();
+        TCP(5);
       }
       // ---- dA half row -> next dZ (or dx)
       if (need_da) {
         float da[TC_HALF];
-        load_half(tmem, quarter, 0, c0, K, da);
+        {
+          float da2[TC_HALF];
+          load_half(tmem, quarter, 0, c0, K, da);
+          load_half(tmem, quarter, K, c0, K, da2);  // the dZ_hi W_lo partial product
+#pragma unroll
+          for (int c = 0; c < TC_HALF; ++c) da[c] += da2[c];
+        }
         if (l > 0) {
 #pragma unroll
-          for (int c = 0; c < TC_HALF; ++c) dz[c] = (c0 + c < kr) ? da[c] * tc_act_grad(p.hidden_act, a[c]) : 0.f;
+          for (int c = 0; c < TC_HALF; ++c) dz[c] = da[c];  // padded columns: zero weight rows give dA = 0
+          act_grad_slice(p.hidden_act, dz, a);
+        } else if (dxvec) {
+          if (c0 < p.in_dim) store_rows_quad(dx, dx_stride, tile * TC_ROWS + wrow, n, c0, p.in_dim, da);  // warp-uniform
         } else if (live) {
           float* dr = dx + row * dx_stride;
 #pragma unroll
           for (int c = 0; c < TC_HALF; ++c)
             if (c0 + c < p.in_dim) dr[c0 + c] = da[c];
         }
+        TCP(6);
         tc::fence_before_sync();
         __syncthreads();  // D (columns 0..63) fully read before the next layer's dA MMA overwrites it
         tc::fence_after_sync();
+        TCP(7);
       }
     }
   }
+  TCP_FLUSH(0);
   // ---- flush dW / db: lanes 0-63 hold dZ_hi^T [A_hi + A_lo], lanes 64-127 the dZ_lo^T part
   tc::fence_before_sync();
   __syncthreads();

@@ -1,4 +1,6 @@
 """GPU: tcgen05 building blocks and the tensor-core MLP (3xTF32) against fp64 / the oracle."""
+import zlib
+
 import pytest
 import torch
 
@@ -51,7 +53,7 @@ CFGS = {
 @pytest.mark.parametrize("name", list(CFGS))
 def test_mlp_tc_forward_backward_vs_oracle(F, name):
     in_dim, dims, out_act = CFGS[name]
-    torch.manual_seed(hash(name) % 1000)
+    torch.manual_seed(zlib.crc32(name.encode()) % 1000)  # str hashes are salted per process
     n = 128 * 300 + 77  # ragged, > 2 tiles per CTA
     spec = F.MlpSpec(in_dim, dims, out_act=out_act)
     assert F.mlp_tc_supported(spec)
@@ -67,7 +69,8 @@ def test_mlp_tc_forward_backward_vs_oracle(F, name):
     # million hidden units) get a zero upstream gradient so the comparison below stays strict for all others.
     with torch.no_grad():
         h, near_kink = x, torch.zeros(n, dtype=torch.bool)
-        for w_, b_ in zip(ws[:-1], bs[:-1]):
+        relu_layers = len(ws) if out_act == "relu" else len(ws) - 1  # a ReLU output has a kink of its own
+        for w_, b_ in list(zip(ws, bs))[:relu_layers]:
             z = torch.nn.functional.linear(h, w_, b_)
             near_kink |= (z.abs() < 1e-5).any(dim=1)
             h = torch.relu(z)

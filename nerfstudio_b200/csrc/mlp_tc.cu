@@ -213,25 +213,39 @@ __device__ __forceinline__ void quad_transpose(float4 (&q)[4]) {
   }
 }
 // v <- columns [c0, c0+16) of row (row0 + lane); rows >= n and columns >= real read as zero.  `stride` % 4 == 0 and a
-// 16-byte aligned base are required (so a chunk that starts below `real` lies inside the row's storage).
-__device__ __forceinline__ void load_rows_quad(const float* __restrict__ base, int64_t stride, int64_t row0, int64_t n,
-                                               int c0, int real, float (&v)[TC_HALF]) {
+// 16-byte aligned base are required (so a chunk that starts below `real` lies inside the row's storage).  Split in two
+// so that a prefetch can stay in flight: `issue` only launches the loads (raw access-order chunks, 16 registers),
+// `finish` — which needs the data — zero-fills the tail and transposes into row-owner order at the point of use.
+__device__ __forceinline__ void load_rows_quad_issue(const float* __restrict__ base, int64_t stride, int64_t row0, int64_t n,
+                                                     int c0, int real, float (&raw)[TC_HALF]) {
+  const int lane = threadIdx.x & 31, col = c0 + 4 * (lane & 3);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t row = row0 + 4 * (lane >> 2) + k;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n && col < real) q = ldg4_early(base + row * stride + col);
+    raw[4 * k] = q.x, raw[4 * k + 1] = q.y, raw[4 * k + 2] = q.z, raw[4 * k + 3] = q.w;
+  }
+}
+__device__ __forceinline__ void load_rows_quad_finish(int c0, int real, const float (&raw)[TC_HALF], float (&v)[TC_HALF]) {
   const int lane = threadIdx.x & 31, col = c0 + 4 * (lane & 3);
   float4 q[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int64_t row = row0 + 4 * (lane >> 2) + k;
-    q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < n && col < real) {
-      q[k] = ldg4_early(base + row * stride + col);
-      if (col + 1 >= real) q[k].y = 0.f;
-      if (col + 2 >= real) q[k].z = 0.f;
-      if (col + 3 >= real) q[k].w = 0.f;
-    }
+    q[k] = make_float4(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2], raw[4 * k + 3]);
+    if (col + 1 >= real) q[k].y = 0.f;
+    if (col + 2 >= real) q[k].z = 0.f;
+    if (col + 3 >= real) q[k].w = 0.f;
   }
   quad_transpose(q);
 #pragma unroll
   for (int k = 0; k < 4; ++k) v[4 * k] = q[k].x, v[4 * k + 1] = q[k].y, v[4 * k + 2] = q[k].z, v[4 * k + 3] = q[k].w;
+}
+__device__ __forceinline__ void load_rows_quad(const float* __restrict__ base, int64_t stride, int64_t row0, int64_t n,
+                                               int c0, int real, float (&v)[TC_HALF]) {
+  float raw[TC_HALF];
+  load_rows_quad_issue(base, stride, row0, n, c0, real, raw);
+  load_rows_quad_finish(c0, real, raw, v);
 }
 // columns [c0, c0+16) ∩ [0, real) of row (row0 + lane) <- v   (rows >= n are skipped)
 __device__ __forceinline__ void store_rows_quad(float* __restrict__ base, int64_t stride, int64_t row0, int64_t n, int c0,
@@ -434,24 +448,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
   const bool xvec = quad_ok(x, x_stride);
   const bool dxvec = dx != nullptr && quad_ok(dx, dx_stride);
   const int wrow = 32 * quarter;  // first tile row of this warp
-  // input rows of layer l (x or the saved hidden activations) for this thread's (row, column slice)
-  auto load_a = [&](int l, int64_t tile, int64_t row, bool live, float (&dst)[TC_HALF]) {
+  // input rows of layer l (x or the saved hidden activations) for this thread's (row, column slice): `issue_a` starts
+  // the loads one layer ahead (raw registers), `finish_a` turns them into row-owner values where they are consumed
+  auto a_is_quad = [&](int l) -> bool {  // warp-uniform
+    if (l == 0) return xvec;
+    return (p.kr[l] & 3) == 0 && quad_ok(hidden + p.hid_off[l - 1] * n, p.kr[l]);
+  };
+  auto issue_a = [&](int l, int64_t tile, int64_t row, bool live, float (&raw)[TC_HALF]) {
     const int kr = p.kr[l];
     if (c0 >= p.K[l]) {  // warp-uniform
 #pragma unroll
-      for (int c = 0; c < TC_HALF; ++c) dst[c] = 0.f;
+      for (int c = 0; c < TC_HALF; ++c) raw[c] = 0.f;
       return;
     }
-    if (l == 0) {
-      if (xvec) load_rows_quad(x, x_stride, tile * TC_ROWS + wrow, n, c0, kr, dst);
-      else load_global_half(x + row * x_stride, live, false, c0, kr, p.K[l], dst);
+    const float* src = (l == 0) ? x : hidden + p.hid_off[l - 1] * n;
+    const int64_t stride = (l == 0) ? x_stride : (int64_t)kr;
+    if (a_is_quad(l)) load_rows_quad_issue(src, stride, tile * TC_ROWS + wrow, n, c0, kr, raw);
+    else load_global_half(src + row * stride, live, false, c0, kr, p.K[l], raw);
+  };
+  auto finish_a = [&](int l, const float (&raw)[TC_HALF], float (&dst)[TC_HALF]) {
+    if (c0 < p.K[l] && a_is_quad(l)) {
+      load_rows_quad_finish(c0, p.kr[l], raw, dst);
     } else {
-      const float* hsrc = hidden + p.hid_off[l - 1] * n;
-      if ((kr & 3) == 0 && quad_ok(hsrc, kr)) load_rows_quad(hsrc, kr, tile * TC_ROWS + wrow, n, c0, kr, dst);
-      else load_global_half(hsrc + row * (int64_t)kr, live, false, c0, kr, p.K[l], dst);
+#pragma unroll
+      for (int c = 0; c < TC_HALF; ++c) dst[c] = raw[c];
     }
   };
-
   const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
   TCP_INIT;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -476,14 +498,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
         act_grad_slice(p.out_act, dz, yv);
       }
     }
-    float a_next[TC_HALF];  // the input row slice of the NEXT layer to be processed (one layer of lookahead)
-    load_a(L - 1, tile, row, live, a_next);
+    float a_next[TC_HALF];  // the input row slice of the NEXT layer to be processed (one layer of lookahead, raw)
+    issue_a(L - 1, tile, row, live, a_next);
     TCP(0);
     for (int l = L - 1; l >= 0; --l) {
       const int N = p.N[l], K = p.K[l], kr = p.kr[l];
-#pragma unroll
-      for (int c = 0; c < TC_HALF; ++c) a[c] = a_next[c];
-      if (l > 0) load_a(l - 1, tile, row, live, a_next);
+      finish_a(l, a_next, a);
+      if (l > 0) issue_a(l - 1, tile, row, live, a_next);
       const bool need_da = (l > 0) || (dx != nullptr);
       if (need_da) store_half_hilo(Zh, Zl, r, c0, dz, N);
       TCP(1);
@@ -598,21 +619,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  // The lo-part lanes hand their values to the hi-part lanes through shared memory (the dZ tile region is free now),
+  // and rows go out as 128-bit REDs where the gradient row is 16-byte aligned: 8x fewer L2 atomics than one atomicAdd
+  // per lane and element (148 CTAs all add into the same few KB).
+  float* scratch = reinterpret_cast<float*>(Zh);  // [4 column groups][64 rows][20 floats (16 + pad)]
   for (int l = 0; l < L; ++l) {
     if (p.dw[l] == nullptr && p.db[l] == nullptr) continue;
     const int K = p.K[l], kr = p.kr[l], nr = p.nr[l];
     const int j = r & 63;
     const bool started = blockIdx.x < n_tiles;
-    for (int cc = c0; cc < K + 16; cc += 64) {  // warp-uniform: column group c0/16 takes chunks c0, c0+64
+    const bool vec = p.dw[l] != nullptr && (kr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw[l]) & 15) == 0;
+    for (int base = 0; base < K + 16; base += 64) {  // uniform trip count: the loop body synchronises the CTA
+      const int cc = base + c0;
+      const bool active = cc < K + 16;  // warp-uniform
       float v[16];
-      tc::ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(DW_COL0 + DW_COLS * l + cc), v);
-      if (!started || j >= nr) continue;
+      if (active) tc::ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(DW_COL0 + DW_COLS * l + cc), v);
+      float* sc = scratch + ((c0 >> 4) * 64 + j) * 20;
+      if (active && r >= 64) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int k = cc + i;
-        if (k < kr && p.dw[l]) atomicAdd(p.dw[l] + (size_t)j * kr + k, v[i]);
-        else if (k == K && p.db[l]) atomicAdd(p.db[l] + j, v[i]);
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(sc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
+      __syncthreads();
+      if (active && r < 64 && started && j < nr) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 o = *reinterpret_cast<const float4*>(sc + i);
+          const float g0 = v[i] + o.x, g1 = v[i + 1] + o.y, g2 = v[i + 2] + o.z, g3 = v[i + 3] + o.w;
+          const int k = cc + i;
+          if (vec && k + 4 <= kr) {
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dw[l] + (size_t)j * kr + k),
+                         "f"(g0), "f"(g1), "f"(g2), "f"(g3)
+                         : "memory");
+          } else {
+            const float g[4] = {g0, g1, g2, g3};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (k + e < kr && p.dw[l]) atomicAdd(p.dw[l] + (size_t)j * kr + k + e, g[e]);
+              else if (k + e == K && p.db[l]) atomicAdd(p.db[l] + j, g[e]);
+            }
+          }
+        }
+      }
+      __syncthreads();
     }
   }
   tc::fence_before_sync();

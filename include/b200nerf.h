@@ -255,7 +255,9 @@ int b2n_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
 
 /* ---- glue of the captured nerfacto step (fields/nerfacto_field.py:234-310; models/nerfacto.py:363-391) -----
  * head_in [R*S, out_stride >= n_sh+geo+n_emb] = [ sh[ray] | base_out[n, 1:1+geo] | emb row ]; emb_mode 0 = zeros,
- * 1 = emb[cam[ray]] (training), 2 = emb[0] (a pre-averaged row, eval). */
+ * 1 = emb[cam[ray]] (training), 2 = emb[0] (a pre-averaged row, eval).  When out is 16-byte aligned and
+ * out_stride % 4 == 0 the rows are written in whole 4-column groups: the padding columns
+ * [n_sh+geo+n_emb, round_up_4(n_sh+geo+n_emb)) (all < out_stride) are zero-filled. */
 int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
                        const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
                        int32_t n_samples, float* out, int32_t out_stride, void* stream);

@@ -400,6 +400,211 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, warp-specialised variant: two tiles in flight per CTA (selected with b2n_tune("tc_fwd_slots", 2))
+//
+// ncu stall samples of the serial kernel above: 22 % waiting for the MMAs, 12 % at the CTA barrier, 8 % on the TMEM
+// load — the tensor pipe and the CUDA cores take turns.  Here two SLOTS of 4 warps each own one 128-row tile (thread =
+// one full row, TMEM quarter = warp & 3) with their own operand tiles and accumulator columns, and warp 8 only issues
+// MMAs, alternating between the slots layer by layer:
+//     worker:  write operand (hi/lo) -> fence.proxy.async -> arrive full[s]   ...   wait done[s] -> tcgen05.ld -> epilogue
+//     issuer:  wait full[s] -> MMAs of that layer -> tcgen05.commit -> done[s]
+// so slot 0's epilogue runs under slot 1's MMAs and vice versa.  (9 warps: a 17-warp version with 2 x 8 worker warps
+// is capped at 96 registers by the 4-warp allocation granularity and spilled its prefetch registers.)
+// ------------------------------------------------------------------------------------------------
+#define TCF_SLOT_THREADS 128
+#define TCF_WORKERS (2 * TCF_SLOT_THREADS)
+#define TCF_THREADS (TCF_WORKERS + 32)
+
+__global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __grid_constant__ TcParams p,
+                                                                    const float* __restrict__ x, int64_t x_stride,
+                                                                    int64_t n, float* __restrict__ y,
+                                                                    float* __restrict__ hidden) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[2], bar_done[2];
+  __shared__ uint32_t tmem_slot;
+  uint8_t* Wr = smem + 4 * TC_TILE_BYTES;                        // weight region behind the two slots' hi/lo tiles
+  float* bias = reinterpret_cast<float*>(Wr + p.w_total);        // [sum N]
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  constexpr int ISSUER_WARP = TCF_WORKERS / 32;
+
+  for (int l = 0; l < p.n_layers; ++l) {  // stage W as K-major canonical [2N rows][K cols] (hi rows, then lo rows)
+    const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
+    uint8_t* wst = Wr + p.w_off[l];
+    const uint32_t cs = (uint32_t)(2 * N) * 16u;
+    for (int idx = t; idx < N * K; idx += TCF_THREADS) {
+      const int j = idx / K, k = idx - j * K;
+      const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
+      float h, lo;
+      tc::split_tf32(v, h, lo);
+      *reinterpret_cast<float*>(wst + tc::canon_off(j, k, cs)) = h;
+      *reinterpret_cast<float*>(wst + tc::canon_off(N + j, k, cs)) = lo;
+    }
+    for (int j = t; j < N; j += TCF_THREADS) bias[p.bias_off[l] + j] = (j < nr && p.b[l]) ? __ldg(p.b[l] + j) : 0.f;
+  }
+  if (t == 0) {
+    tc::mbar_init(&bar_full[0], TCF_SLOT_THREADS), tc::mbar_init(&bar_full[1], TCF_SLOT_THREADS);
+    tc::mbar_init(&bar_done[0], 1), tc::mbar_init(&bar_done[1], 1);
+  }
+  if (warp == ISSUER_WARP) tc::tmem_alloc<256>(&tmem_slot);
+  tc::fence_smem_to_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+  const int L = p.n_layers;
+
+  if (warp < ISSUER_WARP) {
+    // ------------------------------------------------------------------ workers
+    const int s = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    uint8_t* Ah = smem + (size_t)s * 2 * TC_TILE_BYTES;
+    uint8_t* Al = Ah + TC_TILE_BYTES;
+    const uint32_t tm = tmem + (uint32_t)(s * 128) + ((uint32_t)(quarter * 32) << 16);
+    uint32_t ph_done = 0;
+    const bool xvec = quad_ok(x, x_stride);
+    const int in_chunks = p.in_pad >> 2;
+    float4 xn[16];  // the next tile's input row, loaded a whole tile ahead so its DRAM latency is never exposed
+    auto load_x = [&](int64_t tile) {
+      const int64_t row = tile * TC_ROWS + r;
+      const bool live = tile < n_tiles && row < n;
+      const float* src = x + row * x_stride;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int c = 4 * q;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < in_chunks && live && c < p.in_dim) {
+          if (xvec) {  // a chunk that starts below in_dim lies inside the row's storage (stride % 4 == 0)
+            v = ldg4_early(src + c);
+          } else {
+            v.x = ldg1_early(src + c);
+            if (c + 1 < p.in_dim) v.y = ldg1_early(src + c + 1);
+            if (c + 2 < p.in_dim) v.z = ldg1_early(src + c + 2);
+            if (c + 3 < p.in_dim) v.w = ldg1_early(src + c + 3);
+          }
+        }
+        xn[q] = v;
+      }
+    };
+    // one 16-byte chunk (4 columns of this thread's row) as hi / lo into the slot's operand tiles
+    auto put4 = [&](int c, const float4 v) {
+      float4 h, lo;
+      tc::split_tf32(v.x, h.x, lo.x), tc::split_tf32(v.y, h.y, lo.y);
+      tc::split_tf32(v.z, h.z, lo.z), tc::split_tf32(v.w, h.w, lo.w);
+      const uint32_t off = tc::canon_off(r, c, TC_CS_A);
+      *reinterpret_cast<float4*>(Ah + off) = h;
+      *reinterpret_cast<float4*>(Al + off) = lo;
+    };
+    load_x((int64_t)blockIdx.x + (int64_t)s * gridDim.x);
+    for (int64_t k = s;; k += 2) {
+      const int64_t tile = (int64_t)blockIdx.x + k * gridDim.x;
+      if (tile >= n_tiles) break;
+      const int64_t row = tile * TC_ROWS + r;
+      const bool live = row < n;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if (q < in_chunks) {
+          float4 v = xn[q];
+          const int c = 4 * q;  // zero the tail of a chunk that straddles in_dim
+          if (c + 1 >= p.in_dim) v.y = 0.f;
+          if (c + 2 >= p.in_dim) v.z = 0.f;
+          if (c + 3 >= p.in_dim) v.w = 0.f;
+          put4(c, v);
+        }
+      }
+      load_x(tile + 2 * (int64_t)gridDim.x);
+      tc::fence_smem_to_async();
+      tc::fence_before_sync();  // orders this thread's TMEM reads of the previous tile before the issuer's next MMA
+      tc::mbar_arrive(&bar_full[s]);
+      for (int l = 0; l < L; ++l) {
+        const int N = p.N[l], nr = p.nr[l];
+        const bool last = (l == L - 1);
+        const int act = last ? p.out_act : p.hidden_act;
+        tc::mbar_wait(&bar_done[s], ph_done);
+        __syncwarp();
+        ph_done ^= 1;
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int cc = 0; cc < N; cc += 16) {
+          float v[16], v2[16];
+          tc::ld16(tm + (uint32_t)cc, v);
+          tc::ld16(tm + (uint32_t)(N + cc), v2);  // the A_hi W_lo partial product
+#pragma unroll
+          for (int c = 0; c < 16; ++c) v[c] += v2[c];
+          // padded columns: zero weights and zero bias give act(0) = 0 for ReLU / identity (sigmoid only ends a net)
+          bias_act_slice(act, v, bias + p.bias_off[l] + cc, nr - cc);
+          if (!last) {
+            if (hidden != nullptr && live) {
+              float* h = hidden + p.hid_off[l] * n + row * nr + cc;
+#pragma unroll
+              for (int c = 0; c < 16; c += 4)
+                if (cc + c < nr) *reinterpret_cast<float4*>(h + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c += 4) put4(cc + c, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
+          } else if (live) {
+            float* yr = y + row * nr + cc;
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+              if (cc + c < nr) yr[c] = v[c];
+          }
+        }
+        if (!last) {
+          tc::fence_smem_to_async();
+          tc::fence_before_sync();
+          tc::mbar_arrive(&bar_full[s]);
+        }
+      }
+    }
+  } else if (t == TCF_WORKERS) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    uint32_t ph_full0 = 0u, ph_full1 = 0u;
+    for (int64_t k0 = 0; (int64_t)blockIdx.x + k0 * gridDim.x < n_tiles; k0 += 2) {
+      for (int l = 0; l < L; ++l) {
+        const int N = p.N[l], K = p.K[l];
+        const uint32_t cs = (uint32_t)(2 * N) * 16u;
+        const uint32_t wst = tc::smem_u32(Wr + p.w_off[l]);
+        // descriptors differ between k-steps only in the start-address field (bits 0-13, units of 16 B)
+        const uint64_t da = (uint64_t)((2 * TC_CS_A) >> 4), db = (uint64_t)((2 * cs) >> 4);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if ((int64_t)blockIdx.x + (k0 + s) * gridDim.x >= n_tiles) continue;
+          if (s == 0) {
+            tc::mbar_wait(&bar_full[0], ph_full0);
+            ph_full0 ^= 1;
+          } else {
+            tc::mbar_wait(&bar_full[1], ph_full1);
+            ph_full1 ^= 1;
+          }
+          tc::fence_after_sync();
+          const uint32_t d = tmem + (uint32_t)(s * 128);
+          const uint32_t ah = tc::smem_u32(smem + (size_t)s * 2 * TC_TILE_BYTES), al = ah + TC_TILE_BYTES;
+          uint32_t acc = 0;
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {  // pass 0: A_hi x [W_hi; W_lo] (N' = 2N), pass 1: A_lo x W_hi (N' = N)
+            const uint32_t idesc = tc::make_idesc_tf32(TC_ROWS, pass ? N : 2 * N, false, false);
+            uint64_t ad = tc::make_desc(pass ? al : ah, TC_CS_A, 128), bd = tc::make_desc(wst, cs, 128);
+#pragma unroll 2
+            for (int ks = 0; ks < K / 8; ++ks) {
+              tc::mma_tf32(d, ad, bd, idesc, acc);
+              ad += da, bd += db;
+              acc = 1;
+            }
+          }
+          tc::commit(&bar_done[s]);
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == ISSUER_WARP) {
+    __syncwarp();
+    tc::tmem_dealloc<256>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_constant__ TcParams p,
@@ -701,6 +906,15 @@ static int tc_build(const B2nMlp* m, const B2nMlpGrad* g, TcParams& p, bool tran
   return 0;
 }
 
+static int g_tc_fwd_slots = 2;  // 2: warp-specialised two-slot kernel (default), 1: serial kernel
+int b2n_tune_mlp_tc(const char* key, int value) {
+  if (strcmp(key, "tc_fwd_slots") == 0 && (value == 1 || value == 2)) {
+    g_tc_fwd_slots = value;
+    return 1;
+  }
+  return 0;
+}
+
 static int tc_smem_limit() {
   static int lim = 0;
   if (!lim) {
@@ -719,10 +933,16 @@ extern "C" int b2n_mlp_tc_fwd(const B2nMlp* mlp_host, const float* x, int64_t x_
   B2N_UNSUPPORTED(tc_build(mlp_host, nullptr, p, false) != 0,
                   "tensor-core MLP: needs <= 4 layers, widths <= 64 (hidden % 4 == 0), ReLU hidden, no skips");
   B2N_REQUIRE(x_stride >= mlp_host->in_dim, "x_stride smaller than in_dim");
+  const int grid = (int)min(div_up(n, TC_ROWS), (int64_t)b2n_sm_count());
+  const size_t smem2 = 4 * TC_TILE_BYTES + p.w_total + 4 * 64 * TC_MAXL + 1024;
+  if (g_tc_fwd_slots == 2 && smem2 <= (size_t)tc_smem_limit()) {  // two tiles in flight (needs room for 4 operand tiles)
+    cudaFuncSetAttribute(mlp_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    mlp_tc_fwd2_kernel<<<grid, TCF_THREADS, smem2, (cudaStream_t)stream>>>(p, x, x_stride, n, y, hidden);
+    B2N_LAUNCH_CHECK();
+  }
   const size_t smem = 2 * TC_TILE_BYTES + p.w_total + 4 * 64 * TC_MAXL + 1024;
   B2N_UNSUPPORTED(smem > (size_t)tc_smem_limit(), "tensor-core MLP: shared memory");
   cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = (int)min(div_up(n, TC_ROWS), (int64_t)b2n_sm_count());
   mlp_tc_fwd_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, x, x_stride, n, y, hidden);
   B2N_LAUNCH_CHECK();
 }

@@ -116,6 +116,11 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = [], ret
     _lib = lib
+    # B2N_TUNE="key=value,key=value": launch-geometry / kernel-variant knobs applied once at load (see b2n_tune)
+    for kv in filter(None, os.environ.get("B2N_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        if not lib.b2n_tune(k.encode(), int(v)):
+            raise RuntimeError(f"B2N_TUNE: unknown tuning key {k!r}")
     return lib
 
 

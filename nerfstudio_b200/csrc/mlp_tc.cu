@@ -684,6 +684,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row = tile * TC_ROWS + r;
     const bool live = row < n;
+    {  // pull the NEXT tile's rows (dy, y, every layer's input slice) into L2: no registers, and the register
+       // prefetches one layer ahead then see L2 latency instead of DRAM latency
+      const int64_t nrow = row + (int64_t)gridDim.x * TC_ROWS;
+      if (nrow < n) {
+        if (c0 == 0) {
+          tc::prefetch_l2(dy + nrow * p.nr[L - 1]);
+          tc::prefetch_l2(y + nrow * p.nr[L - 1]);
+        }
+        if (c0 < p.K[0]) tc::prefetch_l2(x + nrow * x_stride + c0);
+        for (int l = 1; l < L; ++l)
+          if (c0 < p.K[l]) tc::prefetch_l2(hidden + p.hid_off[l - 1] * n + nrow * p.kr[l] + c0);
+      }
+    }
     float dz[TC_HALF], a[TC_HALF];
     {  // dZ of the last layer = dy * act'(y)   (this thread's column half)
       const int nr = p.nr[L - 1];

@@ -109,6 +109,8 @@ __device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 3xTF32 split: hi keeps the top 19 bits (exactly representable in tf32), lo = a - hi (exact in fp32)
 __device__ __forceinline__ void split_tf32(float a, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);

@@ -112,3 +112,31 @@ def test_mlp_tc_rejects_unsupported(F):
     with pytest.raises(ValueError):
         F.mlp_tc_forward(spec, torch.randn(8, 63).cuda(), [torch.randn(256, 63).cuda(), torch.randn(256, 256).cuda(),
                                                            torch.randn(3, 256).cuda()], [None] * 3, False)
+
+
+@pytest.mark.parametrize("name", ["base", "head", "deep"])
+def test_forward_variants_agree_bitwise(F, name):
+    """The serial kernel and the two-slot warp-specialised kernel issue the same MMA sequence per tile: identical bits."""
+    from nerfstudio_b200 import lib
+
+    in_dim, dims, out_act = CFGS[name]
+    torch.manual_seed(zlib.crc32(name.encode()) % 1000 + 1)
+    n = 128 * 149 + 5  # one CTA gets two tiles (both slots busy), the others one
+    spec = F.MlpSpec(in_dim, dims, out_act=out_act)
+    x = torch.randn(n, in_dim, device="cuda")
+    ws, prev = [], in_dim
+    for d in dims:
+        ws.append(torch.randn(d, prev, device="cuda") / prev ** 0.5)
+        prev = d
+    bs = [torch.randn(d, device="cuda") * 0.1 for d in dims]
+    outs = []
+    try:
+        for slots in (1, 2):
+            assert lib.tune("tc_fwd_slots", slots)
+            y, hidden = F.mlp_tc_forward(spec, x, ws, bs, save_hidden=True)
+            torch.cuda.synchronize()
+            outs.append((y.clone(), hidden.clone()))
+    finally:
+        lib.tune("tc_fwd_slots", 2)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])

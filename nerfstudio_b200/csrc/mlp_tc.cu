@@ -7,12 +7,15 @@
 // so the 1e-4 parity bar holds.  The tensor pipe is nowhere near its limit on K,N <= 64; what the kernel buys is
 // that the 2.1 ms/step the SIMT kernels spend in FFMA disappears into operand staging.
 //
-// Structure (one persistent CTA of 512 threads per SM; threads t, t+128, t+256, t+384 own row t&127 of the tile
-// (== TMEM lane) and its columns are split 4 ways — warps w, w+4, w+8, w+12 share TMEM quarter w&3 (16 warps/SM):
-//   forward  : x row -> hi/lo -> smem (K-major canonical, float4 stores) -> per layer: thread 0 issues the MMAs,
-//              tcgen05.commit -> mbarrier; everyone tcgen05.ld's their row, bias + activation, saves the hidden
-//              row (row-major) for backward, writes the next layer's operand.
-//   backward : per layer  dA = dZ W      A = dZ tile (K-major), B = W^T copy (K-major)            -> TMEM -> regs
+// Structure (persistent CTAs, one per SM; a tile = 128 rows = 128 TMEM lanes):
+//   forward  : default = the warp-specialised two-slot kernel (mlp_tc_fwd2_kernel, see its header); the serial kernel
+//              (mlp_tc_fwd_kernel: x row -> hi/lo -> smem (K-major canonical, float4 stores) -> per layer: thread 0
+//              issues the MMAs, tcgen05.commit -> mbarrier; everyone tcgen05.ld's their row, bias + activation, saves
+//              the hidden row (row-major) for backward, writes the next layer's operand) is kept as the reference
+//              variant.  Weights: hi and lo halves stacked along N -> 2 MMA streams per layer.
+//   backward : 512 threads; threads t, t+128, t+256, t+384 own row t&127 and 16 of its columns (warps w, w+4, w+8,
+//              w+12 share TMEM quarter w&3).  Per layer
+//                         dA = dZ W      A = dZ tile (K-major), B = W^T copy (K-major, hi/lo stacked)  -> TMEM -> regs
 //                         dW += dZ^T A   operands are the transposed tiles (feature x point), written by scalar
 //                                        conflict-free stores; hi and lo of dZ^T are STACKED along M (rows 0-63 /
 //                                        64-127) so one M=128 MMA yields both partial products; a row of ones

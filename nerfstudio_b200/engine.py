@@ -336,7 +336,12 @@ class NerfactoStep:
         update = self._update_due(t)
         overlap = self.allreduce is not None and world > 1
         if self.use_graph and update not in self._graphs:
-            self._capture(update)
+            self._capture(update, split=overlap)
+        if self.use_graph and not overlap:
+            # single process: the whole step is ONE graph launch
+            self._graphs[update][3].replay()
+            return self._finish_step(update)
+
         def run(i: int) -> None:
             if self.use_graph:
                 g = self._graphs[update][i]
@@ -354,15 +359,19 @@ class NerfactoStep:
         if overlap:
             self.allreduce.finish(h_field, h_prop)
         run(2)
+        return self._finish_step(update)
+
+    def _finish_step(self, update: bool) -> Tensor:
         if update:
             self._steps_since_update = 0
         self._steps_since_update += 1
         self.step_count += 1
-        o.steps += 1
+        self.optim.steps += 1
         return self.losses
 
-    def _capture(self, update: bool) -> None:
-        """Warm the kernels up on a side stream (loads modules, sizes smem attributes), then capture."""
+    def _capture(self, update: bool, split: bool) -> None:
+        """Warm the kernels up on a side stream (loads modules, sizes smem attributes), then capture: three graphs
+        (forward + main backward | proposal backward | Adam) when collectives run between them, else one."""
         saved = [t.clone() for t in (self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq)]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -374,6 +383,16 @@ class NerfactoStep:
         torch.cuda.synchronize()
         for dst, src in zip((self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq), saved):
             dst.copy_(src)  # the warm-up pass must not count as an optimisation step
+        if not split:
+            # single process: no collective between the pieces, so the whole step is ONE graph
+            g_all = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_all):
+                self._body(update)
+                if update:
+                    self._body_props(update)
+                self._adam()
+            self._graphs[update] = (None, None, None, g_all)
+            return
         g_main, g_props, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_main):
             self._body(update)
@@ -384,4 +403,4 @@ class NerfactoStep:
             g_props = None  # nothing to replay when the proposal networks are frozen this step
         with torch.cuda.graph(g_adam, pool=g_main.pool()):
             self._adam()
-        self._graphs[update] = (g_main, g_props, g_adam)
+        self._graphs[update] = (g_main, g_props, g_adam, None)

@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
     // [A_hi W_hi | A_hi W_lo] and a second N'=N stream adds A_lo W_hi onto the first half — 2 streams instead of 3
     uint8_t* wst = Wr + p.w_off[l];
     const uint32_t cs = (uint32_t)(2 * N) * 16u;
+#pragma unroll 4
     for (int idx = t; idx < N * K; idx += TC_THREADS) {
       const int j = idx / K, k = idx - j * K;
       const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
@@ -434,6 +435,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __gri
     const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
     uint8_t* wst = Wr + p.w_off[l];
     const uint32_t cs = (uint32_t)(2 * N) * 16u;
+#pragma unroll 4
     for (int idx = t; idx < N * K; idx += TCF_THREADS) {
       const int j = idx / K, k = idx - j * K;
       const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
@@ -523,6 +525,8 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __gri
         const int N = p.N[l], nr = p.nr[l];
         const bool last = (l == L - 1);
         const int act = last ? p.out_act : p.hidden_act;
+        const float* bl = bias + p.bias_off[l];
+        float* hrow = (!last && hidden != nullptr && live) ? hidden + p.hid_off[l] * n + row * nr : nullptr;
         tc::mbar_wait(&bar_done[s], ph_done);
         __syncwarp();
         ph_done ^= 1;
@@ -535,10 +539,10 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __gri
 #pragma unroll
           for (int c = 0; c < 16; ++c) v[c] += v2[c];
           // padded columns: zero weights and zero bias give act(0) = 0 for ReLU / identity (sigmoid only ends a net)
-          bias_act_slice(act, v, bias + p.bias_off[l] + cc, nr - cc);
+          bias_act_slice(act, v, bl + cc, nr - cc);
           if (!last) {
-            if (hidden != nullptr && live) {
-              float* h = hidden + p.hid_off[l] * n + row * nr + cc;
+            if (hrow != nullptr) {
+              float* h = hrow + cc;
 #pragma unroll
               for (int c = 0; c < 16; c += 4)
                 if (cc + c < nr) *reinterpret_cast<float4*>(h + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
@@ -635,6 +639,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
     // MMA's N: dA = [dZ_hi W_hi | dZ_hi W_lo] (N' = 2K) + dZ_lo W_hi (N' = K) in two streams
     uint8_t* wst = Wr + p.w_off[l];
     const uint32_t cs = (uint32_t)(2 * K) * 16u;
+#pragma unroll 4
     for (int idx = t; idx < N * K; idx += TC_THREADS) {
       const int j = idx / K, k = idx - j * K;
       const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;

@@ -105,15 +105,20 @@ class NerfactoStep:
         R = n_rays
         f32 = dict(device=dev, dtype=torch.float32)
         # ---- static inputs
-        self.origins, self.directions = torch.zeros(R, 3, **f32), torch.zeros(R, 3, **f32)
-        self.cams = torch.zeros(R, device=dev, dtype=torch.int64)
-        self.gt = torch.zeros(R, 3, **f32)
+        # one device blob [camera indices (int64) | origins | directions | gt rgb]: a packed pinned host batch
+        # (pack_batch) reaches the GPU with a single async copy; the four tensors are views of it
+        self.inputs = torch.zeros(11 * R, **f32)
+        self.cams = self.inputs[: 2 * R].view(torch.int64)
+        self.origins = self.inputs[2 * R: 5 * R].view(R, 3)
+        self.directions = self.inputs[5 * R: 8 * R].view(R, 3)
+        self.gt = self.inputs[8 * R: 11 * R].view(R, 3)
         self.nears = torch.full((R,), float(cfg.near_plane), **f32)
         self.fars = torch.full((R,), float(cfg.far_plane), **f32)
         self.hyper = torch.zeros(4, **f32)  # lr/bc1, 1/sqrt(bc2), grad_scale, anneal
         # pinned staging ring for the per-step scalars: a slot is rewritten only after the async H2D copy that read it
         # has completed (the CPU may run many steps ahead of the stream)
         self._hyper_ring = torch.zeros(self.HYPER_SLOTS, 4, dtype=torch.float32).pin_memory()
+        self._hyper_np = self._hyper_ring.numpy()  # same memory; one vectorised write per step
         self._hyper_events: List[Optional[torch.cuda.Event]] = [None] * self.HYPER_SLOTS
         self.lin0 = torch.linspace(0.0, 1.0, self.S[0] + 1).to(dev)
         self.u_base = [torch.linspace(0.0, 1.0 - 1.0 / (s + 1), s + 1).to(dev) for s in self.S[1:]]
@@ -301,6 +306,20 @@ class NerfactoStep:
         self.cams.copy_(camera_indices.reshape(-1), non_blocking=True)
         self.gt.copy_(gt_rgb, non_blocking=True)
 
+    def pack_batch(self, origins: Tensor, directions: Tensor, camera_indices: Tensor, gt_rgb: Tensor) -> Tensor:
+        """A pinned host blob in the layout of the static input buffer (what a data loader would hand over)."""
+        R = self.R
+        blob = torch.empty(11 * R, dtype=torch.float32).pin_memory()
+        blob[: 2 * R].view(torch.int64).copy_(camera_indices.reshape(-1))
+        blob[2 * R: 5 * R].view(R, 3).copy_(origins)
+        blob[5 * R: 8 * R].view(R, 3).copy_(directions)
+        blob[8 * R: 11 * R].view(R, 3).copy_(gt_rgb)
+        return blob
+
+    def set_batch_packed(self, blob: Tensor) -> None:
+        """One H2D (or D2D) copy of a batch laid out by pack_batch."""
+        self.inputs.copy_(blob, non_blocking=True)
+
     def _anneal(self, step: int) -> float:
         c = self.cfg
         if not c.use_proposal_weight_anneal:
@@ -324,12 +343,9 @@ class NerfactoStep:
         slot = t % self.HYPER_SLOTS
         if self._hyper_events[slot] is not None:
             self._hyper_events[slot].synchronize()
-        host = self._hyper_ring[slot]
-        host[0] = lr / (1.0 - o.betas[0] ** (t + 1))
-        host[1] = 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1))
-        host[2] = 1.0 / world
-        host[3] = self._anneal(t)
-        self.hyper.copy_(host, non_blocking=True)
+        self._hyper_np[slot] = (lr / (1.0 - o.betas[0] ** (t + 1)), 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1)),
+                                1.0 / world, self._anneal(t))
+        self.hyper.copy_(self._hyper_ring[slot], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
         self._hyper_events[slot] = ev

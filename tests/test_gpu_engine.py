@@ -162,3 +162,17 @@ def test_graph_engine_converges_like_autograd_on_teacher_scene(cuda):
         res[name] = (start, max(late))
     assert res["graph"][1] > res["graph"][0] + 8.0, res
     assert abs(res["graph"][1] - res["autograd"][1]) < 5.0, res
+
+
+def test_packed_batch_equals_set_batch(cuda, golden):
+    """pack_batch + set_batch_packed (one copy) fill the static inputs exactly like set_batch (four copies)."""
+    g = golden("nerfacto_pipeline")
+    model, eng = _mk(g, use_graph=False)
+    ref = [t.clone() for t in (eng.origins, eng.directions, eng.cams, eng.gt)]
+    blob = eng.pack_batch(g["origins"], g["directions"], g["train_cams"], g["gt"])
+    assert blob.is_pinned()
+    eng.inputs.zero_()
+    eng.set_batch_packed(blob)
+    torch.cuda.synchronize()
+    for a, b in zip(ref, (eng.origins, eng.directions, eng.cams, eng.gt)):
+        assert torch.equal(a, b)

@@ -214,6 +214,17 @@ int b2n_raygen(const float* c2w, const float* intr, const float* dist, const int
 int b2n_aabb_collide(const float* origins, const float* directions, const float* aabb_host6, float near_plane,
                      int64_t n_rays, float* nears, float* fars, void* stream);
 
+/* CameraOptimizer.apply_to_raybundle, mode SO3xR3 (cameras/camera_optimizers.py:148-153; exponential map
+ * cameras/lie_groups.py:25-58): out_origins = origins + t[cam], out_directions = R(w[cam]) directions with
+ * pose_adjustment [C,6] = (t | w).  frozen: optional uint8 [C], 1 = non-trainable camera (identity, no gradient;
+ * camera_optimizers.py:127-131).  bwd ACCUMULATES d_pose_adjustment [C,6]; either upstream gradient may be NULL. */
+int b2n_pose_apply_fwd(const float* pose_adjustment, const int64_t* camera_indices, const uint8_t* frozen,
+                       const float* origins, const float* directions, int64_t n_rays, float* out_origins,
+                       float* out_directions, void* stream);
+int b2n_pose_apply_bwd(const float* pose_adjustment, const int64_t* camera_indices, const uint8_t* frozen,
+                       const float* directions, const float* d_out_origins, const float* d_out_directions,
+                       int64_t n_rays, float* d_pose_adjustment, void* stream);
+
 /* ---- K7-K12: packed (instant-ngp) path; nerfacc 0.5.2 call sites models/instant_ngp.py:120-198 ----------
  * pack_info: ray_indices int64 [M] sorted -> packed_info int64 [R,2] (start,count). */
 int b2n_pack_info(const int64_t* ray_indices, int64_t m, int64_t n_rays, int64_t* packed_info, void* stream);

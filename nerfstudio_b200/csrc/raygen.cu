@@ -123,3 +123,130 @@ extern "C" int b2n_aabb_collide(const float* origins, const float* directions, c
   aabb_collide_kernel<<<(unsigned)div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(box, origins, directions, near_plane, n_rays, nears, fars);
   B2N_LAUNCH_CHECK();
 }
+
+// ------------------------------------------------------------------------------------------------
+// a4: CameraOptimizer.apply_to_raybundle, mode SO3xR3 (cameras/camera_optimizers.py:148-153 with the exponential
+// map of cameras/lie_groups.py:25-58 evaluated per ray): origins += t[cam], directions = R(w[cam]) directions with
+//   theta = sqrt(max(|w|^2, 1e-4)), R = I + sin(theta)/theta K + (1 - cos(theta))/theta^2 K^2, K = skew(w).
+// The backward follows the same chain of elementary operations the reference's autograd differentiates
+// (f1 = inv*sin, f2 = inv*inv*(1-cos), K^2 by matrix product, clamp passing the gradient where |w|^2 >= 1e-4).
+// ------------------------------------------------------------------------------------------------
+struct PoseTerms {
+  float K[3][3], K2[3][3], f1, f2, inv, s, c, theta, n;
+};
+
+__device__ __forceinline__ void pose_terms(const float* __restrict__ w, PoseTerms& p) {
+  const float w0 = w[0], w1 = w[1], w2 = w[2];
+  p.n = w0 * w0 + w1 * w1 + w2 * w2;
+  p.theta = sqrtf(fmaxf(p.n, 1e-4f));
+  p.inv = 1.f / p.theta;
+  p.s = sinf(p.theta), p.c = cosf(p.theta);
+  p.f1 = p.inv * p.s;
+  p.f2 = p.inv * p.inv * (1.f - p.c);
+  p.K[0][0] = 0.f, p.K[0][1] = -w2, p.K[0][2] = w1;
+  p.K[1][0] = w2, p.K[1][1] = 0.f, p.K[1][2] = -w0;
+  p.K[2][0] = -w1, p.K[2][1] = w0, p.K[2][2] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) p.K2[i][j] = p.K[i][0] * p.K[0][j] + p.K[i][1] * p.K[1][j] + p.K[i][2] * p.K[2][j];
+}
+
+__global__ void pose_apply_fwd_kernel(const float* __restrict__ pose, const int64_t* __restrict__ cam,
+                                      const uint8_t* __restrict__ frozen, const float* __restrict__ o,
+                                      const float* __restrict__ d, int64_t n, float* __restrict__ out_o,
+                                      float* __restrict__ out_d) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t c = __ldg(cam + i);
+  const float d0 = __ldg(d + 3 * i), d1 = __ldg(d + 3 * i + 1), d2 = __ldg(d + 3 * i + 2);
+  if (frozen != nullptr && frozen[c]) {  // non-trainable camera: identity transform
+    out_o[3 * i] = __ldg(o + 3 * i), out_o[3 * i + 1] = __ldg(o + 3 * i + 1), out_o[3 * i + 2] = __ldg(o + 3 * i + 2);
+    out_d[3 * i] = d0, out_d[3 * i + 1] = d1, out_d[3 * i + 2] = d2;
+    return;
+  }
+  float t[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) t[k] = __ldg(pose + 6 * c + k);
+  PoseTerms p;
+  pose_terms(t + 3, p);
+  const float dv[3] = {d0, d1, d2};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    out_o[3 * i + a] = __ldg(o + 3 * i + a) + t[a];
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc += (p.f1 * p.K[a][j] + p.f2 * p.K2[a][j] + (a == j ? 1.f : 0.f)) * dv[j];
+    out_d[3 * i + a] = acc;
+  }
+}
+
+__global__ void pose_apply_bwd_kernel(const float* __restrict__ pose, const int64_t* __restrict__ cam,
+                                      const uint8_t* __restrict__ frozen, const float* __restrict__ d,
+                                      const float* __restrict__ g_o, const float* __restrict__ g_d, int64_t n,
+                                      float* __restrict__ d_pose) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t c = __ldg(cam + i);
+  if (frozen != nullptr && frozen[c]) return;
+  float w[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[k] = __ldg(pose + 6 * c + 3 + k);
+  PoseTerms p;
+  pose_terms(w, p);
+  float dR[3][3];  // dL/dR = g_d d^T
+  float df1 = 0.f, df2 = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      dR[a][j] = (g_d ? __ldg(g_d + 3 * i + a) : 0.f) * __ldg(d + 3 * i + j);
+      df1 += dR[a][j] * p.K[a][j];
+      df2 += dR[a][j] * p.K2[a][j];
+    }
+  // K2 = K K  =>  dK = f1 dR + f2 (dR K^T + K^T dR)
+  float dK[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t += dR[a][k] * p.K[j][k] + p.K[k][a] * dR[k][j];
+      dK[a][j] = p.f1 * dR[a][j] + p.f2 * t;
+    }
+  float dw[3] = {dK[2][1] - dK[1][2], dK[0][2] - dK[2][0], dK[1][0] - dK[0][1]};
+  // f1 = inv*s, f2 = inv*inv*(1-c), inv = 1/theta, theta = sqrt(clamp(n, 1e-4)), n = w.w
+  const float dinv = df1 * p.s + df2 * 2.f * p.inv * (1.f - p.c);
+  float dtheta = df1 * p.inv * p.c + df2 * p.inv * p.inv * p.s;
+  dtheta -= dinv * p.inv * p.inv;
+  const float dn = (p.n >= 1e-4f) ? dtheta * 0.5f / p.theta : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) dw[k] += 2.f * w[k] * dn;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (g_o) atomicAdd(d_pose + 6 * c + k, __ldg(g_o + 3 * i + k));
+    atomicAdd(d_pose + 6 * c + 3 + k, dw[k]);
+  }
+}
+
+extern "C" int b2n_pose_apply_fwd(const float* pose_adjustment, const int64_t* camera_indices, const uint8_t* frozen,
+                                  const float* origins, const float* directions, int64_t n_rays, float* out_origins,
+                                  float* out_directions, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(pose_adjustment && camera_indices && origins && directions && out_origins && out_directions, "null pointer");
+  pose_apply_fwd_kernel<<<(unsigned)div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+      pose_adjustment, camera_indices, frozen, origins, directions, n_rays, out_origins, out_directions);
+  B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_pose_apply_bwd(const float* pose_adjustment, const int64_t* camera_indices, const uint8_t* frozen,
+                                  const float* directions, const float* d_out_origins, const float* d_out_directions,
+                                  int64_t n_rays, float* d_pose_adjustment, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(pose_adjustment && camera_indices && directions && d_pose_adjustment, "null pointer");
+  B2N_REQUIRE(d_out_origins || d_out_directions, "no upstream gradient");
+  pose_apply_bwd_kernel<<<(unsigned)div_up(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+      pose_adjustment, camera_indices, frozen, directions, d_out_origins, d_out_directions, n_rays, d_pose_adjustment);
+  B2N_LAUNCH_CHECK();
+}

@@ -715,6 +715,41 @@ def aabb_collide(origins: Tensor, directions: Tensor, aabb: Sequence[float], nea
     return n, f
 
 
+class _PoseApplyFn(torch.autograd.Function):
+    """CameraOptimizer.apply_to_raybundle (SO3xR3): gradients flow to pose_adjustment only (rays are data)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, pose, cams, frozen, origins, directions):
+        pose, o, d = _c(pose), _c(origins.float()), _c(directions.float())
+        cams = _c(cams.reshape(-1).to(torch.int64))
+        R = o.shape[0]
+        out_o, out_d = torch.empty_like(o), torch.empty_like(d)
+        call("b2n_pose_apply_fwd", ptr(pose), ptr(cams, torch.int64), ptr(frozen, torch.uint8), ptr(o), ptr(d), R,
+             ptr(out_o), ptr(out_d), stream())
+        ctx.save_for_backward(pose, cams, d)
+        ctx.frozen = frozen
+        return out_o, out_d
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g_o, g_d):
+        pose, cams, d = ctx.saved_tensors
+        d_pose = torch.zeros_like(pose)
+        g_o = None if g_o is None else _c(g_o.float())
+        g_d = None if g_d is None else _c(g_d.float())
+        if g_o is not None or g_d is not None:
+            call("b2n_pose_apply_bwd", ptr(pose), ptr(cams, torch.int64), ptr(ctx.frozen, torch.uint8), ptr(d), ptr(g_o),
+                 ptr(g_d), d.shape[0], ptr(d_pose), stream())
+        return d_pose, None, None, None, None
+
+
+def pose_apply(pose_adjustment: Tensor, camera_indices: Tensor, origins: Tensor, directions: Tensor,
+               frozen: Optional[Tensor] = None):
+    """(origins + t[cam], R(w[cam]) @ directions) for pose_adjustment [C,6] = (t | w); frozen: uint8 [C] or None."""
+    return _PoseApplyFn.apply(pose_adjustment, camera_indices, frozen, origins, directions)
+
+
 # ----------------------------------------------------------------------------------------
 # packed path
 # ----------------------------------------------------------------------------------------

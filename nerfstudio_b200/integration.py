@@ -14,7 +14,9 @@ What `install()` does (each step is the binding a nerfstudio maintainer would ot
    imported from them (`from nerfstudio.fields.nerfacto_field import NerfactoField` binds at import time):
    HashEncoding / SHEncoding / NeRFEncoding, MLP / MLPWithHashEncoding, trunc_exp, NerfactoField,
    HashMLPDensityField, the samplers, RGB / accumulation / depth renderers, interlevel / distortion losses;
-3. patches `RaySamples.get_weights` (cameras/rays.py:129-152) to the warp-scan kernel.
+3. patches `RaySamples.get_weights` (cameras/rays.py:129-152) to the warp-scan kernel;
+4. patches `CameraOptimizer.apply_to_raybundle` (cameras/camera_optimizers.py:148-153) to the fused SO3xR3 kernel
+   (the module, its `pose_adjustment` parameter and every other method stay the reference's).
 
 Everything replaced keeps the reference's constructor signature, attributes and state_dict keys, so configs and
 checkpoints are untouched.  `uninstall()` restores the originals.
@@ -104,6 +106,21 @@ def install(shim_third_party: bool = True, patch_get_weights: bool = True) -> Li
         rays = importlib.import_module("nerfstudio.cameras.rays")
         _set(rays.RaySamples, "get_weights", OurSamples.get_weights)
         done.append("nerfstudio.cameras.rays.RaySamples.get_weights")
+    # 4. the camera optimiser's per-ray pose correction (cameras/camera_optimizers.py:148-153): one fused kernel for
+    #    mode SO3xR3, the reference's own code for anything else
+    cam_opt = importlib.import_module("nerfstudio.cameras.camera_optimizers")
+    from .cameras.camera_optimizers import fused_apply_to_raybundle
+
+    original_apply = cam_opt.CameraOptimizer.apply_to_raybundle
+
+    def apply_to_raybundle(self, raybundle) -> None:
+        if self.config.mode == "SO3xR3" and raybundle.origins.is_cuda:
+            fused_apply_to_raybundle(self, raybundle)
+        else:
+            original_apply(self, raybundle)
+
+    _set(cam_opt.CameraOptimizer, "apply_to_raybundle", apply_to_raybundle)
+    done.append("nerfstudio.cameras.camera_optimizers.CameraOptimizer.apply_to_raybundle")
     return done
 
 

@@ -747,3 +747,35 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, 
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
     denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
     p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# a4  CameraOptimizer (SO3xR3): nerfstudio/cameras/lie_groups.py:25-58, cameras/camera_optimizers.py:112-153,177-184
+# ----------------------------------------------------------------------------------------------------------
+def exp_map_so3xr3(tangent: Tensor) -> Tensor:
+    """[B,6] (translation | so(3) log-rotation) -> [B,3,4] = [R | t]; |w|^2 is clamped at 1e-4 before the sqrt."""
+    w = tangent[:, 3:]
+    n = (w * w).sum(1)
+    theta = torch.clamp(n, 1e-4).sqrt()
+    inv = 1.0 / theta
+    f1 = inv * theta.sin()
+    f2 = inv * inv * (1.0 - theta.cos())
+    K = torch.zeros(w.shape[0], 3, 3, dtype=w.dtype)
+    K[:, 0, 1], K[:, 0, 2] = -w[:, 2], w[:, 1]
+    K[:, 1, 0], K[:, 1, 2] = w[:, 2], -w[:, 0]
+    K[:, 2, 0], K[:, 2, 1] = -w[:, 1], w[:, 0]
+    out = torch.zeros(w.shape[0], 3, 4, dtype=w.dtype)
+    out[:, :3, :3] = f1[:, None, None] * K + f2[:, None, None] * torch.bmm(K, K) + torch.eye(3, dtype=w.dtype)[None]
+    out[:, :3, 3] = tangent[:, :3]
+    return out
+
+
+def camera_opt_apply(pose_adjustment: Tensor, camera_indices: Tensor, origins: Tensor, directions: Tensor):
+    """apply_to_raybundle: origins + t[cam], R[cam] @ directions."""
+    m = exp_map_so3xr3(pose_adjustment[camera_indices.reshape(-1)])
+    return origins + m[:, :3, 3], torch.bmm(m[:, :3, :3], directions[..., None]).squeeze(-1)
+
+
+def camera_opt_regularizer(pose_adjustment: Tensor, trans_l2_penalty: float = 1e-2, rot_l2_penalty: float = 1e-3) -> Tensor:
+    return (pose_adjustment[:, :3].norm(dim=-1).mean() * trans_l2_penalty
+            + pose_adjustment[:, 3:].norm(dim=-1).mean() * rot_l2_penalty)

@@ -509,9 +509,37 @@ def g_pipeline():
     save("nerfacto_pipeline", **out)
 
 
+def g_camera_opt():
+    """CameraOptimizer.apply_to_raybundle (SO3xR3), with the pose gradients and the regulariser."""
+    from nerfstudio.cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
+
+    torch.manual_seed(11)
+    C, R = 8, 512
+    opt = CameraOptimizer(CameraOptimizerConfig(mode="SO3xR3"), num_cameras=C, device="cpu")
+    with torch.no_grad():
+        opt.pose_adjustment.copy_(torch.randn(C, 6) * 0.05)
+        opt.pose_adjustment[0].zero_()               # the initial state: |w|^2 clamped at 1e-4
+        opt.pose_adjustment[1, 3:] *= 0.01            # below the clamp
+        opt.pose_adjustment[2, 3:] *= 20.0            # a large rotation (~1 rad)
+    o, d = make_rays(R, 5)
+    rb = bundle(o, d, cam_hi=C, seed=3)
+    opt.apply_to_raybundle(rb)
+    go, gd = torch.randn(R, 3), torch.randn(R, 3)
+    (g_pose,) = torch.autograd.grad((rb.origins * go).sum() + (rb.directions * gd).sum(), [opt.pose_adjustment])
+    loss = {}
+    opt.get_loss_dict(loss)
+    mats = opt(torch.arange(C))
+    save("camera_opt", pose=opt.pose_adjustment, cams=rb.camera_indices, origins=o, directions=d, out_origins=rb.origins,
+         out_directions=rb.directions, go=go, gd=gd, g_pose=g_pose, regularizer=loss["camera_opt_regularizer"], matrices=mats)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
-    for fn in (g_hash, g_encodings, g_mlp, g_density_field, g_nerfacto_field, g_samplers, g_render, g_losses,
-               g_raygen, g_vanilla, g_pipeline):
+    fns = (g_hash, g_encodings, g_mlp, g_density_field, g_nerfacto_field, g_samplers, g_render, g_losses,
+           g_raygen, g_vanilla, g_pipeline, g_camera_opt)
+    only = set(sys.argv[1:])  # e.g. `python tests/golden/make_golden.py g_camera_opt` regenerates one fixture
+    for fn in fns:
+        if only and fn.__name__ not in only:
+            continue
         print(fn.__name__)
         fn()

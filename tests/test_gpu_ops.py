@@ -359,3 +359,47 @@ def test_adam_vs_oracle(F):
     assert_close(pc, p, 1e-5)
     assert_close(mc, m, 1e-5)
     assert_close(vc, v, 1e-5)
+
+
+def test_camera_optimizer_pose_apply_vs_reference(F, golden):
+    """a4: fused SO3xR3 ray correction and its pose gradients vs the reference's CameraOptimizer (golden)."""
+    from nerfstudio_b200.cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
+    from nerfstudio_b200.cameras.rays import RayBundle
+
+    g = golden("camera_opt")
+    C = g["pose"].shape[0]
+    opt = CameraOptimizer(CameraOptimizerConfig(mode="SO3xR3"), num_cameras=C, device="cuda")
+    with torch.no_grad():
+        opt.pose_adjustment.copy_(g["pose"].cuda())
+    rb = RayBundle(origins=g["origins"].cuda(), directions=g["directions"].cuda(),
+                   pixel_area=torch.ones(g["origins"].shape[0], 1, device="cuda"), camera_indices=g["cams"].cuda())
+    opt.apply_to_raybundle(rb)
+    assert_close(rb.origins, g["out_origins"], 1e-6, "origins")
+    assert_close(rb.directions, g["out_directions"], 1e-5, "directions")
+    (gp,) = torch.autograd.grad((rb.origins * g["go"].cuda()).sum() + (rb.directions * g["gd"].cuda()).sum(),
+                                [opt.pose_adjustment])
+    assert_close(gp, g["g_pose"], 1e-4, "g_pose")
+    assert_close(opt(torch.arange(C, device="cuda")), g["matrices"], 1e-6, "matrices")
+    losses = {}
+    opt.get_loss_dict(losses)
+    assert_close(losses["camera_opt_regularizer"], g["regularizer"], 1e-6, "regularizer")
+
+    # non-trainable cameras: identity transform and no gradient (camera_optimizers.py:127-131)
+    frozen_idx = torch.tensor([2, 5])
+    opt2 = CameraOptimizer(CameraOptimizerConfig(mode="SO3xR3"), num_cameras=C, device="cuda",
+                           non_trainable_camera_indices=frozen_idx)
+    with torch.no_grad():
+        opt2.pose_adjustment.copy_(g["pose"].cuda())
+    rb2 = RayBundle(origins=g["origins"].cuda(), directions=g["directions"].cuda(),
+                    pixel_area=torch.ones(g["origins"].shape[0], 1, device="cuda"), camera_indices=g["cams"].cuda())
+    opt2.apply_to_raybundle(rb2)
+    is_frozen = torch.isin(g["cams"].reshape(-1), frozen_idx)
+    assert torch.equal(rb2.origins.cpu()[is_frozen], g["origins"][is_frozen])
+    assert torch.equal(rb2.directions.cpu()[is_frozen], g["directions"][is_frozen])
+    assert_close(rb2.directions.cpu()[~is_frozen], g["out_directions"][~is_frozen], 1e-5, "unfrozen directions")
+    (gp2,) = torch.autograd.grad(rb2.origins.sum() + (rb2.directions * g["gd"].cuda()).sum(), [opt2.pose_adjustment])
+    assert float(gp2[frozen_idx].abs().max()) == 0.0
+    # mode "off" leaves the bundle alone and owns no parameters
+    off = CameraOptimizer(CameraOptimizerConfig(mode="off"), num_cameras=C, device="cuda")
+    off.apply_to_raybundle(rb2)
+    assert len(list(off.parameters())) == 0

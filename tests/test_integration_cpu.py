@@ -69,3 +69,29 @@ def test_state_dict_layout_identical_to_reference(installed):
         ref.load_state_dict(a)   # our checkpoint loads into the reference ...
         ours.load_state_dict(b)  # ... and the reference's into ours
     assert torch.equal(ours_f.mlp_base.model[0].scalings, ref_f.mlp_base.model[0].scalings)
+
+
+def test_camera_optimizer_patch_keeps_reference_module(installed):
+    """install() swaps only CameraOptimizer.apply_to_raybundle; parameters / state_dict stay the reference's, our mirror
+    has the same key, and CPU bundles (no kernel available) still take the reference's own code path."""
+    import numpy as np
+
+    from nerfstudio.cameras.camera_optimizers import CameraOptimizer as RefOpt
+    from nerfstudio.cameras.camera_optimizers import CameraOptimizerConfig as RefCfg
+    from nerfstudio.cameras.rays import RayBundle as RefBundle
+    from nerfstudio_b200.cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
+
+    assert "nerfstudio.cameras.camera_optimizers.CameraOptimizer.apply_to_raybundle" in installed
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera_opt.npz"))
+    C = g["pose"].shape[0]
+    ref = RefOpt(RefCfg(mode="SO3xR3"), num_cameras=C, device="cpu")
+    ours = CameraOptimizer(CameraOptimizerConfig(mode="SO3xR3"), num_cameras=C, device="cpu")
+    assert list(ref.state_dict().keys()) == list(ours.state_dict().keys()) == ["pose_adjustment"]
+    ours.load_state_dict(ref.state_dict())
+    with torch.no_grad():
+        ref.pose_adjustment.copy_(torch.from_numpy(g["pose"]))
+    rb = RefBundle(origins=torch.from_numpy(g["origins"]), directions=torch.from_numpy(g["directions"]),
+                   pixel_area=torch.ones(g["origins"].shape[0], 1), camera_indices=torch.from_numpy(g["cams"]))
+    ref.apply_to_raybundle(rb)  # patched method, CPU tensors -> the reference's original code
+    assert torch.allclose(rb.directions, torch.from_numpy(g["out_directions"]), atol=1e-6)
+    assert torch.allclose(rb.origins, torch.from_numpy(g["out_origins"]), atol=1e-6)

@@ -289,3 +289,16 @@ def test_c_restatement_of_hash_indices(golden):
                                 sc.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(L), ctypes.c_int32(log2T),
                                 out.ctypes.data_as(ctypes.c_void_p))
         assert np.array_equal(out, g[f"{nm}_idx"].numpy()), nm
+
+
+def test_camera_optimizer_so3xr3(golden):
+    """a4: pose-corrected rays, pose gradients and the regulariser vs the reference's CameraOptimizer."""
+    g = golden("camera_opt")
+    pose = g["pose"].clone().requires_grad_(True)
+    o, d = O.camera_opt_apply(pose, g["cams"], g["origins"], g["directions"])
+    assert_close(o, g["out_origins"], 1e-6, "origins")
+    assert_close(d, g["out_directions"], 1e-6, "directions")
+    (gp,) = torch.autograd.grad((o * g["go"]).sum() + (d * g["gd"]).sum(), [pose])
+    assert_close(gp, g["g_pose"], 1e-5, "g_pose")
+    assert_close(O.exp_map_so3xr3(g["pose"]), g["matrices"], 1e-6, "matrices")
+    assert_close(O.camera_opt_regularizer(g["pose"]), g["regularizer"], 1e-6, "regularizer")

@@ -138,9 +138,25 @@ def oracle_step_factory(n_rays: int, seed: int = 0):
     return step
 
 
-def time_cpu(n_rays: int, steps: int, warmup: int):
+def pick_cpu_threads():
+    """The thread count at which the CPU port runs fastest on this host (torch's intra-op parallelism stops scaling —
+    and on a 128-thread box reverses — well before all hardware threads are used): one 256-ray step per candidate."""
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    best = (0.0, 1)
+    for c in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
+        torch.set_num_threads(c)
+        step = oracle_step_factory(256)
+        step()
+        t0 = time.perf_counter()
+        step()
+        rps = 256 / (time.perf_counter() - t0)
+        if rps > best[0]:
+            best = (rps, c)
+    return best[1], best[0]
+
+
+def time_cpu(n_rays: int, steps: int, warmup: int, threads: int):
+    torch.set_num_threads(threads)
     step = oracle_step_factory(n_rays)
     for _ in range(warmup):
         step()
@@ -148,7 +164,7 @@ def time_cpu(n_rays: int, steps: int, warmup: int):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return n_rays * steps / dt, dt / steps, cores
+    return n_rays * steps / dt, dt / steps, threads
 
 
 def run_reference(args) -> None:
@@ -157,16 +173,20 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # the full 4096-ray batch when the run stays within minutes (~2.5 s/step on 8 cores), else a bounded sample
-    n_rays = RAYS_PER_GPU if args.steps + args.warmup <= 40 else 1024
-    rps, sec, cores = time_cpu(n_rays, args.steps, args.warmup)
+    threads, rps_est = pick_cpu_threads()
+    # rays per step: the full 4096-ray batch if steps + warmup of it fit in ~150 s at the calibrated rate, else a
+    # bounded sample of the same workload (multiple of 64 rays, at least 64)
+    budget_rays = rps_est * 150.0 / max(args.steps + args.warmup, 1)
+    n_rays = int(min(RAYS_PER_GPU, max(64, (int(budget_rays) // 64) * 64)))
+    rps, sec, cores = time_cpu(n_rays, args.steps, args.warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{n_rays} rays/step of the 4096-ray batch (CPU bounded sample)"},
         "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {n_rays} rays, fwd+bwd+Adam, torch CPU fp32, {cores} threads"},
+                         "sample": f"{args.steps} steps x {n_rays} rays, fwd+bwd+Adam, torch CPU fp32, {cores} threads "
+                                   f"(fastest of 8/16/32/64/{os.cpu_count()} on this host)"},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -328,7 +348,8 @@ def run_b200(args) -> None:
                     "kernel_ms_per_step": kernel_table}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rps, sec, cores = time_cpu(512, 3, 1)
+        threads, _ = pick_cpu_threads()
+        rps, sec, cores = time_cpu(512, 3, 1, threads)
         cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
                "sample": f"3 steps x 512 rays of the same workload (fwd+bwd+Adam), torch CPU fp32, {cores} threads"}
     line = {

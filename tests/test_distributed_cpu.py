@@ -48,6 +48,33 @@ def test_flat_grad_allreduce_and_broadcast_world2():
         assert p0 == 0.0         # every replica starts from rank 0's weights
 
 
+def _worker_segments(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from nerfstudio_b200 import distributed as D
+
+    D.init_from_env("gloo")
+    ar = D.FlatGradAllReduce()
+    flat = torch.arange(12.0) * (rank + 1)  # [field segment | proposal segment], split at 8 like engine.grad_split
+    h_field = ar.start(flat[:8])            # summed while the "proposal backward" would run ...
+    flat[8:] += 100.0 * (rank + 1)          # ... which still writes the other segment
+    h_prop = ar.start(flat[8:])
+    ar.finish(h_field, h_prop)
+    out[rank] = flat.tolist()
+    dist.destroy_process_group()
+
+
+def test_segmented_async_allreduce_world2():
+    """engine.NerfactoStep at N > 1: two async collectives over views of ONE flat buffer, summed in place."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_segments, args=(2, port, out), nprocs=2, join=True)
+    expect = [3.0 * i for i in range(8)] + [3.0 * i + 300.0 for i in range(8, 12)]
+    assert out[0] == expect and out[1] == expect
+
+
 def test_single_process_allreduce_is_identity():
     sys.path.insert(0, ROOT)
     from nerfstudio_b200.distributed import FlatGradAllReduce

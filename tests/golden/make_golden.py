@@ -509,6 +509,42 @@ def g_pipeline():
     save("nerfacto_pipeline", **out)
 
 
+def g_samplers_extra():
+    """The other SpacedSampler subclasses the reference tests (tests/model_components/test_ray_sampler.py:37-86):
+    LinearDisparitySampler, SqrtSampler, LogSampler — that test's set-up (10 rays, near 2 / far 4, 15 samples) plus
+    64 rays with varied near/far, eval and single-jitter training mode."""
+    from nerfstudio.model_components.ray_samplers import LinearDisparitySampler, LogSampler, SqrtSampler
+
+    torch.manual_seed(8)
+    out = {}
+    o, d = make_rays(64, 22)
+    near, far = torch.full((64, 1), 0.05), torch.full((64, 1), 1000.0)
+    far[::3], near[::5] = 6.0, 2.0
+    rb = bundle(o, d)
+    rb.nears, rb.fars = near, far
+    rb_t = RayBundle(origins=torch.zeros(10, 3), directions=torch.ones(10, 3), pixel_area=torch.ones(10, 1))
+    col = NearFarCollider(near_plane=2, far_plane=4)
+    col.train()
+    rb_t = col(rb_t)
+    out.update(nears=near, fars=far, t_nears=rb_t.nears, t_fars=rb_t.fars)
+    for kind, cls in (("lindisp", LinearDisparitySampler), ("sqrt", SqrtSampler), ("log", LogSampler)):
+        s = cls(num_samples=15)
+        s.eval()
+        rs = s(rb_t)
+        assert rs.frustums.get_positions().shape[-2] == 15
+        out[f"{kind}_t_ebins"] = torch.cat([rs.frustums.starts[..., 0], rs.frustums.ends[:, -1:, 0]], -1)
+        for mode in ("eval", "single"):
+            s = cls(num_samples=24, single_jitter=True)
+            s.train(mode != "eval")
+            with Recorder() as rec:
+                rs = s(rb)
+            out[f"{kind}_{mode}_sbins"] = torch.cat([rs.spacing_starts[..., 0], rs.spacing_ends[:, -1:, 0]], -1)
+            out[f"{kind}_{mode}_ebins"] = torch.cat([rs.frustums.starts[..., 0], rs.frustums.ends[:, -1:, 0]], -1)
+            if rec.rands:
+                out[f"{kind}_{mode}_jitter"] = rec.rands[0]
+    save("samplers_extra", **out)
+
+
 def g_camera_opt():
     """CameraOptimizer.apply_to_raybundle (SO3xR3), with the pose gradients and the regulariser."""
     from nerfstudio.cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
@@ -536,7 +572,7 @@ def g_camera_opt():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     fns = (g_hash, g_encodings, g_mlp, g_density_field, g_nerfacto_field, g_samplers, g_render, g_losses,
-           g_raygen, g_vanilla, g_pipeline, g_camera_opt)
+           g_raygen, g_vanilla, g_pipeline, g_camera_opt, g_samplers_extra)
     only = set(sys.argv[1:])  # e.g. `python tests/golden/make_golden.py g_camera_opt` regenerates one fixture
     for fn in fns:
         if only and fn.__name__ not in only:

@@ -403,3 +403,19 @@ def test_camera_optimizer_pose_apply_vs_reference(F, golden):
     off = CameraOptimizer(CameraOptimizerConfig(mode="off"), num_cameras=C, device="cuda")
     off.apply_to_raybundle(rb2)
     assert len(list(off.parameters())) == 0
+
+
+def test_other_spaced_samplers_golden(F, golden):
+    """LinearDisparity / Sqrt / Log spacing (reference tests/model_components/test_ray_sampler.py:37-86): spacing bins
+    bit-exact; euclidean bins bit-exact for 1/x and sqrt (IEEE-rounded), ≤ 1e-6 for log/exp (libm vs CUDA ulps)."""
+    g = golden("samplers_extra")
+    for kind in ("lindisp", "sqrt", "log"):
+        tol = 1e-6 if kind == "log" else 0.0
+        _, eb = F.spaced_sample(cu(g["t_nears"]), cu(g["t_fars"]), 15, kind, None)
+        assert eb.shape == (10, 16)
+        assert_close(eb, g[f"{kind}_t_ebins"], tol, f"{kind} test set-up")
+        for mode in ("eval", "single"):
+            jit = g.get(f"{kind}_{mode}_jitter")
+            sb, eb = F.spaced_sample(cu(g["nears"]), cu(g["fars"]), 24, kind, cu(jit) if jit is not None else None)
+            assert torch.equal(sb.cpu(), g[f"{kind}_{mode}_sbins"].expand(64, -1)), (kind, mode)
+            assert_close(eb, g[f"{kind}_{mode}_ebins"], tol, f"{kind} {mode}")

@@ -302,3 +302,17 @@ def test_camera_optimizer_so3xr3(golden):
     assert_close(gp, g["g_pose"], 1e-5, "g_pose")
     assert_close(O.exp_map_so3xr3(g["pose"]), g["matrices"], 1e-6, "matrices")
     assert_close(O.camera_opt_regularizer(g["pose"]), g["regularizer"], 1e-6, "regularizer")
+
+
+def test_other_spaced_samplers(golden):
+    """LinearDisparity / Sqrt / Log samplers (reference tests/model_components/test_ray_sampler.py:37-86 set-up and a
+    varied near/far batch): bit-exact spacing bins, euclidean bins to fp32 rounding of the spacing functions."""
+    g = golden("samplers_extra")
+    for kind in ("lindisp", "sqrt", "log"):
+        _, eb = O.spaced_sample(g["t_nears"], g["t_fars"], 15, kind, None)
+        assert eb.shape == (10, 16)
+        assert_close(eb, g[f"{kind}_t_ebins"], 0.0, f"{kind} test set-up")
+        for mode in ("eval", "single"):
+            sb, eb = O.spaced_sample(g["nears"], g["fars"], 24, kind, g.get(f"{kind}_{mode}_jitter"))
+            assert torch.equal(sb.expand(64, -1), g[f"{kind}_{mode}_sbins"]), (kind, mode)
+            assert_close(eb, g[f"{kind}_{mode}_ebins"], 0.0, f"{kind} {mode}")

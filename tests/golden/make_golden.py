@@ -545,6 +545,25 @@ def g_samplers_extra():
     save("samplers_extra", **out)
 
 
+def g_aabb_intersect():
+    """nerfstudio.utils.math.intersect_aabb — the function the reference itself compares with
+    nerfacc.ray_aabb_intersect (tests/utils/test_aabb_intersection.py:117-183, rtol 1e-3): the only pinned statement
+    about the nerfacc call used by the packed path."""
+    from nerfstudio.utils.math import intersect_aabb
+
+    g = torch.Generator().manual_seed(496)
+    lo = (torch.rand(3, generator=g) - 0.5) * 100
+    aabb = torch.cat([lo, lo + torch.rand(3, generator=g) * 100 + 1.0])
+    centre, half = (aabb[:3] + aabb[3:]) / 2, (aabb[3:] - aabb[:3]) / 2
+    R = 500
+    o = centre + (torch.rand(R, 3, generator=g) - 0.5) * 1000
+    target = centre + (torch.rand(R, 3, generator=g) - 0.5) * 2 * half * 1.5   # some rays miss the box
+    d = torch.nn.functional.normalize(target - o, dim=-1)
+    o[:50] = centre + (torch.rand(50, 3, generator=g) - 0.5) * half               # origins inside the box
+    t_min, t_max = intersect_aabb(o, d, aabb)
+    save("aabb_intersect", aabb=aabb, origins=o, directions=d, t_min=t_min, t_max=t_max)
+
+
 def g_camera_opt():
     """CameraOptimizer.apply_to_raybundle (SO3xR3), with the pose gradients and the regulariser."""
     from nerfstudio.cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
@@ -572,7 +591,7 @@ def g_camera_opt():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     fns = (g_hash, g_encodings, g_mlp, g_density_field, g_nerfacto_field, g_samplers, g_render, g_losses,
-           g_raygen, g_vanilla, g_pipeline, g_camera_opt, g_samplers_extra)
+           g_raygen, g_vanilla, g_pipeline, g_camera_opt, g_samplers_extra, g_aabb_intersect)
     only = set(sys.argv[1:])  # e.g. `python tests/golden/make_golden.py g_camera_opt` regenerates one fixture
     for fn in fns:
         if only and fn.__name__ not in only:

@@ -316,3 +316,25 @@ def test_other_spaced_samplers(golden):
             sb, eb = O.spaced_sample(g["nears"], g["fars"], 24, kind, g.get(f"{kind}_{mode}_jitter"))
             assert torch.equal(sb.expand(64, -1), g[f"{kind}_{mode}_sbins"]), (kind, mode)
             assert_close(eb, g[f"{kind}_{mode}_ebins"], 0.0, f"{kind} {mode}")
+
+
+def test_ray_aabb_intersect_vs_reference_slab_test(golden):
+    """The packed path's ray/box test against nerfstudio.utils.math.intersect_aabb, which the reference compares with
+    nerfacc.ray_aabb_intersect at rtol 1e-3 (tests/utils/test_aabb_intersection.py:150-183); plus that test's
+    boundary property (:117-147): o + d t_min and o + d t_max lie on the box."""
+    g = golden("aabb_intersect")
+    tmin, tmax, hit = O.ray_aabb_intersect(g["origins"], g["directions"], g["aabb"], near=0.0, far=1e10)
+    ref_hit = g["t_min"] < 1e10
+    assert int(ref_hit.sum()) > 10 and int((~ref_hit).sum()) > 10
+    assert torch.equal(hit, ref_hit)
+    assert torch.allclose(tmin[hit], g["t_min"][hit], rtol=1e-3)
+    assert torch.allclose(tmax[hit], g["t_max"][hit], rtol=1e-3)
+    aabb = g["aabb"]
+    for t in (tmin[hit], tmax[hit]):
+        p = g["origins"][hit] + g["directions"][hit] * t[:, None]
+        inside = ((p >= aabb[:3] - 1e-2) & (p <= aabb[3:] + 1e-2)).all(dim=-1)
+        on_face = (((p - aabb[:3]).abs() < 1e-2) | ((p - aabb[3:]).abs() < 1e-2)).any(dim=-1)
+        origin_inside = ((g["origins"][hit] > aabb[:3]) & (g["origins"][hit] < aabb[3:])).all(dim=-1)
+        # t_min = 0 for origins inside the box: that point is the origin, not a boundary point
+        ok = inside & (on_face | (origin_inside & (t == 0)))
+        assert bool(ok.all())

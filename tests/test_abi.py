@@ -56,3 +56,29 @@ def test_no_cpu_fallback_for_cpu_tensors(libpath):
 
     with pytest.raises(RuntimeError, match="no CPU path"):
         F.sh_encode(torch.zeros(4, 3), 4)
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, smoke() and bench.py's CPU-baseline legs may import it.  Static
+    check over the package sources (an import anywhere else would put a CPU path behind the product API)."""
+    import ast
+    import os
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nerfstudio_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(root):
+        for fn in files:
+            if not fn.endswith(".py"):
+                continue
+            path = os.path.join(dirpath, fn)
+            rel = os.path.relpath(path, root)
+            tree = ast.parse(open(path).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                if any(n == "oracle" or n.startswith("oracle.") for n in names) and rel != "smoke.py":
+                    offenders.append(rel)
+    assert offenders == [], offenders

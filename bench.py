@@ -17,7 +17,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -43,44 +42,67 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons of this rank's GPU, sampled through NVML from a thread of this process.
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    The thread is started long before the timed region (nothing is forked or initialised between the barrier and the
+    first timed launch — round 1 spawned nvidia-smi there and, on an 8-GPU node, lost ~85 ms of the window to NVML
+    start-up).  Samples carry a host timestamp; `window(t0, t1)` summarises those that fall inside a timed region."""
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
-    def start(self):
+    def __init__(self, device_index: int, period_s: float = 0.004):
+        self.rows, self.period, self.err = [], period_s, None
+        self._stop = threading.Event()
+        self.h = self.max_mhz = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:  # noqa: BLE001
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            pynvml.nvmlInit()
+            self.nv = pynvml
             try:
-                sm.append(float(r[1])), mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:  # noqa: BLE001
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[device_index]) if vis and vis.split(",")[device_index].isdigit() else device_index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._sample()  # first NVML queries (slow path) happen here, not in the timed region
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+
+    def _sample(self):
+        nv = self.nv
+        mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:  # noqa: BLE001
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        self.rows.append((time.perf_counter(), mhz, mask))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(self.period)
+
+    def window(self, spans) -> dict:
+        """spans: list of (t0, t1) host times of the timed regions."""
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [self.err or "NVML unavailable"]}
+        rows = [r for r in self.rows if any(t0 <= r[0] <= t1 for t0, t1 in spans)]
+        sm = sorted(r[1] for r in rows)
+        reasons = sorted({name for _, _, m in rows for name, bit in self.REASONS if m & bit})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "reasons": reasons, "source": "NVML, in-process thread started before warm-up"}
+
+    def stop(self):
+        self._stop.set()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -193,6 +215,21 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------------
+STATE_STEP = 100  # the timed windows start at this optimisation step (fixed training state: gradient sparsity of the
+#                   proposal levels, hence density_field_bwd's time, depends on how far training has progressed)
+
+# algorithmic flops of the tiny MLPs: 2 * sum(in_i * out_i) per row forward; backward = dA + dW = 2x
+_MLP_FLOPS = {(32, 16): 2 * (32 * 64 + 64 * 16), (64, 3): 2 * (63 * 64 + 64 * 64 + 64 * 3), (63, 3): 2 * (63 * 64 + 64 * 64 + 64 * 3)}
+
+
+def sustained_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured sustained bf16 (MEASURED_PEAKS.json)"
+    return 1500.0, "fallback (B200_PROFILING.md)"
+
+
 def run_b200(args) -> None:
     from nerfstudio_b200 import distributed as D
     from nerfstudio_b200 import functional as F
@@ -206,6 +243,7 @@ def run_b200(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib.load()
+    sampler = ClockSampler(local)  # NVML thread: started now, long before any timed region
     for kv in filter(None, args.tune.split(",")):
         k, v = kv.split("=")
         assert lib.tune(k, int(v)), f"unknown tuning key {k}"
@@ -215,18 +253,6 @@ def run_b200(args) -> None:
     if args.force_proposal_update:
         model.proposal_sampler.update_sched = lambda step: -1  # proposal networks trained on every step
     allreduce = D.FlatGradAllReduce() if world > 1 else None
-    if args.engine == "autograd":
-        trainer = Trainer(model, allreduce=allreduce)
-        engine = None
-    else:
-        from nerfstudio_b200.engine import NerfactoStep
-
-        engine = NerfactoStep(model, RAYS_PER_GPU, allreduce=allreduce, use_graph=(args.engine == "graph"),
-                              always_update_proposals=args.force_proposal_update, mlp_backend=args.mlp,
-                              fused_proposals=not args.unfused_proposals)
-        trainer = engine
-    D.broadcast_parameters(trainer.optim.flat)
-    n_params = trainer.optim.flat.numel()
 
     # independent ray draws per rank (scripts/train.py:98: seed + rank)
     n_batches = 4
@@ -235,11 +261,25 @@ def run_b200(args) -> None:
         rays, gt = synthetic_rays(RAYS_PER_GPU, NUM_IMAGES, seed=1000 * rank + b)
         host.append(({k: v.pin_memory() for k, v in rays.items()}, gt.pin_memory()))
     resident = [({k: v.to(dev) for k, v in r.items()}, g.to(dev)) for r, g in host]
-    torch.manual_seed(42 + rank)
 
-    packed = ([engine.pack_batch(r["origins"], r["directions"], r["camera_indices"], g) for r, g in host]
-              if engine is not None else None)  # pinned, laid out by the engine's loader-side helper
-    packed_dev = [b.to(dev) for b in packed] if packed is not None else None
+    fused = None
+    if args.engine == "autograd":
+        trainer = Trainer(model, allreduce=allreduce)
+        engine = None
+    else:
+        # the captured step behind the reference's training surface (Trainer.train_iteration /
+        # Pipeline.get_train_loss_dict): nerfstudio_b200/pipeline.py
+        from nerfstudio_b200.pipeline import FusedTrainStep, HostRayQueue
+
+        fused = FusedTrainStep(model, None, RAYS_PER_GPU, allreduce=allreduce, use_graph=(args.engine == "graph"),
+                               always_update_proposals=args.force_proposal_update, mlp_backend=args.mlp,
+                               fused_proposals=not args.unfused_proposals)
+        engine = trainer = fused.engine
+        fused.datamanager = HostRayQueue(engine, host)
+    D.broadcast_parameters(trainer.optim.flat)
+    n_params = trainer.optim.flat.numel()
+    torch.manual_seed(42 + rank)
+    packed_dev = [it[2].to(dev) for it in fused.datamanager.items] if fused is not None else None
 
     def step_resident(i):
         rays, gt = resident[i % n_batches]
@@ -249,10 +289,12 @@ def run_b200(args) -> None:
         return trainer.train_iteration(bundle_from(rays), {"image": gt})
 
     def step_e2e(i):
+        if fused is not None:
+            # THE plugin call: Trainer.train_iteration(step) -> pinned host RayBundle from the data manager, H2D copy,
+            # one graph replay (fwd + losses + bwd + allreduce + Adam), then a device -> host read of the loss
+            loss, _loss_dict, _metrics = fused.train_iteration(i)
+            return float(loss)
         rays, gt = host[i % n_batches]  # pinned host memory -> device inside the timed region
-        if engine is not None:
-            engine.set_batch_packed(packed[i % n_batches])  # one async H2D copy of the whole batch
-            return float(engine.step()[3].item())  # device -> host read of the step's loss
         d_rays = {k: v.to(dev, non_blocking=True) for k, v in rays.items()}
         stats = trainer.train_iteration(bundle_from(d_rays), {"image": gt.to(dev, non_blocking=True)})
         return float(stats["loss"].item())
@@ -262,98 +304,144 @@ def run_b200(args) -> None:
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, sampler=None):
-        barrier()
-        if sampler:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        barrier()
-        clocks = sampler.stop() if sampler else None
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return float(ms.item()), clocks
+    spans = []
 
-    for i in range(max(args.warmup, 3)):
+    def timed(fn, steps, windows, first_step):
+        """`windows` back-to-back timed regions of exactly `steps` steps each; every region is bracketed by
+        barrier + synchronize on both sides, timed with CUDA events, max over ranks.  Returns the per-window ms."""
+        out = []
+        for w in range(windows):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for i in range(steps):
+                fn(first_step + w * steps + i)
+            e1.record()
+            barrier()
+            spans.append((t0, time.perf_counter()))
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+            out.append(float(ms.item()))
+        return out
+
+    # warm-up: at least the requested steps, and always up to the fixed training state STATE_STEP (also warms NCCL's
+    # channels at N > 1: the driver asks for only 5 warm-up steps)
+    n_warm = max(args.warmup, 3, STATE_STEP)
+    for i in range(n_warm):
         step_resident(i)
     lib.LAUNCHES = 0
     F.KERNEL_TIMES.clear()
     F.PROFILE_KERNELS = engine is None
-    ms, clocks = timed(step_resident, args.steps, ClockSampler(local))
+    win_ms = timed(step_resident, args.steps, args.windows, n_warm)
     F.PROFILE_KERNELS = False
     launches = lib.LAUNCHES
-    torch.cuda.synchronize()
+    ms = sorted(win_ms)[len(win_ms) // 2]  # median window
     value = world * RAYS_PER_GPU * args.steps / (ms * 1e-3)
-    kt = F.kernel_time_summary()
+    clocks = sampler.window(list(spans))
+
+    for i in range(3):
+        step_e2e(i)
+    e2e_ms = timed(step_e2e, args.steps, args.windows, 3)
+    ms_e2e = sorted(e2e_ms)[len(e2e_ms) // 2]
+    e2e_value = world * RAYS_PER_GPU * args.steps / (ms_e2e * 1e-3)
+    if fused is not None:
+        h2d = fused.datamanager.bytes_per_batch
+    else:
+        h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * 4
+
+    # ---- per-kernel durations (after the timed regions): the same launch sequence run eagerly with CUDA events around
+    # every C-ABI call on the launching stream (a CUDA graph has no per-node events)
+    kernel_table, ms_prof, n_prof, prof, scatter_frac = None, ms / args.steps, args.steps, {}, {}
     if engine is not None:
-        # per-kernel durations: the same launch sequence run eagerly with CUDA events around every C-ABI call
-        # (a CUDA graph has no per-node events); `launches` = our kernel launches replayed per graph x steps
         was_graph, engine.use_graph = engine.use_graph, False
         lib.LAUNCHES, lib.PROFILE = 0, None
         step_resident(0)
-        launches = lib.LAUNCHES * args.steps
+        launches_per_step = lib.LAUNCHES
+        launches = launches_per_step * args.steps * args.windows
         lib.PROFILE = {}
-        n_prof = 5
+        n_prof = 10
         for i in range(n_prof):
             step_resident(i)
         torch.cuda.synchronize()
         prof, lib.PROFILE = lib.profile_summary(), None
         engine.use_graph = was_graph
-        S = engine.S
-        # algorithmic bytes of every kernel that gathers from / scatters into a hash table: 8 corners x F(2) x 4 B per
-        # (point, level); scatter counted as read + write.  The fused density-field kernels carry the proposal grids.
-        hb = {}
-        for i, L in ((0, 5), (1, 5), (2, 16)):
-            n_pts, b = RAYS_PER_GPU * S[i], RAYS_PER_GPU * S[i] * L * 8 * 2 * 4
-            hb[f"b2n_hashgrid_fwd[n={n_pts}]"], hb[f"b2n_hashgrid_bwd[n={n_pts}]"] = b, 2 * b
-            hb[f"b2n_density_field_fwd[n={n_pts}]"] = b
-            hb[f"b2n_density_field_bwd[n={n_pts}]"] = 3 * b  # re-gather + scatter
-        kt = {k: {"launches": c, "ms_total": t, "ms_avg": t / c, "bytes_per_launch": hb[k]} for k, (c, t) in prof.items() if k in hb}
         kernel_table = {k: round(t / n_prof, 4) for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
         ms_prof = sum(t for _, t in prof.values()) / n_prof
-    else:
-        kernel_table, ms_prof, n_prof = None, ms / args.steps, args.steps
-
-    for i in range(3):
-        step_e2e(i)
-    ms_e2e, _ = timed(step_e2e, args.steps)
-    e2e_value = world * RAYS_PER_GPU * args.steps / (ms_e2e * 1e-3)
-    if packed is not None:
-        h2d = packed[0].numel() * packed[0].element_size()
-    else:
-        h2d = sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * 4
-
+        # measured fraction of samples whose density gradient is non-zero: density_field_bwd skips the scatter for the
+        # others, so its algorithmic bytes are gather + frac * (read + write)
+        for lvl in (0, 1):
+            scatter_frac[RAYS_PER_GPU * engine.S[lvl]] = float((engine.d_dens[lvl] != 0).float().mean().item())
+    sampler.stop()
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (hash-grid gather / scatter), algorithmic bytes: 8 corners x F x 4 B
-    peak, peak_src = peaks()
-    dom = max(kt.items(), key=lambda kv: kv[1]["ms_total"]) if kt else None
-    roofline = None
-    if dom is not None:
-        name, st = dom
-        ach = st["bytes_per_launch"] / (st["ms_avg"] * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")  # dram read+write per launch, ncu --set full
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(name.split("[")[0], {}).get(name)
-        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": peak_src, "launches_per_step": st["launches"] / n_prof,
-                    "ms_avg": st["ms_avg"], "share_of_step": st["ms_avg"] * st["launches"] / n_prof / ms_prof,
-                    "all_hash_kernels": {k: {"ms_avg": v["ms_avg"], "GBps": v["bytes_per_launch"] / (v["ms_avg"] * 1e-3) / 1e9,
-                                             "launches_per_step": v["launches"] / n_prof} for k, v in kt.items()},
-                    "kernel_ms_per_step": kernel_table}
+
+    # ---- rooflines.  (1) the step's DOMINANT kernel (largest time per step); (2) the hash gather on the 16-level grid —
+    # the kernel north_star's ">= 60 % of the HBM roofline" names; (3) every hash kernel, for the record.
+    hbm_peak, peak_src = peaks()
+    # per-launch DRAM (read+write) and L2 (lts__t_bytes) bytes of the same kernels from the committed `ncu --set full`
+    # capture of this build (scripts/ncu_traffic.py -> profiles/ncu_traffic.json: {call key: {dram_bytes, lts_bytes, ...}})
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    ncu = json.load(open(tpath)) if os.path.exists(tpath) else {}
+
+    def ncu_of(key, field):
+        return (ncu.get(key) or {}).get(field)
+
+    roofline = gather_roof = None
+    hash_rows = {}
+    if prof:
+        S = engine.S
+        hb = {}
+        for i, L in ((0, 5), (1, 5), (2, 16)):
+            n_pts = RAYS_PER_GPU * S[i]
+            b = n_pts * L * 8 * 2 * 4  # 8 corners x F(2) x 4 B per (point, level)
+            hb[f"b2n_hashgrid_fwd[n={n_pts}]"], hb[f"b2n_hashgrid_bwd[n={n_pts}]"] = b, 2 * b
+            hb[f"b2n_density_field_fwd[n={n_pts}]"] = b
+            hb[f"b2n_density_field_bwd[n={n_pts}]"] = int(b * (1 + 2 * scatter_frac.get(n_pts, 1.0)))
+        for k, (c, t) in prof.items():
+            if k in hb:
+                hash_rows[k] = {"ms_avg": t / c, "GBps": hb[k] / (t / c * 1e-3) / 1e9, "frac_of_hbm_peak": hb[k] / (t / c * 1e-3) / 1e9 / hbm_peak,
+                                "bytes_per_launch": hb[k], "launches_per_step": c / n_prof}
+        name, (c, t) = max(prof.items(), key=lambda kv: kv[1][1])
+        ms_avg = t / c
+        share = t / n_prof / ms_prof
+        if name.startswith("b2n_mlp_tc"):
+            tpeak, tsrc = sustained_tensor_peak()
+            n_rows = int(name.split("n=")[1].split(",")[0])
+            key = (int(name.split("in=")[1].split(",")[0]), int(name.split("out=")[1].split("]")[0]))
+            fl = _MLP_FLOPS.get(key, 0) * n_rows * (2 if "bwd" in name else 1)
+            ach = fl / (ms_avg * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": name, "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                        "traffic": ncu_of(name, "dram_bytes"), "peak_source": tsrc, "flops_per_launch": fl,
+                        "note": "algorithmic fp32 flops of the tiny MLP (3xTF32 issues 3 tensor-core passes per product); "
+                                "K, N <= 64 GEMMs are latency-chained per 128-row tile, never near the tensor peak"}
+        else:
+            by = hb.get(name)
+            ach = by / (ms_avg * 1e-3) / 1e9 if by else None
+            roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": ach / hbm_peak if ach else None, "traffic": ncu_of(name, "dram_bytes"), "peak_source": peak_src,
+                        "bytes_per_launch": by}
+        roofline.update({"launches_per_step": c / n_prof, "ms_avg": ms_avg, "share_of_step": share,
+                         "scatter_fraction_measured": scatter_frac or None})
+        gname = f"b2n_hashgrid_fwd[n={RAYS_PER_GPU * S[2]}]"
+        if gname in hash_rows:
+            g = hash_rows[gname]
+            gather_roof = {"bound": "hbm", "kernel": gname, "achieved": g["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                           "frac": g["frac_of_hbm_peak"], "traffic": ncu_of(gname, "dram_bytes"), "l2_bytes": ncu_of(gname, "lts_bytes"),
+                           "bytes_per_launch": g["bytes_per_launch"], "ms_avg": g["ms_avg"], "peak_source": peak_src,
+                           "note": "64 B per (sample, level); the 64 MiB table is L2-resident on B200, so DRAM traffic < algorithmic bytes"}
+        # whole step against the hash roofline (SURVEY 8d: 1.99 GB algorithmic per 4096-ray step)
+        step_bytes = sum(v["bytes_per_launch"] * v["launches_per_step"] for v in hash_rows.values())
+        step_roof = {"algorithmic_hash_bytes_per_step": step_bytes, "GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak}
+    else:
+        step_roof = None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads, _ = pick_cpu_threads()
-        rps, sec, cores = time_cpu(512, 3, 1, threads)
-        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": f"3 steps x 512 rays of the same workload (fwd+bwd+Adam), torch CPU fp32, {cores} threads"}
+        cpu = cpu_baseline_sample()
     line = {
-        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch_rays": world * RAYS_PER_GPU,
@@ -362,13 +450,159 @@ def run_b200(args) -> None:
                                  if (engine is not None and engine.tc) else "fp32 tables, fp32 SIMT MLPs (1e-4 parity mode)"), "optimizer": "fused Adam over one flat buffer", "engine": args.engine,
                    "proposal_update": "every step" if args.force_proposal_update else "reference schedule",
                    "l2": f"per-step working set {4 * 4 * n_params / 1e6:.0f} MB (params+grads+Adam moments) > 126 MB L2",
+                   "timing": f"median of {args.windows} windows of exactly {args.steps} steps, each bracketed by barrier+synchronize; "
+                             f"windows start at optimisation step {n_warm}",
                    "params": n_params},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "windows_ms": win_ms, "e2e_windows_ms": e2e_ms,
+        "roofline": roofline, "roofline_hash_gather": gather_roof, "roofline_step": step_roof,
+        "hash_kernels": hash_rows or None, "kernel_ms_per_step": kernel_table, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "through": ("FusedTrainStep.train_iteration(step): the reference's Trainer.train_iteration / "
+                            "Pipeline.get_train_loss_dict surface (nerfstudio_b200/pipeline.py)") if fused is not None else "Trainer.train_iteration (autograd path)"},
         "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_ngp(args) -> None:
+    """--workload ngp: BASELINE configs[1] (instant-ngp: 16-level hash grid T=2^19 F=2, 64-wide MLPs, 128^3 x 4 occupancy
+    grid, cone_angle 0.004, alpha_thre 0.01) on the analytic-sphere scene of SURVEY 8d — the packed path end to end:
+    occupancy update every 16 steps, march, sigma_fn + pruning, field on M packed samples, packed compositing, loss,
+    backward, Adam.  M (samples per step) is data dependent and reported."""
+    from nerfstudio_b200 import distributed as D
+    from nerfstudio_b200 import lib
+    from nerfstudio_b200.instant_ngp import InstantNGPModelConfig, NGPModel, NGPTrainer
+    from nerfstudio_b200.scene import bundle_from, sphere_scene_rays
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 core has no CPU fallback")
+    rank, local, world = D.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib.load()
+    sampler = ClockSampler(local)
+    torch.manual_seed(0)
+    cfg = InstantNGPModelConfig(implementation="torch", background_color="black")
+    model = NGPModel(cfg, torch.tensor([[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5]]), num_train_data=100).to(dev)
+    allreduce = D.FlatGradAllReduce() if world > 1 else None
+    trainer = NGPTrainer(model, allreduce=allreduce)
+    D.broadcast_parameters(trainer.optim.flat)
+    n_batches = 8
+    host = []
+    for b in range(n_batches):
+        rays, gt = sphere_scene_rays(RAYS_PER_GPU, seed=1000 * rank + b)
+        host.append(({k: v.pin_memory() for k, v in rays.items()}, gt.pin_memory()))
+    resident = [({k: v.to(dev) for k, v in r.items()}, g.to(dev)) for r, g in host]
+    torch.manual_seed(42 + rank)
+    samples = []
+
+    def step_resident(i):
+        rays, gt = resident[i % n_batches]
+        out = trainer.train_iteration(bundle_from(rays), {"image": gt})
+        samples.append(trainer.num_samples)
+        return out
+
+    def step_e2e(i):
+        rays, gt = host[i % n_batches]
+        d_rays = {k: v.to(dev, non_blocking=True) for k, v in rays.items()}
+        return float(trainer.train_iteration(bundle_from(d_rays), {"image": gt.to(dev, non_blocking=True)})["loss"].item())
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    spans = []
+
+    def timed(fn, steps, windows, first):
+        out = []
+        for w in range(windows):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for i in range(steps):
+                fn(first + w * steps + i)
+            e1.record()
+            barrier()
+            spans.append((t0, time.perf_counter()))
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+            out.append(float(ms.item()))
+        return out
+
+    n_warm = max(args.warmup, 320)  # past the occupancy grid's 256-step warm-up: the grid has converged to the sphere
+    for i in range(n_warm):
+        step_resident(i)
+    samples.clear()
+    lib.LAUNCHES = 0
+    win_ms = timed(step_resident, args.steps, args.windows, n_warm)
+    launches = lib.LAUNCHES
+    m_mean = float(torch.stack([s.sum() for s in samples]).float().mean().item())
+    ms = sorted(win_ms)[len(win_ms) // 2]
+    value = world * RAYS_PER_GPU * args.steps / (ms * 1e-3)
+    clocks = sampler.window(list(spans))
+    for i in range(3):
+        step_e2e(i)
+    e2e_ms = timed(step_e2e, args.steps, args.windows, n_warm + 3)
+    ms_e2e = sorted(e2e_ms)[len(e2e_ms) // 2]
+    # per-kernel profile (CUDA events around every C-ABI launch), 32 steps = two occupancy updates
+    lib.PROFILE_BY_SIZE, lib.PROFILE = False, {}
+    n_prof = 32
+    first = trainer.step
+    for i in range(n_prof):
+        step_resident(first + i)
+    torch.cuda.synchronize()
+    prof, sizes = lib.profile_summary(), lib.profile_sizes()
+    lib.PROFILE, lib.PROFILE_BY_SIZE = None, True
+    sampler.stop()
+    if rank != 0:
+        return
+    hbm_peak, peak_src = peaks()
+    table = {k: {"ms_per_step": round(t / n_prof, 4), "launches_per_step": round(c / n_prof, 2)} for k, (c, t) in
+             sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    ms_prof = sum(t for _, t in prof.values()) / n_prof
+    name, (c, t) = max(prof.items(), key=lambda kv: kv[1][1])
+    roofline = {"kernel": name, "ms_per_step": t / n_prof, "launches_per_step": c / n_prof, "share_of_kernel_time": t / n_prof / ms_prof}
+    hash_rows = {}
+    for k, mult in (("b2n_hashgrid_fwd", 1), ("b2n_hashgrid_bwd", 2)):
+        if k in prof:
+            by = sizes[k] * 16 * 8 * 2 * 4 * mult  # 64 B per (sample, level), 16 levels; scatter = read + write
+            gbps = by / (prof[k][1] * 1e-3) / 1e9
+            hash_rows[k] = {"points_per_step": sizes[k] / n_prof, "GBps": gbps, "frac_of_hbm_peak": gbps / hbm_peak}
+    if name in hash_rows:
+        roofline.update({"bound": "hbm", "achieved": hash_rows[name]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                         "frac": hash_rows[name]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src})
+    else:
+        roofline.update({"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                         "note": "the step is launch/latency bound at this sample count; see hash_kernels for the gather"})
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "instant-ngp 4096 rays/GPU, L16/T2^19/F2 grid + 64-wide MLPs, 128^3 x 4 occupancy grid, "
+                               "cone_angle 0.004, alpha_thre 0.01, aabb +-1.5; analytic sphere r=0.5 (SURVEY 8d config 2)",
+                   "global_batch_rays": world * RAYS_PER_GPU, "samples_per_step_M": m_mean,
+                   "samples_per_ray": m_mean / RAYS_PER_GPU, "engine": "autograd over the drop-in modules (packed path)",
+                   "background": "black (opaque synthetic targets)", "occupancy_update": "every 16 steps, inside the timed region",
+                   "timing": f"median of {args.windows} windows of exactly {args.steps} steps; windows start at step {n_warm}"},
+        "windows_ms": win_ms, "e2e_windows_ms": e2e_ms, "roofline": roofline, "hash_kernels": hash_rows,
+        "kernel_ms_per_step": table, "cpu_baseline": None,
+        "e2e": {"value": world * RAYS_PER_GPU * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host[0][0].values()) + host[0][1].numel() * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "through": "NGPTrainer.train_iteration"},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    threads, _ = pick_cpu_threads()
+    rps, sec, cores = time_cpu(512, 3, 1, threads)
+    return {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"3 steps x 512 rays of the same workload (fwd+bwd+Adam), torch CPU fp32, {cores} threads"}
 
 
 def main() -> None:
@@ -377,6 +611,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="nerfacto", choices=["nerfacto", "ngp"],
+                    help="nerfacto = BASELINE configs[2], the metric's workload (default); ngp = configs[1] (instant-ngp)")
+    ap.add_argument("--windows", type=int, default=3, help="timed windows of exactly --steps steps each (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mlp", default="auto", choices=["auto", "tc", "simt"],
                     help="tiny-MLP kernels of the graph/eager engine: tcgen05 3xTF32 (tc) or fp32 SIMT")
@@ -390,6 +627,8 @@ def main() -> None:
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "ngp":
+        run_ngp(args)
     else:
         run_b200(args)
     if torch.distributed.is_available() and torch.distributed.is_initialized():

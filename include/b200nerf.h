@@ -172,6 +172,11 @@ int b2n_pdf_sample(const float* bins, const float* weights, const float* u_base,
                    int32_t spacing,
                    float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out, void* stream);
 
+/* parity pin of the PDF sampler's normaliser: out[r] = sum(x[r, 0..n_cols)) accumulated in the order of torch's CPU
+ * `sum` kernel (8-lane vectors x 4 interleaved rows x 4 cascade levels; model_components/ray_samplers.py:306 calls it),
+ * so that cdf and searchsorted indices reproduce the reference's bits. */
+int b2n_torch_row_sum(const float* x, int64_t n_rows, int32_t n_cols, float* out, void* stream);
+
 /* ---- a21-a23: transmittance weights and compositing ---------------------------------------------------
  * Sample intervals are given as starts/ends [R,S] with row stride `bin_stride`: for an [R,S+1] edge array
  * pass starts=edges, ends=edges+1, bin_stride=S+1 (what the reference's samplers produce).
@@ -251,6 +256,46 @@ int b2n_occgrid_fill(const float* origins, const float* directions, const float*
                      const uint8_t* binaries, int32_t levels, int32_t res, const float* roi_host6, float step,
                      float cone_angle, float near_plane, float far_plane, const float* jitter, int64_t n_rays,
                      const int64_t* offsets, int64_t* ray_indices, float* t_starts, float* t_ends, void* stream);
+
+/* exclusive scan of per-ray counts -> pack offsets int64 [n] and the total (device int64) — the step between the count and
+ * the fill pass of the march / the pruning (replaces a framework cumsum). */
+int b2n_scan_counts(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* total, void* stream);
+/* packed sample midpoints x[i] = o[ray_i] + d[ray_i] * (ts_i + te_i)/2: what VolumetricSampler.get_sigma_fn evaluates the
+ * density at (model_components/ray_samplers.py:406-430). */
+int b2n_packed_positions(const float* origins, const float* directions, const int64_t* ray_indices,
+                         const float* t_starts, const float* t_ends, int64_t m, float* x, void* stream);
+/* K8: visibility pruning of marched samples (nerfacc render_visibility_from_density inside OccGridEstimator.sampling,
+ * called from ray_samplers.py:481-493): keep sample i iff trans[i] >= early_stop_eps && alphas[i] >= alpha_thre.
+ * alpha_cap_dev (optional device scalar): the threshold used is min(alpha_thre, *alpha_cap_dev) — nerfacc caps alpha_thre
+ * with occs.mean(), which b2n_occgrid_binarize leaves in device memory.
+ * Two passes like the march: counts int32 [R] -> b2n_scan_counts -> fill (order within a ray preserved). */
+int b2n_packed_prune_count(const float* trans, const float* alphas, const int64_t* packed_info, int64_t n_rays,
+                           float early_stop_eps, float alpha_thre, const float* alpha_cap_dev, int32_t* counts,
+                           void* stream);
+int b2n_packed_prune_fill(const float* trans, const float* alphas, const int64_t* packed_info, int64_t n_rays,
+                          float early_stop_eps, float alpha_thre, const float* alpha_cap_dev, const int64_t* offsets,
+                          const float* t_starts,
+                          const float* t_ends, int64_t* out_ray_indices, float* out_t_starts, float* out_t_ends,
+                          void* stream);
+/* K9: occupancy-grid update (nerfacc OccGridEstimator.update_every_n_steps as called by models/instant_ngp.py:149-164).
+ *  points:   x [n,3] = lo + ((coord(cell) + jitter)/res) * (hi - lo) for one level; cell_ids int64 [n] or NULL (= 0..n-1,
+ *            the warm-up "all cells" case); coord = (id / res^2, id / res % res, id % res); level_aabb_host6 = (lo | hi).
+ *  ema:      occs[level_offset + cell] = max(occs[..] * ema_decay, occ_new) — candidates are formed from the OLD values;
+ *            a cell listed several times gets the largest candidate.  scratch_n: float [n].
+ *  binarize: binaries[i] = occs[i] > min(mean(occs), occ_thre) over all levels (n cells); the mean is a deterministic
+ *            fp64 reduction.  scratch_parts: double [512]; stats_out: float [2] = (threshold used, mean(occs));
+ *            binaries may be NULL (statistics only). */
+int b2n_occgrid_points(const int64_t* cell_ids, const float* jitter, int64_t n, int32_t res,
+                       const float* level_aabb_host6, float* x, void* stream);
+int b2n_occgrid_ema(float* occs, const int64_t* cell_ids, const float* occ_new, int64_t n, int64_t level_offset,
+                    float ema_decay, float* scratch_n, void* stream);
+int b2n_occgrid_binarize(const float* occs, int64_t n, float occ_thre, double* scratch_parts, float* stats_out,
+                         uint8_t* binaries, void* stream);
+/* nerfacc.ray_aabb_intersect (models/instant_ngp.py does not call it per step; VolumetricSampler users and the reference's
+ * tests/utils/test_aabb_intersection.py do): aabbs [K,6]; t_mins/t_maxs [n,K], hits uint8 [n,K]; misses = miss_value. */
+int b2n_ray_aabb_intersect(const float* origins, const float* directions, const float* aabbs, int64_t n_rays,
+                           int32_t n_boxes, float near_plane, float far_plane, float miss_value, float* t_mins,
+                           float* t_maxs, uint8_t* hits, void* stream);
 
 /* ---- optimiser step either side of the path: torch.optim.Adam semantics ---------------
  * p,g,m,v flat fp32 [n]; step is the 1-based step count; grads are multiplied by grad_scale first

@@ -281,3 +281,263 @@ extern "C" int b2n_occgrid_fill(const float* origins, const float* directions, c
       mp, origins, directions, t_min, t_max, binaries, jitter, n_rays, nullptr, offsets, ray_indices, t_starts, t_ends);
   B2N_LAUNCH_CHECK();
 }
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of per-ray sample counts -> pack offsets + total (one CTA; R is a few thousand rays).
+// Replaces the framework cumsum between the count and the fill pass of the march / the pruning.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int64_t n,
+                                                           int64_t* __restrict__ offsets, int64_t* __restrict__ total) {
+  __shared__ long long warp_tot[32], warp_excl[32];
+  __shared__ long long carry_s, chunk_tot;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const long long v = i < n ? (long long)counts[i] : 0;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const long long w = warp_tot[lane];
+      long long wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_excl[lane] = wi - w;
+      if (lane == 31) chunk_tot = wi;
+    }
+    __syncthreads();
+    if (i < n) offsets[i] = carry_s + warp_excl[warp] + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s += chunk_tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
+extern "C" int b2n_scan_counts(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* total, void* stream) {
+  B2N_REQUIRE(total != nullptr, "null pointer");
+  B2N_REQUIRE(n == 0 || (counts && offsets), "null pointer");
+  scan_counts_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(counts, n, offsets, total);
+  B2N_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8 — visibility / alpha pruning of marched samples (nerfacc render_visibility_from_density as called by
+// OccGridEstimator.sampling; model_components/ray_samplers.py:481-493): keep = T >= early_stop_eps && alpha >= alpha_thre,
+// order within a ray preserved.  Count and fill share the predicate, so counts/offsets/indices agree bit for bit.
+// ------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(PW * 32) packed_prune_kernel(
+    const float* __restrict__ trans, const float* __restrict__ alphas, const int64_t* __restrict__ info, int64_t n_rays,
+    float eps, float alpha_thre_host, const float* __restrict__ alpha_cap, int32_t* __restrict__ counts,
+    const int64_t* __restrict__ offsets,
+    const float* __restrict__ ts, const float* __restrict__ te, int64_t* __restrict__ out_ri, float* __restrict__ out_ts,
+    float* __restrict__ out_te) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * PW + warp;
+  if (r >= n_rays) return;
+  const float alpha_thre = alpha_cap ? fminf(alpha_thre_host, __ldg(alpha_cap)) : alpha_thre_host;
+  const int64_t base = info[2 * r];
+  const int cnt = (int)info[2 * r + 1];
+  int64_t out = FILL ? offsets[r] : 0;
+  int n = 0;
+  for (int i0 = 0; i0 < cnt; i0 += 32) {
+    const int i = i0 + lane;
+    const bool keep = i < cnt && __ldg(trans + base + i) >= eps && __ldg(alphas + base + i) >= alpha_thre;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (FILL && keep) {
+      const int64_t dst = out + n + __popc(m & ((1u << lane) - 1u));
+      out_ri[dst] = r, out_ts[dst] = __ldg(ts + base + i), out_te[dst] = __ldg(te + base + i);
+    }
+    n += __popc(m);
+  }
+  if (!FILL && lane == 0) counts[r] = n;
+}
+
+extern "C" int b2n_packed_prune_count(const float* trans, const float* alphas, const int64_t* packed_info, int64_t n_rays,
+                                      float early_stop_eps, float alpha_thre, const float* alpha_cap_dev, int32_t* counts,
+                                      void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(trans && alphas && packed_info && counts, "null pointer");
+  packed_prune_kernel<false><<<(unsigned)div_up(n_rays, PW), PW * 32, 0, (cudaStream_t)stream>>>(
+      trans, alphas, packed_info, n_rays, early_stop_eps, alpha_thre, alpha_cap_dev, counts, nullptr, nullptr, nullptr, nullptr,
+      nullptr, nullptr);
+  B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_packed_prune_fill(const float* trans, const float* alphas, const int64_t* packed_info, int64_t n_rays,
+                                     float early_stop_eps, float alpha_thre, const float* alpha_cap_dev, const int64_t* offsets,
+                                     const float* t_starts, const float* t_ends, int64_t* out_ray_indices, float* out_t_starts, float* out_t_ends,
+                                     void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(trans && alphas && packed_info && offsets && t_starts && t_ends && out_ray_indices && out_t_starts && out_t_ends,
+              "null pointer");
+  packed_prune_kernel<true><<<(unsigned)div_up(n_rays, PW), PW * 32, 0, (cudaStream_t)stream>>>(
+      trans, alphas, packed_info, n_rays, early_stop_eps, alpha_thre, alpha_cap_dev, nullptr, offsets, t_starts, t_ends, out_ray_indices,
+      out_t_starts, out_t_ends);
+  B2N_LAUNCH_CHECK();
+}
+
+// packed sample midpoints: x[i] = o[ray] + d[ray] * (ts+te)/2 — the positions VolumetricSampler's sigma_fn evaluates
+// (model_components/ray_samplers.py:417-427), each op separately rounded like the reference's torch chain.
+__global__ void packed_positions_kernel(const float* __restrict__ origins, const float* __restrict__ directions,
+                                        const int64_t* __restrict__ ri, const float* __restrict__ ts,
+                                        const float* __restrict__ te, int64_t m, float* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int64_t r = ri[i];
+  const float mid = div_rn(add_rn(__ldg(ts + i), __ldg(te + i)), 2.f);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) x[3 * i + a] = add_rn(__ldg(origins + 3 * r + a), mul_rn(__ldg(directions + 3 * r + a), mid));
+}
+
+extern "C" int b2n_packed_positions(const float* origins, const float* directions, const int64_t* ray_indices,
+                                    const float* t_starts, const float* t_ends, int64_t m, float* x, void* stream) {
+  if (m == 0) return B2N_OK;
+  B2N_REQUIRE(origins && directions && ray_indices && t_starts && t_ends && x, "null pointer");
+  packed_positions_kernel<<<(unsigned)div_up(m, 256), 256, 0, (cudaStream_t)stream>>>(origins, directions, ray_indices, t_starts, t_ends, m, x);
+  B2N_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9 — occupancy-grid update (nerfacc OccGridEstimator._update as called by
+// models/instant_ngp.py:149-164): jittered cell centres -> occ_eval_fn -> EMA max -> threshold -> binaries.
+// ------------------------------------------------------------------------------------------------
+// x = lo + ((coord + jitter) / res) * (hi - lo), coord = (id / res^2, id / res % res, id % res); ids NULL = 0..n-1
+__global__ void occgrid_points_kernel(const int64_t* __restrict__ ids, const float* __restrict__ jitter, int64_t n, int res,
+                                      float lo0, float lo1, float lo2, float ex0, float ex1, float ex2, float* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = ids ? ids[i] : i;
+  const int c[3] = {(int)(id / ((int64_t)res * res)), (int)((id / res) % res), (int)(id % res)};
+  const float lo[3] = {lo0, lo1, lo2}, ex[3] = {ex0, ex1, ex2};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float u = div_rn(add_rn((float)c[a], __ldg(jitter + 3 * i + a)), (float)res);
+    x[3 * i + a] = add_rn(lo[a], mul_rn(u, ex[a]));
+  }
+}
+
+extern "C" int b2n_occgrid_points(const int64_t* cell_ids, const float* jitter, int64_t n, int32_t res,
+                                  const float* level_aabb_host6, float* x, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(jitter && x && level_aabb_host6 && res >= 1, "bad arguments");
+  const float* b = level_aabb_host6;
+  occgrid_points_kernel<<<(unsigned)div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      cell_ids, jitter, n, res, b[0], b[1], b[2], b[3] - b[0], b[4] - b[1], b[5] - b[2], x);
+  B2N_LAUNCH_CHECK();
+}
+
+// occs[off + id] <- max(occs[off + id] * decay, occ_new) for the sampled cells.  A cell may be sampled more than once
+// (uniform + occupied draws overlap); the reference's indexed assignment then keeps an unspecified one of the
+// candidates, all computed from the OLD value — here the largest (deterministic).  Three passes: candidates from the
+// old values, reset, atomic max (non-negative floats order like their bit patterns).
+__global__ void occ_cand_kernel(const float* __restrict__ occs, const int64_t* __restrict__ ids, const float* __restrict__ occ_new,
+                                int64_t n, int64_t off, float decay, float* __restrict__ cand) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = off + (ids ? ids[i] : i);
+  cand[i] = fmaxf(mul_rn(occs[id], decay), fmaxf(__ldg(occ_new + i), 0.f));
+}
+__global__ void occ_reset_kernel(float* __restrict__ occs, const int64_t* __restrict__ ids, int64_t n, int64_t off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) occs[off + (ids ? ids[i] : i)] = 0.f;
+}
+__global__ void occ_max_kernel(float* __restrict__ occs, const int64_t* __restrict__ ids, const float* __restrict__ cand,
+                               int64_t n, int64_t off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMax(reinterpret_cast<int*>(occs + off + (ids ? ids[i] : i)), __float_as_int(cand[i]));
+}
+
+extern "C" int b2n_occgrid_ema(float* occs, const int64_t* cell_ids, const float* occ_new, int64_t n, int64_t level_offset,
+                               float ema_decay, float* scratch_n, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(occs && occ_new && scratch_n, "null pointer");
+  const unsigned g = (unsigned)div_up(n, 256);
+  cudaStream_t s = (cudaStream_t)stream;
+  occ_cand_kernel<<<g, 256, 0, s>>>(occs, cell_ids, occ_new, n, level_offset, ema_decay, scratch_n);
+  occ_reset_kernel<<<g, 256, 0, s>>>(occs, cell_ids, n, level_offset);
+  occ_max_kernel<<<g, 256, 0, s>>>(occs, cell_ids, scratch_n, n, level_offset);
+  B2N_LAUNCH_CHECK();
+}
+
+// binaries = occs > min(mean(occs), occ_thre); the mean is a deterministic fp64 two-level reduction.
+#define OCC_PARTS 512
+__global__ void __launch_bounds__(256) occ_partial_kernel(const float* __restrict__ occs, int64_t n, double* __restrict__ parts) {
+  __shared__ double sm[8];
+  const int64_t per = div_up_dev(n, (int64_t)OCC_PARTS);
+  const int64_t a = (int64_t)blockIdx.x * per, b = min(n, a + per);
+  double s = 0.0;
+  for (int64_t i = a + threadIdx.x; i < b; i += 256) s += (double)__ldg(occs + i);
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sm[w];
+    parts[blockIdx.x] = t;
+  }
+}
+__global__ void occ_threshold_kernel(const double* __restrict__ parts, int64_t n, float occ_thre, float* __restrict__ stats) {
+  double t = 0.0;
+  for (int i = 0; i < OCC_PARTS; ++i) t += parts[i];
+  const float mean = (float)(t / (double)n);
+  stats[0] = fminf(mean, occ_thre), stats[1] = mean;
+}
+__global__ void occ_binarize_kernel(const float* __restrict__ occs, int64_t n, const float* __restrict__ thre, uint8_t* __restrict__ bin) {
+  const float t = __ldg(thre);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) bin[i] = occs[i] > t ? 1 : 0;
+}
+
+extern "C" int b2n_occgrid_binarize(const float* occs, int64_t n, float occ_thre, double* scratch_parts, float* stats_out,
+                                    uint8_t* binaries, void* stream) {
+  B2N_REQUIRE(occs && scratch_parts && stats_out && n >= 1, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  occ_partial_kernel<<<OCC_PARTS, 256, 0, s>>>(occs, n, scratch_parts);
+  occ_threshold_kernel<<<1, 1, 0, s>>>(scratch_parts, n, occ_thre, stats_out);
+  if (binaries)
+    occ_binarize_kernel<<<(unsigned)min(div_up(n, 256), (int64_t)b2n_sm_count() * 16), 256, 0, s>>>(occs, n, stats_out, binaries);
+  B2N_LAUNCH_CHECK();
+}
+
+// nerfacc.ray_aabb_intersect (the reference's proxy: utils/math.py:138-175 intersect_aabb, division by d, no epsilon):
+// t_mins/t_maxs [n,K], hits uint8 [n,K]; misses get miss_value.
+__global__ void ray_aabb_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ aabbs,
+                                int64_t n, int k, float near_plane, float far_plane, float miss, float* __restrict__ tmin,
+                                float* __restrict__ tmax, uint8_t* __restrict__ hits) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * k) return;
+  const int64_t r = idx / k;
+  const int b = (int)(idx - r * k);
+  float tn = -INFINITY, tf = INFINITY;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float inv = div_rn(1.f, __ldg(d + 3 * r + a));
+    const float t1 = mul_rn(sub_rn(__ldg(aabbs + 6 * b + a), __ldg(o + 3 * r + a)), inv);
+    const float t2 = mul_rn(sub_rn(__ldg(aabbs + 6 * b + 3 + a), __ldg(o + 3 * r + a)), inv);
+    tn = fmaxf(tn, fminf(t1, t2)), tf = fminf(tf, fmaxf(t1, t2));
+  }
+  tn = fmaxf(tn, near_plane), tf = fminf(tf, far_plane);
+  const bool hit = tf > tn;
+  tmin[idx] = hit ? tn : miss, tmax[idx] = hit ? tf : miss, hits[idx] = hit ? 1 : 0;
+}
+
+extern "C" int b2n_ray_aabb_intersect(const float* origins, const float* directions, const float* aabbs, int64_t n_rays,
+                                      int32_t n_boxes, float near_plane, float far_plane, float miss_value, float* t_mins,
+                                      float* t_maxs, uint8_t* hits, void* stream) {
+  if (n_rays == 0 || n_boxes == 0) return B2N_OK;
+  B2N_REQUIRE(origins && directions && aabbs && t_mins && t_maxs && hits, "null pointer");
+  ray_aabb_kernel<<<(unsigned)div_up(n_rays * n_boxes, 256), 256, 0, (cudaStream_t)stream>>>(
+      origins, directions, aabbs, n_rays, n_boxes, near_plane, far_plane, miss_value, t_mins, t_maxs, hits);
+  B2N_LAUNCH_CHECK();
+}

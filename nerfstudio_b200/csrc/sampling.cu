@@ -2,8 +2,9 @@
 //
 // Index work (searchsorted) must be bit-exact with the reference's torch path
 // (nerfstudio/model_components/ray_samplers.py:78-128,276-372), so every elementwise step is a separately
-// rounded fp32 op, the running sums are accumulated in fp64 and rounded to fp32 per element (what torch's CPU
-// cumsum does), and linspace tables come from the host (torch.linspace) instead of being recomputed.
+// rounded fp32 op, the normaliser is summed in torch's CPU order (common.cuh:torch_cpu_row_sum), the running sums
+// are accumulated in fp64 and rounded to fp32 per element (what torch's CPU cumsum does; the fp64 partial sums of
+// pdf values >= 2^-15 are exact, so the scan order cannot change them), and linspace tables come from the host (torch.linspace) instead of being recomputed.
 // One warp owns one ray; cdf and bin edges live in shared memory; the scan is a warp-shuffle scan over
 // per-lane contiguous chunks.
 #include "common.cuh"
@@ -86,17 +87,14 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) pdf_sample_kernel(
   const int chunk = (S + 31) / 32;
   const int i0 = lane * chunk, i1 = min(S, i0 + chunk);
 
-  // pass 1: padded weights into smem (eb reused as scratch for w), fp64 total
-  double tot = 0.0;
+  // pass 1: padded weights into smem (eb reused as scratch for w); their sum in torch's CPU summation order
   for (int i = i0; i < i1; ++i) {
     float w = __ldg(wrow + i);
     if (anneal != 1.f) w = powf(w, anneal);
-    w = add_rn(w, pad_hist);
-    eb[i] = w;
-    tot += (double)w;
+    eb[i] = add_rn(w, pad_hist);
   }
-  tot = warp_sum_d(tot);
-  float w_sum = (float)tot;
+  __syncwarp();
+  float w_sum = torch_cpu_row_sum(eb, S, lane);
   const float padding = fmaxf(sub_rn(eps, w_sum), 0.f);
   const float pad_each = div_rn(padding, (float)S);
   w_sum = add_rn(w_sum, padding);
@@ -159,5 +157,21 @@ extern "C" int b2n_pdf_sample(const float* bins, const float* weights, const flo
       bins, weights, u_base, jitter, jitter_per_bin, nears, fars, n_rays, n_in, n_out, anneal, anneal_dev,
       histogram_padding, eps,
       spacing, new_sbins, new_ebins, cdf_out, inds_out);
+  B2N_LAUNCH_CHECK();
+}
+
+// diagnostic / parity pin: out[r] = torch.sum(x[r, :]) in torch's CPU summation order (common.cuh:torch_cpu_row_sum)
+__global__ void torch_row_sum_kernel(const float* __restrict__ x, int64_t n_rows, int S, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= n_rows) return;
+  const float v = torch_cpu_row_sum(x + r * S, S, lane);
+  if (lane == 0) out[r] = v;
+}
+
+extern "C" int b2n_torch_row_sum(const float* x, int64_t n_rows, int32_t n_cols, float* out, void* stream) {
+  if (n_rows == 0) return B2N_OK;
+  B2N_REQUIRE(x && out && n_cols >= 1, "bad arguments");
+  torch_row_sum_kernel<<<(unsigned)div_up(n_rows, 4), 128, 0, (cudaStream_t)stream>>>(x, n_rows, n_cols, out);
   B2N_LAUNCH_CHECK();
 }

@@ -66,12 +66,14 @@ class NerfactoStep:
         self.model, self.cfg, self.R = model, cfg, n_rays
         self.optim = FlatAdam(model, lr=lr, betas=betas, eps=eps, lr_schedule=lr_schedule)
         self.allreduce, self.use_graph = allreduce, use_graph
-        prop_ids = {id(p) for p in model.proposal_networks.parameters()}
-        firsts = [off for p, off in zip(self.optim.params, self.optim.offsets) if id(p) in prop_ids]
-        lasts = [off for p, off in zip(self.optim.params, self.optim.offsets) if id(p) not in prop_ids]
-        # flat layout is [field parameters | proposal parameters] (module registration order); fall back to one
-        # segment if a model orders them differently
-        self.grad_split = min(firsts) if firsts and lasts and min(firsts) > max(lasts) else self.optim.flat.numel()
+        # the proposal networks' segment of the flat buffer (FlatAdam groups parameters by Model.get_param_groups()).
+        # When it is the tail of the buffer the gradient all-reduce is split there (field segment summed while the
+        # proposal backward still runs); any other layout gets ONE all-reduce after the whole backward — never a
+        # collective over memory the proposal backward is still accumulating into.
+        seg = self.optim.segment_of("proposal_networks")
+        total = self.optim.flat.numel()
+        self.grad_split = seg[0] if seg is not None and seg[1] == total and seg[0] > 0 else None
+        self._prop_steps = 0  # optimiser steps the proposal group has taken (its own bias-correction count)
         self.always_update = always_update_proposals
         dev = self.optim.flat.device
         self.dev = dev
@@ -114,10 +116,11 @@ class NerfactoStep:
         self.gt = self.inputs[8 * R: 11 * R].view(R, 3)
         self.nears = torch.full((R,), float(cfg.near_plane), **f32)
         self.fars = torch.full((R,), float(cfg.far_plane), **f32)
-        self.hyper = torch.zeros(4, **f32)  # lr/bc1, 1/sqrt(bc2), grad_scale, anneal
+        # [lr/bc1, 1/sqrt(bc2), grad_scale, anneal | the same three for the proposal group's own step count, pad]
+        self.hyper = torch.zeros(8, **f32)
         # pinned staging ring for the per-step scalars: a slot is rewritten only after the async H2D copy that read it
         # has completed (the CPU may run many steps ahead of the stream)
-        self._hyper_ring = torch.zeros(self.HYPER_SLOTS, 4, dtype=torch.float32).pin_memory()
+        self._hyper_ring = torch.zeros(self.HYPER_SLOTS, 8, dtype=torch.float32).pin_memory()
         self._hyper_np = self._hyper_ring.numpy()  # same memory; one vectorised write per step
         self._hyper_events: List[Optional[torch.cuda.Event]] = [None] * self.HYPER_SLOTS
         self.lin0 = torch.linspace(0.0, 1.0, self.S[0] + 1).to(dev)
@@ -293,10 +296,23 @@ class NerfactoStep:
             for lvl in (0, 1):
                 self._density_net_bwd(lvl, self.props[lvl], None)
 
-    def _adam(self) -> None:
+    def _adam(self, update: bool = True) -> None:
+        """Fused Adam over the flat buffer.  Frozen proposal networks are NOT stepped (reference: their grads are None
+        and engine/optimizers.py:155 skips the group), and when they are, they use their own bias-correction count."""
         o = self.optim
-        call("b2n_adam_step_dev", ptr(o.flat), ptr(o.flat_grad), ptr(o.exp_avg), ptr(o.exp_avg_sq), o.flat.numel(),
-             ptr(self.hyper), float(o.betas[0]), float(o.betas[1]), float(o.eps), stream())
+        runs = []
+        for name, a, b in o.segments:
+            is_prop = name == "proposal_networks"
+            if is_prop and not update:
+                continue
+            slot = 4 if (is_prop and not self.always_update) else 0
+            if runs and runs[-1][1] == a and runs[-1][2] == slot:
+                runs[-1][1] = b
+            else:
+                runs.append([a, b, slot])
+        for a, b, slot in runs:
+            call("b2n_adam_step_dev", _off(o.flat, a), _off(o.flat_grad, a), _off(o.exp_avg, a), _off(o.exp_avg_sq, a),
+                 b - a, _off(self.hyper, slot), float(o.betas[0]), float(o.betas[1]), float(o.eps), stream())
 
     # ------------------------------------------------------------------------------------------------
     def set_batch(self, origins: Tensor, directions: Tensor, camera_indices: Tensor, gt_rgb: Tensor) -> None:
@@ -343,8 +359,11 @@ class NerfactoStep:
         slot = t % self.HYPER_SLOTS
         if self._hyper_events[slot] is not None:
             self._hyper_events[slot].synchronize()
+        pt = self._prop_steps
         self._hyper_np[slot] = (lr / (1.0 - o.betas[0] ** (t + 1)), 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1)),
-                                1.0 / world, self._anneal(t))
+                                1.0 / world, self._anneal(t),
+                                lr / (1.0 - o.betas[0] ** (pt + 1)), 1.0 / math.sqrt(1.0 - o.betas[1] ** (pt + 1)),
+                                1.0 / world, 0.0)
         self.hyper.copy_(self._hyper_ring[slot], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -364,25 +383,34 @@ class NerfactoStep:
                 if g is not None:
                     g.replay()
             else:
-                (self._body, self._body_props, lambda _u: self._adam())[i](update)
+                (self._body, self._body_props, self._adam)[i](update)
 
         # [forward + losses + main-field backward] -> start summing the field's gradient segment over NVLink while
         # the [proposal backward] runs -> sum the proposal segment -> [Adam].  One process per GPU, two collectives.
         run(0)
-        h_field = self.allreduce.start(o.flat_grad[: self.grad_split]) if overlap else None
+        split = self.grad_split if overlap else None
+        h_field = self.allreduce.start(o.flat_grad[:split]) if split is not None else None
         run(1)
-        h_prop = self.allreduce.start(o.flat_grad[self.grad_split:]) if overlap else None
+        h_rest = None
+        if overlap and split is None:
+            h_rest = self.allreduce.start(o.flat_grad)  # unknown layout: one collective after the whole backward
+        elif overlap and update:
+            h_rest = self.allreduce.start(o.flat_grad[split:])  # frozen proposals: nothing to sum, nothing stepped
         if overlap:
-            self.allreduce.finish(h_field, h_prop)
+            self.allreduce.finish(h_field, h_rest)
         run(2)
         return self._finish_step(update)
 
     def _finish_step(self, update: bool) -> Tensor:
         if update:
             self._steps_since_update = 0
+            self._prop_steps += 1
         self._steps_since_update += 1
         self.step_count += 1
         self.optim.steps += 1
+        for name in self.optim.group_steps:
+            if update or name != "proposal_networks":
+                self.optim.group_steps[name] += 1
         return self.losses
 
     def _capture(self, update: bool, split: bool) -> None:
@@ -394,7 +422,7 @@ class NerfactoStep:
         with torch.cuda.stream(s):
             self._body(update)
             self._body_props(update)
-            self._adam()
+            self._adam(update)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         for dst, src in zip((self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq), saved):
@@ -406,7 +434,7 @@ class NerfactoStep:
                 self._body(update)
                 if update:
                     self._body_props(update)
-                self._adam()
+                self._adam(update)
             self._graphs[update] = (None, None, None, g_all)
             return
         g_main, g_props, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
@@ -418,5 +446,5 @@ class NerfactoStep:
         else:
             g_props = None  # nothing to replay when the proposal networks are frozen this step
         with torch.cuda.graph(g_adam, pool=g_main.pool()):
-            self._adam()
+            self._adam(update)
         self._graphs[update] = (g_main, g_props, g_adam, None)

@@ -499,6 +499,14 @@ def pdf_sample(sbins: Tensor, weights: Tensor, num_samples: int, jitter: Optiona
     return (new_sb, new_eb, cdf, inds) if want_aux else (new_sb, new_eb)
 
 
+def torch_row_sum(x: Tensor) -> Tensor:
+    """Row sums of x [R,S] in the summation order of torch's CPU kernel (bit-identical to x.cpu().sum(-1))."""
+    x = _c(x.float())
+    out = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+    call("b2n_torch_row_sum", ptr(x), x.shape[0], x.shape[1], ptr(out), stream())
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # weights / compositing / losses
 # ----------------------------------------------------------------------------------------
@@ -817,12 +825,28 @@ def packed_accumulate(weights: Tensor, values: Optional[Tensor], packed_info: Te
     return _PackedAccumFn.apply(weights, values, _c(packed_info.long()))
 
 
+def _u8(binaries: Tensor) -> Tensor:
+    """bool and uint8 share the 1-byte 0/1 storage: view, never copy (the 128^3 x 4 grid is 8 MB)."""
+    b = _c(binaries)
+    return b.view(torch.uint8) if b.dtype == torch.bool else b
+
+
+def scan_counts(counts: Tensor) -> Tuple[Tensor, int]:
+    """int32 [n] -> (exclusive offsets int64 [n], total).  The total comes back to the host (one sync): the packed
+    outputs of the reference's API are dynamically sized."""
+    n = counts.shape[0]
+    offsets = torch.empty(n, device=counts.device, dtype=torch.int64)
+    total = torch.empty(1, device=counts.device, dtype=torch.int64)
+    call("b2n_scan_counts", ptr(counts, torch.int32), n, ptr(offsets, torch.int64), ptr(total, torch.int64), stream())
+    return offsets, int(total.item())
+
+
 def occgrid_march(origins, directions, binaries, roi_aabb, step, near_plane=0.0, far_plane=1e10, cone_angle=0.0,
                   jitter=None, t_min=None, t_max=None):
     """-> (ray_indices int64 [M], t_starts [M], t_ends [M]), sorted by ray then t.  binaries uint8/bool [levels,r,r,r]."""
     o, d = _c(origins.float()), _c(directions.float())
     R = o.shape[0]
-    b = _c(binaries.to(torch.uint8))
+    b = _u8(binaries)
     levels, res = b.shape[0], b.shape[1]
     roi = host_floats(roi_aabb)
     roip = C.cast(roi, C.c_void_p)
@@ -831,9 +855,7 @@ def occgrid_march(origins, directions, binaries, roi_aabb, step, near_plane=0.0,
     counts = torch.empty(R, device=o.device, dtype=torch.int32)
     call("b2n_occgrid_count", ptr(o), ptr(d), ptr(tmn), ptr(tmx), ptr(b, torch.uint8), levels, res, roip, float(step),
          float(cone_angle), float(near_plane), float(far_plane), ptr(jit), R, ptr(counts, torch.int32), stream())
-    csum = torch.cumsum(counts.long(), 0)
-    offsets = _c(csum - counts.long())
-    M = int(csum[-1].item()) if R > 0 else 0
+    offsets, M = scan_counts(counts) if R > 0 else (None, 0)
     ri = torch.empty(M, device=o.device, dtype=torch.int64)
     ts = torch.empty(M, device=o.device, dtype=torch.float32)
     te = torch.empty(M, device=o.device, dtype=torch.float32)
@@ -842,6 +864,79 @@ def occgrid_march(origins, directions, binaries, roi_aabb, step, near_plane=0.0,
              float(cone_angle), float(near_plane), float(far_plane), ptr(jit), R, ptr(offsets, torch.int64),
              ptr(ri, torch.int64), ptr(ts), ptr(te), stream())
     return ri, ts, te
+
+
+def packed_positions(origins: Tensor, directions: Tensor, ray_indices: Tensor, t_starts: Tensor, t_ends: Tensor) -> Tensor:
+    """Sample midpoints o[ray] + d[ray] * (ts + te)/2 -> [M,3] (no [M,3] gathers of origins/directions materialised)."""
+    o, d, ri = _c(origins.float()), _c(directions.float()), _c(ray_indices.long())
+    ts, te = _c(t_starts.float().reshape(-1)), _c(t_ends.float().reshape(-1))
+    x = torch.empty(ri.shape[0], 3, device=o.device, dtype=torch.float32)
+    call("b2n_packed_positions", ptr(o), ptr(d), ptr(ri, torch.int64), ptr(ts), ptr(te), ri.shape[0], ptr(x), stream())
+    return x
+
+
+def packed_prune(ray_indices: Tensor, t_starts: Tensor, t_ends: Tensor, trans: Tensor, alphas: Tensor, packed_info: Tensor,
+                 early_stop_eps: float, alpha_thre: float, alpha_cap: Optional[Tensor] = None):
+    """K8: keep samples with T >= early_stop_eps and alpha >= alpha_thre -> compacted (ray_indices, t_starts, t_ends).
+    alpha_cap: optional device scalar; the threshold used is min(alpha_thre, alpha_cap) (nerfacc caps it with
+    occs.mean() — kept on the device so no host round trip is needed)."""
+    info = _c(packed_info.long())
+    R = info.shape[0]
+    tr, al, ts, te = _c(trans.float()), _c(alphas.float()), _c(t_starts.float()), _c(t_ends.float())
+    counts = torch.empty(R, device=tr.device, dtype=torch.int32)
+    call("b2n_packed_prune_count", ptr(tr), ptr(al), ptr(info, torch.int64), R, float(early_stop_eps), float(alpha_thre),
+         ptr(alpha_cap), ptr(counts, torch.int32), stream())
+    offsets, M = scan_counts(counts)
+    ri = torch.empty(M, device=tr.device, dtype=torch.int64)
+    ots, ote = torch.empty(M, device=tr.device), torch.empty(M, device=tr.device)
+    if M > 0:
+        call("b2n_packed_prune_fill", ptr(tr), ptr(al), ptr(info, torch.int64), R, float(early_stop_eps), float(alpha_thre),
+             ptr(alpha_cap), ptr(offsets, torch.int64), ptr(ts), ptr(te), ptr(ri, torch.int64), ptr(ots), ptr(ote), stream())
+    return ri, ots, ote
+
+
+def occgrid_points(cell_ids: Optional[Tensor], jitter: Tensor, res: int, level_aabb: Sequence[float]) -> Tensor:
+    """Jittered sample point of each listed cell of one grid level (cell_ids None = every cell in order)."""
+    jit = _c(jitter.float())
+    n = jit.shape[0]
+    ids = None if cell_ids is None else _c(cell_ids.long())
+    x = torch.empty(n, 3, device=jit.device, dtype=torch.float32)
+    box = host_floats(level_aabb)
+    call("b2n_occgrid_points", ptr(ids, torch.int64), ptr(jit), n, int(res), C.cast(box, C.c_void_p), ptr(x), stream())
+    return x
+
+
+def occgrid_ema(occs: Tensor, cell_ids: Optional[Tensor], occ_new: Tensor, level_offset: int, ema_decay: float) -> None:
+    """In place: occs[level_offset + cell] = max(occs[..] * decay, occ_new) (old values; duplicates -> largest)."""
+    occ_new = _c(occ_new.float().reshape(-1))
+    n = occ_new.shape[0]
+    ids = None if cell_ids is None else _c(cell_ids.long())
+    scratch = torch.empty(n, device=occs.device, dtype=torch.float32)
+    call("b2n_occgrid_ema", ptr(occs), ptr(ids, torch.int64), ptr(occ_new), n, int(level_offset), float(ema_decay),
+         ptr(scratch), stream())
+
+
+def occgrid_binarize(occs: Tensor, occ_thre: float, binaries_out: Optional[Tensor]) -> Tensor:
+    """binaries_out (bool/uint8, occs.numel() elements; None = statistics only) <- occs > min(mean(occs), occ_thre).
+    Returns a device tensor [threshold used, mean(occs)]."""
+    parts = torch.empty(512, device=occs.device, dtype=torch.float64)
+    stats = torch.empty(2, device=occs.device, dtype=torch.float32)
+    b = None if binaries_out is None else _u8(binaries_out)
+    call("b2n_occgrid_binarize", ptr(occs), occs.numel(), float(occ_thre), ptr(parts, torch.float64), ptr(stats),
+         ptr(b, torch.uint8), stream())
+    return stats
+
+
+def ray_aabb_intersect(origins: Tensor, directions: Tensor, aabbs: Tensor, near_plane: float, far_plane: float,
+                       miss_value: float):
+    o, d, bx = _c(origins.float()), _c(directions.float()), _c(aabbs.float().reshape(-1, 6))
+    n, k = o.shape[0], bx.shape[0]
+    tmin = torch.empty(n, k, device=o.device, dtype=torch.float32)
+    tmax = torch.empty_like(tmin)
+    hits = torch.empty(n, k, device=o.device, dtype=torch.uint8)
+    call("b2n_ray_aabb_intersect", ptr(o), ptr(d), ptr(bx), n, k, float(near_plane), float(far_plane), float(miss_value),
+         ptr(tmin), ptr(tmax), ptr(hits, torch.uint8), stream())
+    return tmin, tmax, hits.bool()
 
 
 # ----------------------------------------------------------------------------------------

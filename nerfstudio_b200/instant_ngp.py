@@ -97,3 +97,31 @@ class NGPModel(nn.Module):
         pred, gt = self.renderer_rgb.blend_background_for_loss_computation(
             pred_image=outputs["rgb"], pred_accumulation=outputs["accumulation"], gt_image=batch["image"])
         return {"rgb_loss": self.rgb_loss(gt, pred)}
+
+
+class NGPTrainer:
+    """One instant-ngp optimisation step as engine/trainer.py:486-530 runs it: occupancy callback
+    (BEFORE_TRAIN_ITERATION, models/instant_ngp.py:149-164), forward on packed samples, MSE loss, backward, (gradient
+    all-reduce), fused Adam over one flat buffer (configs/method_configs.py:263-270: Adam lr 1e-2 eps 1e-15)."""
+
+    def __init__(self, model: NGPModel, lr: float = 1e-2, eps: float = 1e-15, allreduce=None) -> None:
+        from .optim import FlatAdam
+
+        self.model, self.allreduce, self.step = model, allreduce, 0
+        self.optim = FlatAdam(model, lr=lr, eps=eps)
+        self.last_num_samples = 0
+
+    def train_iteration(self, ray_bundle: RayBundle, batch: Dict[str, Tensor]) -> Dict[str, Tensor]:
+        m = self.model
+        m.train()
+        m.update_occupancy_grid(self.step)
+        self.optim.zero_grad()
+        out = m(ray_bundle)
+        loss_dict = m.get_loss_dict(out, batch)
+        loss = loss_dict["rgb_loss"]
+        loss.backward()
+        scale = self.allreduce(self.optim.flat_grad) if self.allreduce is not None else 1.0
+        self.optim.step(grad_scale=scale)
+        self.step += 1
+        self.num_samples = out["num_samples_per_ray"]  # device tensor; summed by the caller when it wants M
+        return {"loss": loss.detach(), "rgb_loss": loss.detach()}

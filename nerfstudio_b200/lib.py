@@ -64,6 +64,7 @@ _SIGNATURES = {
     "b2n_density_act_bwd": [_P, _I64, _P, _P, _I64, _F, _P, _I64, _P],
     "b2n_spaced_sample": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P, _P],
     "b2n_pdf_sample": [_P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _I32, _F, _P, _F, _F, _I32, _P, _P, _P, _P, _P],
+    "b2n_torch_row_sum": [_P, _I64, _I32, _P, _P],
     "b2n_weights_fwd": [_P, _P, _I64, _P, _I64, _I32, _P, _P],
     "b2n_weights_bwd": [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P],
     "b2n_composite_fwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P],
@@ -81,6 +82,14 @@ _SIGNATURES = {
     "b2n_packed_accumulate_bwd": [_P, _P, _I32, _P, _P, _I64, _P, _P, _P],
     "b2n_occgrid_count": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P],
     "b2n_occgrid_fill": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P, _P, _P, _P],
+    "b2n_scan_counts": [_P, _I64, _P, _P, _P],
+    "b2n_packed_positions": [_P, _P, _P, _P, _P, _I64, _P, _P],
+    "b2n_packed_prune_count": [_P, _P, _P, _I64, _F, _F, _P, _P, _P],
+    "b2n_packed_prune_fill": [_P, _P, _P, _I64, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b2n_occgrid_points": [_P, _P, _I64, _I32, _P, _P, _P],
+    "b2n_occgrid_ema": [_P, _P, _P, _I64, _I64, _F, _P, _P],
+    "b2n_occgrid_binarize": [_P, _I64, _F, _P, _P, _P, _P],
+    "b2n_ray_aabb_intersect": [_P, _P, _P, _I64, _I32, _F, _F, _F, _P, _P, _P, _P],
     "b2n_density_field_fwd": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _F, _P, _P],
     "b2n_density_field_bwd": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _P, _I64, _I64,
                               _I32, _I32, _P, _F, _P, _P, _P],
@@ -143,6 +152,7 @@ LAUNCHES = 0  # kernel-launching C-ABI calls made by this process (bench.py repo
 
 
 PROFILE = None  # set to {} to time every C-ABI launch with CUDA events on the launching stream (eager mode only)
+PROFILE_BY_SIZE = True  # False: one row per entry point (dynamic sizes, e.g. packed instant-ngp samples); n is summed
 _N_ARG = {"b2n_hashgrid_fwd": 3, "b2n_hashgrid_bwd": 4, "b2n_mlp_fwd": 2, "b2n_mlp_bwd": 6, "b2n_mlp_tc_fwd": 3,
           "b2n_mlp_tc_bwd": 7}
 
@@ -157,18 +167,29 @@ def call(name: str, *args) -> None:
     e0.record()
     check(getattr(load(), name)(*args), name)
     e1.record()
-    if name == "b2n_density_field_fwd":
+    n_arg = int(args[_N_ARG[name]]) if name in _N_ARG else 0
+    if not PROFILE_BY_SIZE:
+        key = name
+    elif name == "b2n_density_field_fwd":
         key = f"{name}[n={args[8] * args[9]}]"
     elif name == "b2n_density_field_bwd":
         key = f"{name}[n={args[9] * args[10]}]"
+    elif name in _N_ARG and name.startswith("b2n_mlp"):
+        m = args[0]._obj  # byref(B2nMlp): two networks of one model may share n (base / colour head)
+        key = f"{name}[n={args[_N_ARG[name]]},in={m.in_dim},out={m.out_dims[m.n_layers - 1]}]"
     else:
         key = f"{name}[n={args[_N_ARG[name]]}]" if name in _N_ARG else name
-    PROFILE.setdefault(key, []).append((e0, e1))
+    PROFILE.setdefault(key, []).append((e0, e1, n_arg))
 
 
 def profile_summary() -> dict:
     """key -> (launches, total ms); call after torch.cuda.synchronize()."""
-    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (PROFILE or {}).items()}
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b, _ in v)) for k, v in (PROFILE or {}).items()}
+
+
+def profile_sizes() -> dict:
+    """key -> sum of the size argument n over the profiled launches (entry points listed in _N_ARG)."""
+    return {k: sum(n for _, _, n in v) for k, v in (PROFILE or {}).items()}
 
 
 def stream() -> C.c_void_p:

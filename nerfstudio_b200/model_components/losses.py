@@ -31,17 +31,30 @@ def distortion_loss(weights_list: List[Tensor], ray_samples_list) -> Tensor:
     return F.distortion_loss(weights_list[-1][..., 0], ray_samples_to_sdist(ray_samples_list[-1]))
 
 
+class _DistortionRowsFn(torch.autograd.Function):
+    """Per-ray distortion values [R] (losses.py:135-146), differentiable w.r.t. w."""
+
+    @staticmethod
+    def forward(ctx, t: Tensor, w: Tensor) -> Tensor:
+        import ctypes as C
+
+        from ..lib import call, ptr, stream
+
+        t, w = t.contiguous().float(), w.contiguous().float()
+        rows = torch.empty(w.shape[0], device=w.device)
+        d_w = torch.empty_like(w)
+        call("b2n_distortion_fwd_bwd", ptr(t), ptr(w), w.shape[0], w.shape[1], 1.0, ptr(rows), ptr(d_w), stream())
+        ctx.save_for_backward(d_w)
+        return rows
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        (d_w,) = ctx.saved_tensors
+        return None, d_w * g[:, None]
+
+
 def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
-    """Per-ray distortion values [R] (no mean)."""
-    return F._DistortionFn.apply(t.detach(), w) if w.dim() == 1 else _rows(t, w)
-
-
-def _rows(t: Tensor, w: Tensor) -> Tensor:
-    import ctypes as C
-
-    from ..lib import call, ptr, stream
-
-    t, w = t.contiguous().float(), w.contiguous().float()
-    rows = torch.empty(w.shape[0], device=w.device)
-    call("b2n_distortion_fwd_bwd", ptr(t), ptr(w), w.shape[0], w.shape[1], 1.0, ptr(rows), C.c_void_p(0), stream())
-    return rows
+    """Per-ray distortion values (no mean): t [R,S+1] (or [S+1]), w [R,S] (or [S]) -> [R] (or a scalar)."""
+    if w.dim() == 1:
+        return _DistortionRowsFn.apply(t.detach()[None], w[None])[0]
+    return _DistortionRowsFn.apply(t.detach(), w)

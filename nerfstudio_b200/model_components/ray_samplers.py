@@ -8,6 +8,8 @@ the reference draws it (`torch.rand((R,1))` / `((R,S+1))`), so seeded runs consu
 """
 from __future__ import annotations
 
+import contextlib
+
 from typing import Any, Callable, List, Optional, Tuple
 
 import torch
@@ -191,6 +193,7 @@ class ProposalNetworkSampler(Sampler):
         self._anneal = 1.0
         self._steps_since_update = 0
         self._step = 0
+        self.last_updated = True
 
     def set_anneal(self, anneal: float) -> None:
         self._anneal = anneal
@@ -218,7 +221,8 @@ class ProposalNetworkSampler(Sampler):
             if is_prop:
                 fn = density_fns[i_level]
                 field = getattr(fn, "__self__", None)
-                with torch.enable_grad() if updated else torch.no_grad():
+                # the reference adds no_grad on frozen steps and otherwise inherits the caller's grad mode (:604-609)
+                with contextlib.nullcontext() if updated else torch.no_grad():
                     if field is not None and hasattr(field, "get_density") and getattr(fn, "__name__", "") == "density_fn":
                         density, _ = field.get_density(ray_samples)  # ray form: no [R,S,3] positions materialised
                     else:
@@ -226,6 +230,7 @@ class ProposalNetworkSampler(Sampler):
                     weights = ray_samples.get_weights(density)
                 weights_list.append(weights)
                 ray_samples_list.append(ray_samples)
+        self.last_updated = bool(updated)  # the trainer skips the optimiser step of frozen proposal networks
         if updated:
             self._steps_since_update = 0
         assert ray_samples is not None
@@ -247,7 +252,7 @@ class VolumetricSampler(Sampler):
         density_fn = self.density_fn
 
         def sigma_fn(t_starts, t_ends, ray_indices):
-            positions = origins[ray_indices] + directions[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+            positions = F.packed_positions(origins, directions, ray_indices, t_starts, t_ends)  # o + d (ts+te)/2
             if times is None:
                 return density_fn(positions).squeeze(-1)
             return density_fn(positions, times[ray_indices]).squeeze(-1)

@@ -206,7 +206,9 @@ class Trainer:
         scale = 1.0
         if self.allreduce is not None:
             scale = self.allreduce(self.optim.flat_grad)
-        self.optim.step(grad_scale=scale)
+        # frozen proposal networks are not stepped (their grads are None in the reference: engine/optimizers.py:155)
+        active = None if m.proposal_sampler.last_updated else [g for g in self.optim.group_steps if g != "proposal_networks"]
+        self.optim.step(grad_scale=scale, active=active)
         m.after_train_iteration(self.step)
         self.step += 1
         loss_dict["loss"] = loss.detach()

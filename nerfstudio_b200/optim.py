@@ -5,7 +5,12 @@ multi-GPU path all-reduces with one NCCL call.
 
 Semantics = torch.optim.Adam as the reference configures it (engine/optimizers.py:51-58;
 configs/method_configs.py:106-119): lr 1e-2, betas (0.9, 0.999), eps 1e-15, no weight decay, every element
-updated every step (moments decay even where the gradient is zero)."""
+updated on every step IN WHICH ITS GROUP RECEIVED GRADIENTS.  The reference's
+`Optimizers.optimizer_scaler_step_all` (engine/optimizers.py:142-159) steps a parameter group only when some
+`p.grad is not None`; nerfacto's proposal networks run under `no_grad` on most steps after the first ten
+(model_components/ray_samplers.py:590,604-609), so on those steps their parameters, moments and bias-correction step
+count stay untouched.  `step(active=...)` reproduces that: groups come from the module's `get_param_groups()`, each
+keeps its own step counter, and contiguous active segments with equal counters share one kernel launch."""
 from __future__ import annotations
 
 from typing import Callable, Optional
@@ -45,6 +50,21 @@ class FlatAdam:
         self.params, self.offsets = params, offs
         self.lr, self.betas, self.eps, self.lr_schedule = lr, betas, eps, lr_schedule
         self.steps = 0
+        # parameter groups (reference: Model.get_param_groups) -> contiguous [start, end) segments of the flat buffer
+        group_of = {}
+        if hasattr(module, "get_param_groups"):
+            for name, plist in module.get_param_groups().items():
+                for p in plist:
+                    group_of[id(p)] = name
+        self.segments = []  # [name, start, end]
+        for p, off in zip(params, offs):
+            name = group_of.get(id(p), "default")
+            end = off + (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            if self.segments and self.segments[-1][0] == name and self.segments[-1][2] == off:
+                self.segments[-1][2] = end
+            else:
+                self.segments.append([name, off, end])
+        self.group_steps = {name: 0 for name, _, _ in self.segments}
 
     def zero_grad(self) -> None:
         self.flat_grad.zero_()
@@ -52,8 +72,27 @@ class FlatAdam:
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
                 p.grad = self.flat_grad[off: off + p.numel()].view(p.shape)
 
-    def step(self, grad_scale: float = 1.0) -> None:
+    def segment_of(self, group: str):
+        """(start, end) of a group that occupies ONE contiguous range of the flat buffer, else None."""
+        segs = [(a, b) for name, a, b in self.segments if name == group]
+        return segs[0] if len(segs) == 1 else None
+
+    def step(self, grad_scale: float = 1.0, active=None) -> None:
+        """active: iterable of group names that received gradients this step (None = all)."""
         self.steps += 1
         lr = self.lr_schedule(self.steps - 1) if self.lr_schedule is not None else self.lr
-        F.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.steps, lr, self.betas, self.eps,
-                    grad_scale)
+        names = set(self.group_steps) if active is None else set(active) & set(self.group_steps)
+        for name in names:
+            self.group_steps[name] += 1
+        runs = []  # merge neighbouring active segments whose step counts agree: one launch in the common case
+        for name, a, b in self.segments:
+            if name not in names:
+                continue
+            t = self.group_steps[name]
+            if runs and runs[-1][1] == a and runs[-1][2] == t:
+                runs[-1][1] = b
+            else:
+                runs.append([a, b, t])
+        for a, b, t in runs:
+            F.adam_step(self.flat[a:b], self.flat_grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], t, lr, self.betas,
+                        self.eps, grad_scale)

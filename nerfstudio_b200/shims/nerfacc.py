@@ -5,7 +5,8 @@ calls `OccGridEstimator(...).sampling / .update_every_n_steps`, `pack_info`, `re
 `accumulate_along_rays`, `ray_aabb_intersect` (models/instant_ngp.py:120-198).  nerfacc 0.5.2's
 sources are not available here; semantics follow its published behaviour and are restated in
 oracle/nerf_oracle.py — parity with nerfacc itself is UNPINNED, parity with the oracle is bit-exact for
-ray indices / counts.
+ray indices / counts / occupancy bits.  Every arithmetic step runs in csrc/packed.cu; torch supplies buffers and
+random draws only.
 """
 from __future__ import annotations
 
@@ -42,20 +43,14 @@ def accumulate_along_rays(weights: Tensor, values: Optional[Tensor] = None, ray_
 
 def ray_aabb_intersect(rays_o: Tensor, rays_d: Tensor, aabbs: Tensor, near_plane: float = -float("inf"),
                        far_plane: float = float("inf"), miss_value: float = float("inf")):
-    """-> (t_mins [n,K], t_maxs [n,K], hits [n,K]) — small slab test, torch ops (not on the per-step path)."""
-    o, d = rays_o[:, None, :], rays_d[:, None, :]
-    inv = 1.0 / d
-    t1 = (aabbs[None, :, :3] - o) * inv
-    t2 = (aabbs[None, :, 3:] - o) * inv
-    tmin = torch.minimum(t1, t2).amax(-1).clamp(min=near_plane)
-    tmax = torch.maximum(t1, t2).amin(-1).clamp(max=far_plane)
-    hits = tmax > tmin
-    return torch.where(hits, tmin, torch.full_like(tmin, miss_value)), \
-        torch.where(hits, tmax, torch.full_like(tmax, miss_value)), hits
+    """-> (t_mins [n,K], t_maxs [n,K], hits [n,K]): slab test kernel (packed.cu:ray_aabb_kernel)."""
+    return F.ray_aabb_intersect(rays_o, rays_d, aabbs, near_plane, far_plane, miss_value)
 
 
 class OccGridEstimator(nn.Module):
-    """Multi-level occupancy grid: marching (K7), visibility pruning (K8) and EMA update (K9)."""
+    """Multi-level occupancy grid: marching (K7), visibility pruning (K8) and EMA update (K9) on the kernels of
+    csrc/packed.cu.  torch is used for the buffers (state_dict-visible, as nerfacc's) and for the random draws
+    (stratified offsets, cell sampling, jitter) — the reference never seeds these per op, so tests pass them in."""
 
     def __init__(self, roi_aabb: Union[Tensor, list], resolution: Union[int, list, Tensor] = 128, levels: int = 1) -> None:
         super().__init__()
@@ -66,30 +61,39 @@ class OccGridEstimator(nn.Module):
         assert int(res[0]) == int(res[1]) == int(res[2]), "cubic grids only"
         self.levels = levels
         self.cells_per_lvl = int(res.prod().item())
+        self._res = int(res[0])
         centre, half = (roi[:3] + roi[3:]) / 2, (roi[3:] - roi[:3]) / 2
         aabbs = torch.stack([torch.cat([centre - half * 2 ** i, centre + half * 2 ** i]) for i in range(levels)])
+        self._roi = roi.tolist()
+        self._level_boxes = [aabbs[i].tolist() for i in range(levels)]
         self.register_buffer("resolution", res)
         self.register_buffer("aabbs", aabbs)
         self.register_buffer("occs", torch.zeros(levels * self.cells_per_lvl))
         self.register_buffer("binaries", torch.zeros([levels] + res.tolist(), dtype=torch.bool))
-        r = int(res[0])
-        coords = torch.stack(torch.meshgrid([torch.arange(r)] * 3, indexing="ij"), dim=-1).reshape(-1, 3)
-        self.register_buffer("grid_coords", coords, persistent=False)
-        self.register_buffer("grid_indices", torch.arange(self.cells_per_lvl), persistent=False)
+        self._stats: Optional[Tensor] = None  # device [threshold, mean(occs)] of the current occs (None = stale)
+
+    def _load_from_state_dict(self, *a, **k):
+        self._stats = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _occ_stats(self) -> Tensor:
+        if self._stats is None or self._stats.device != self.occs.device:
+            self._stats = F.occgrid_binarize(self.occs, 1e-2, None)
+        return self._stats
 
     @torch.no_grad()
     def sampling(self, rays_o: Tensor, rays_d: Tensor, sigma_fn: Optional[Callable] = None,
                  alpha_fn: Optional[Callable] = None, near_plane: float = 0.0, far_plane: float = 1e10,
                  t_min: Optional[Tensor] = None, t_max: Optional[Tensor] = None, render_step_size: float = 1e-3,
                  early_stop_eps: float = 1e-4, alpha_thre: float = 0.0, stratified: bool = False,
-                 cone_angle: float = 0.0) -> Tuple[Tensor, Tensor, Tensor]:
-        jitter = torch.rand(rays_o.shape[0], device=rays_o.device) if stratified else None
-        ri, ts, te = F.occgrid_march(rays_o, rays_d, self.binaries, self.aabbs[0].tolist(), render_step_size,
+                 cone_angle: float = 0.0, jitter: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """`jitter` (extension, tests): the per-ray stratified offsets in [0,1) instead of a fresh torch.rand draw."""
+        if jitter is None and stratified:
+            jitter = torch.rand(rays_o.shape[0], device=rays_o.device)
+        ri, ts, te = F.occgrid_march(rays_o, rays_d, self.binaries, self._roi, render_step_size,
                                      near_plane, far_plane, cone_angle, jitter, t_min, t_max)
         if (sigma_fn is not None or alpha_fn is not None) and ri.numel() > 0:
-            alpha_thre = min(alpha_thre, float(self.occs.mean().item()))
-            n_rays = rays_o.shape[0]
-            info = F.pack_info(ri, n_rays)
+            info = F.pack_info(ri, rays_o.shape[0])
             if sigma_fn is not None:
                 sigmas = sigma_fn(ts, te, ri).reshape(-1).float()
                 _, trans, alphas = F.packed_weights(ts, te, sigmas, info)
@@ -98,32 +102,39 @@ class OccGridEstimator(nn.Module):
                 # T = exclusive product of (1 - alpha): reuse the density kernel with sigma*dt = -log(1-alpha)
                 sd = -torch.log1p(-alphas.clamp(max=1 - 1e-7))
                 _, trans, _ = F.packed_weights(torch.zeros_like(sd), torch.ones_like(sd), sd, info)
-            keep = (trans >= early_stop_eps) & (alphas >= alpha_thre)
-            ri, ts, te = ri[keep], ts[keep], te[keep]
+            # alpha_thre = min(alpha_thre, occs.mean()) — the mean stays on the device (stats[1])
+            ri, ts, te = F.packed_prune(ri, ts, te, trans, alphas, info, early_stop_eps, alpha_thre,
+                                        alpha_cap=self._occ_stats()[1:2])
         return ri, ts, te
+
+    def _sample_cells(self, lvl: int, n: int) -> Tensor:
+        """nerfacc `_sample_uniform_and_occupied_cells`: n uniform cells + (up to) n currently occupied ones."""
+        dev = self.occs.device
+        uniform = torch.randint(self.cells_per_lvl, (n,), device=dev)
+        occupied = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
+        if n < occupied.numel():
+            occupied = occupied[torch.randint(occupied.numel(), (n,), device=dev)]
+        return torch.cat([uniform, occupied])
 
     @torch.no_grad()
     def update_every_n_steps(self, step: int, occ_eval_fn: Callable, occ_thre: float = 1e-2, ema_decay: float = 0.95,
-                             warmup_steps: int = 256, n: int = 16) -> None:
+                             warmup_steps: int = 256, n: int = 16, cells: Optional[list] = None,
+                             jitters: Optional[list] = None) -> None:
+        """`cells` / `jitters` (extension, tests): per-level recorded cell ids (None = all cells) and [n,3] jitter
+        instead of fresh draws."""
         if not self.training or step % n != 0:
             return
-        r = int(self.resolution[0])
         dev = self.occs.device
         for lvl in range(self.levels):
-            if step < warmup_steps:
-                idx = self.grid_indices
+            if cells is not None:
+                idx = cells[lvl]
+            elif step < warmup_steps:
+                idx = None  # every cell of the level, in order
             else:
-                n_s = self.cells_per_lvl // 4
-                uniform = torch.randint(self.cells_per_lvl, (n_s,), device=dev)
-                occupied = torch.nonzero(self.binaries[lvl].flatten())[:, 0]
-                if occupied.numel() > n_s:
-                    occupied = occupied[torch.randint(occupied.numel(), (n_s,), device=dev)]
-                idx = torch.cat([uniform, occupied])
-            coords = self.grid_coords[idx]
-            x = (coords + torch.rand(coords.shape, device=dev)) / r
-            lo, hi = self.aabbs[lvl, :3], self.aabbs[lvl, 3:]
-            occ = occ_eval_fn(lo + x * (hi - lo)).reshape(-1).float()
-            cell = idx + lvl * self.cells_per_lvl
-            self.occs[cell] = torch.maximum(self.occs[cell] * ema_decay, occ)
-        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
-        self.binaries = (self.occs > thre).view(self.binaries.shape)
+                idx = self._sample_cells(lvl, self.cells_per_lvl // 4)
+            count = self.cells_per_lvl if idx is None else idx.numel()
+            jit = jitters[lvl] if jitters is not None else torch.rand(count, 3, device=dev)
+            x = F.occgrid_points(idx, jit, self._res, self._level_boxes[lvl])
+            occ = occ_eval_fn(x).reshape(-1).float()
+            F.occgrid_ema(self.occs, idx, occ, lvl * self.cells_per_lvl, ema_decay)
+        self._stats = F.occgrid_binarize(self.occs, occ_thre, self.binaries)

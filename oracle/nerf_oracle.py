@@ -673,6 +673,49 @@ def occgrid_march(
     return torch.tensor(ri, dtype=torch.int64), torch.stack(ts), torch.stack(te)
 
 
+def packed_visibility_prune(ray_indices: Tensor, t_starts: Tensor, t_ends: Tensor, sigmas: Tensor, n_rays: int,
+                            early_stop_eps: float, alpha_thre: float, occs_mean: Optional[float] = None):
+    """Pruning inside nerfacc's OccGridEstimator.sampling when a sigma_fn is given (training; call site
+    model_components/ray_samplers.py:481-493): alpha_thre = min(alpha_thre, occs.mean()); keep samples with
+    T >= early_stop_eps and alpha >= alpha_thre (render_visibility_from_density).  PARITY UNPINNED (restated)."""
+    if occs_mean is not None:
+        alpha_thre = min(alpha_thre, occs_mean)
+    _, trans, alphas = packed_weights(t_starts, t_ends, sigmas, ray_indices, n_rays)
+    keep = (trans >= early_stop_eps) & (alphas >= alpha_thre)
+    return ray_indices[keep], t_starts[keep], t_ends[keep], keep
+
+
+def occgrid_cell_points(cell_ids: Tensor, jitter: Tensor, res: int, level_aabb: Tensor) -> Tensor:
+    """Jittered sample position of grid cells (nerfacc OccGridEstimator._update): coords from the ij-meshgrid flattening
+    id = (x*res + y)*res + z; x = lo + ((coord + jitter)/res) * (hi - lo)."""
+    coords = torch.stack([cell_ids // (res * res), (cell_ids // res) % res, cell_ids % res], -1).to(torch.float32)
+    u = (coords + jitter) / res
+    return level_aabb[:3] + u * (level_aabb[3:] - level_aabb[:3])
+
+
+def occgrid_update(occs: Tensor, levels: int, res: int, aabbs: Tensor, cells: List[Optional[Tensor]], jitters: List[Tensor],
+                   occ_eval_fn, occ_thre: float = 1e-2, ema_decay: float = 0.95):
+    """One occupancy update (nerfacc OccGridEstimator._update via update_every_n_steps; called by
+    models/instant_ngp.py:149-164 with occ_eval_fn = density_fn(x) * render_step_size).  `cells[l]` = sampled cell ids of
+    level l (None = all cells: the warm-up case), `jitters[l]` = their [n,3] U(0,1) offsets — the recorded random stream.
+    EMA: occs[cell] = max(occs[cell]*decay, occ) with candidates formed from the OLD values; nerfacc's indexed assignment
+    leaves the winner among duplicate cells unspecified — restated as the largest candidate.  Threshold
+    min(mean(occs), occ_thre) with the mean accumulated in fp64.  Returns (occs, binaries bool [levels*res^3], thre).
+    PARITY UNPINNED (nerfacc 0.5.2 sources unavailable)."""
+    occs = occs.clone()
+    per = res ** 3
+    for lvl in range(levels):
+        ids = torch.arange(per) if cells[lvl] is None else cells[lvl]
+        x = occgrid_cell_points(ids, jitters[lvl], res, aabbs[lvl])
+        occ = occ_eval_fn(x).reshape(-1).to(torch.float32).clamp_min(0.0)
+        cand = torch.maximum(occs[lvl * per + ids] * ema_decay, occ)
+        occs[lvl * per + ids] = 0.0
+        occs.scatter_reduce_(0, lvl * per + ids, cand, reduce="amax", include_self=True)
+    mean = (occs.double().sum() / occs.numel()).to(torch.float32)
+    thre = torch.minimum(mean, torch.tensor(occ_thre, dtype=torch.float32))
+    return occs, occs > thre, thre
+
+
 # ----------------------------------------------------------------------------------------
 # full nerfacto training step (a7 + a15..a24), the unit `bench.py --impl reference` times
 # ----------------------------------------------------------------------------------------

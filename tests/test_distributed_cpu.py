@@ -90,3 +90,53 @@ def test_reference_arm_runs_on_rank0_only():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_flat_adam_skips_frozen_groups(monkeypatch):
+    """optim.FlatAdam.step(active=...): a group that received no gradients this step is not touched (parameters, moments,
+    bias-correction count) — the reference's Optimizers.optimizer_scaler_step_all skips groups whose grads are None
+    (engine/optimizers.py:142-159).  Host logic only: the kernel call is replaced by the oracle's Adam."""
+    from oracle import nerf_oracle as O
+    from nerfstudio_b200 import functional as F
+    from nerfstudio_b200.optim import FlatAdam
+
+    calls = []
+
+    def fake_adam(p, g, m, v, step, lr, betas=(0.9, 0.999), eps=1e-15, grad_scale=1.0):
+        calls.append((p.data_ptr(), p.numel(), step))
+        O.adam_step(p, g * grad_scale, m, v, step, lr, betas[0], betas[1], eps)
+
+    monkeypatch.setattr(F, "adam_step", fake_adam)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.field = torch.nn.Linear(5, 3)
+            self.proposal_networks = torch.nn.Linear(4, 2)
+
+        def get_param_groups(self):
+            return {"proposal_networks": list(self.proposal_networks.parameters()), "fields": list(self.field.parameters())}
+
+    torch.manual_seed(0)
+    m = M()
+    opt = FlatAdam(m, lr=1e-2)
+    assert [s[0] for s in opt.segments] == ["fields", "proposal_networks"] and opt.segment_of("proposal_networks")[1] == opt.flat.numel()
+    ref = [p.detach().clone().requires_grad_(True) for p in m.parameters()]
+    ref_opt = {"fields": torch.optim.Adam(ref[:2], lr=1e-2, eps=1e-15), "proposal_networks": torch.optim.Adam(ref[2:], lr=1e-2, eps=1e-15)}
+    for step, active in enumerate([None, ["fields"], ["fields"], None]):
+        opt.zero_grad()
+        gs = [torch.randn_like(p) for p in ref]
+        for p, r, gr in zip(m.parameters(), ref, gs):
+            is_prop = any(p is q for q in m.proposal_networks.parameters())
+            live = active is None or not is_prop
+            p.grad.copy_(gr if live else torch.zeros_like(gr))
+            r.grad = gr.clone() if live else None
+        calls.clear()
+        opt.step(active=active)
+        for name, o in ref_opt.items():
+            if active is None or name in active:
+                o.step()
+        assert len(calls) == (1 if step == 0 else (1 if active else 2)), calls  # equal counters share one launch
+        for p, r in zip(m.parameters(), ref):
+            assert torch.allclose(p, r, atol=1e-7), step
+    assert opt.group_steps == {"fields": 4, "proposal_networks": 2}

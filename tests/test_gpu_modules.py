@@ -204,6 +204,62 @@ def test_full_nerfacto_pipeline_train_and_eval(cuda, golden):
                 assert_grad_close(gr, g["g_" + k], "g_" + k, 5e-3, sparse_switching=k.startswith("p") or "table" in k)
 
 
+def test_nerfacto_pipeline_staged_levels(cuda, golden):
+    """The composed hot path held to the per-operator bar: every level is fed the REFERENCE's recorded samples
+    (`train_sbins{i}` / `train_ebins{i}`), so each stage sees the inputs the reference saw and the stacked resampling
+    cannot amplify 1e-7 differences.  Weights of all three levels, rendered outputs, all three losses and EVERY parameter
+    gradient (entry-wise, no direction/norm escape) at 1e-4; the two PDF resampling steps reproduce the recorded
+    searchsorted indices exactly; the median-depth sample is the reference's on every ray."""
+    from nerfstudio_b200 import functional as F
+    from nerfstudio_b200.field_components.field_heads import FieldHeadNames
+    from nerfstudio_b200.model_components.losses import distortion_loss, interlevel_loss
+
+    g = golden("nerfacto_pipeline")
+    model = _pipeline_model(g).train()
+    rb = model.collider(_bundle(g["origins"], g["directions"], g["train_cams"]))
+    nets = list(model.proposal_networks) + [model.field]
+    weights_list, samples_list, field_out = [], [], None
+    for i in range(3):
+        rs = rb.samples_from_bins(cu(g[f"train_ebins{i}"]), cu(g[f"train_sbins{i}"]), None)
+        if i < 2:
+            density, _ = nets[i].get_density(rs)
+        else:
+            field_out = model.field.forward(rs)
+            density = field_out[FieldHeadNames.DENSITY]
+        w = rs.get_weights(density)
+        assert_close(w, g[f"train_w{i}"], REL, f"staged w{i}")
+        weights_list.append(w), samples_list.append(rs)
+    # the resampling steps on the reference's own (annealed) weights: indices bit-exact, bins to fp32 round-off
+    for i in range(2):
+        S_next = g[f"train_sbins{i + 1}"].shape[1] - 1
+        wa = torch.pow(g[f"train_w{i}"][..., 0], 0.7)  # ray_samplers.py:601 on the reference's device (CPU golden)
+        nsb, neb, cdf, inds = F.pdf_sample(cu(g[f"train_sbins{i}"]), cu(wa), S_next, cu(g[f"train_rand{i + 1}"]),
+                                           rb.nears, rb.fars, "piecewise", want_aux=True)
+        assert torch.equal(inds.cpu(), g[f"train_inds{i}"]), f"level {i}: searchsorted indices differ from the reference"
+        assert torch.equal(nsb.cpu(), g[f"train_sbins{i + 1}"]) and torch.equal(neb.cpu(), g[f"train_ebins{i + 1}"]), i
+    rgb = model.renderer_rgb(rgb=field_out[FieldHeadNames.RGB], weights=weights_list[2])
+    acc = model.renderer_accumulation(weights=weights_list[2])
+    exp_depth = model.renderer_expected_depth(weights=weights_list[2], ray_samples=samples_list[2])
+    with torch.no_grad():
+        med = model.renderer_depth(weights=weights_list[2], ray_samples=samples_list[2])
+    assert_close(rgb, g["train_rgb"], REL), assert_close(acc, g["train_acc"], REL)
+    assert_close(exp_depth, g["train_exp_depth"], REL)
+    assert torch.equal(med.cpu(), g["train_depth"]), "median depth must select the reference's sample on every ray"
+    pred, gt = model.renderer_rgb.blend_background_for_loss_computation(pred_image=rgb, pred_accumulation=acc,
+                                                                        gt_image=cu(g["gt"]))
+    l_rgb = model.rgb_loss(gt, pred)
+    l_inter = model.config.interlevel_loss_mult * interlevel_loss(weights_list, samples_list)
+    l_dist = model.config.distortion_loss_mult * distortion_loss(weights_list, samples_list)
+    assert_close(l_rgb, g["loss_rgb"], REL), assert_close(l_inter, g["loss_interlevel"], REL)
+    assert_close(l_dist, g["loss_distortion"], REL)
+    loss = l_rgb + l_inter + l_dist
+    assert_close(loss, g["loss"], REL)
+    named = _named_params(model)
+    grads = torch.autograd.grad(loss, list(named.values()))
+    for k, gr in zip(named, grads):
+        assert_close(gr, g["g_" + k], REL, "staged g_" + k)
+
+
 def test_trainer_step_matches_torch_adam(cuda, golden):
     """One Trainer.train_iteration == the same forward/backward followed by torch.optim.Adam on a deep copy."""
     import copy

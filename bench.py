@@ -160,6 +160,61 @@ def oracle_step_factory(n_rays: int, seed: int = 0):
     return step
 
 
+def reference_step_factory(n_rays: int, seed: int = 0):
+    """The REFERENCE ITSELF on the host cores: the unmodified `nerfstudio.models.nerfacto.NerfactoModel` (torch
+    implementation, its own samplers / fields / renderers / losses, torch.optim.Adam as configs/method_configs.py:106-113
+    configures it) imported from /root/reference or oracle/_ref (oracle/make_ref.py).  None when it is not importable."""
+    from oracle import ref_loader
+
+    if ref_loader.load() is None:
+        return None
+    import nerfstudio.models.nerfacto as NM
+    from nerfstudio.cameras.rays import RayBundle
+    from nerfstudio.data.scene_box import SceneBox
+    from nerfstudio_b200.scene import synthetic_rays
+
+    torch.manual_seed(seed)
+    cfg = NM.NerfactoModelConfig(implementation="torch", average_init_density=0.01)
+    cfg.camera_optimizer.mode = "off"
+    model = NM.NerfactoModel(cfg, scene_box=SceneBox(aabb=torch.tensor([[-1.0, -1, -1], [1, 1, 1]])),
+                             num_train_data=NUM_IMAGES).train()
+    model.proposal_sampler.update_sched = lambda step: -1  # proposal networks trained every step, as the GPU arm does
+    groups = model.get_param_groups()
+    opts = [torch.optim.Adam(groups[k], lr=1e-2, eps=1e-15) for k in ("proposal_networks", "fields")]
+    rays, gt = synthetic_rays(n_rays, NUM_IMAGES, seed)
+    counter = {"step": 0}
+
+    def step():
+        rb = RayBundle(origins=rays["origins"], directions=rays["directions"], pixel_area=rays["pixel_area"],
+                       camera_indices=rays["camera_indices"])
+        for o in opts:
+            o.zero_grad(set_to_none=True)
+        out = model(rb)
+        batch = {"image": gt}
+        md = model.get_metrics_dict(out, batch)
+        loss = sum(model.get_loss_dict(out, batch, md).values())
+        loss.backward()
+        for o in opts:
+            o.step()
+        model.proposal_sampler.step_cb(counter["step"])
+        counter["step"] += 1
+        return float(loss.detach())
+
+    return step
+
+
+def cpu_step_factory(n_rays: int):
+    """(step fn, kind): the reference itself when importable, else the oracle's restatement of it."""
+    try:
+        step = reference_step_factory(n_rays)
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"[bench] reference not runnable ({type(e).__name__}: {e}); using the oracle port\n")
+        step = None
+    if step is not None:
+        return step, "reference"
+    return oracle_step_factory(n_rays), "port"
+
+
 def pick_cpu_threads():
     """The thread count at which the CPU port runs fastest on this host (torch's intra-op parallelism stops scaling —
     and on a 128-thread box reverses — well before all hardware threads are used): one 256-ray step per candidate."""
@@ -167,7 +222,7 @@ def pick_cpu_threads():
     best = (0.0, 1)
     for c in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
         torch.set_num_threads(c)
-        step = oracle_step_factory(256)
+        step, _ = cpu_step_factory(256)
         step()
         t0 = time.perf_counter()
         step()
@@ -179,14 +234,14 @@ def pick_cpu_threads():
 
 def time_cpu(n_rays: int, steps: int, warmup: int, threads: int):
     torch.set_num_threads(threads)
-    step = oracle_step_factory(n_rays)
+    step, kind = cpu_step_factory(n_rays)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return n_rays * steps / dt, dt / steps, threads
+    return n_rays * steps / dt, dt / steps, threads, kind
 
 
 def run_reference(args) -> None:
@@ -200,14 +255,16 @@ def run_reference(args) -> None:
     # bounded sample of the same workload (multiple of 64 rays, at least 64)
     budget_rays = rps_est * 150.0 / max(args.steps + args.warmup, 1)
     n_rays = int(min(RAYS_PER_GPU, max(64, (int(budget_rays) // 64) * 64)))
-    rps, sec, cores = time_cpu(n_rays, args.steps, args.warmup, threads)
+    rps, sec, cores, kind = time_cpu(n_rays, args.steps, args.warmup, threads)
+    what = ("the unmodified reference NerfactoModel (torch path, torch.optim.Adam)" if kind == "reference"
+            else "oracle port of the reference's torch path")
     line = {
         "impl": "reference", "metric": METRIC, "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": f"{n_rays} rays/step of the 4096-ray batch (CPU bounded sample)"},
-        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps x {n_rays} rays, fwd+bwd+Adam, torch CPU fp32, {cores} threads "
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} steps x {n_rays} rays, fwd+bwd+Adam, {what}, torch CPU fp32, {cores} threads "
                                    f"(fastest of 8/16/32/64/{os.cpu_count()} on this host)"},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -600,9 +657,10 @@ def run_ngp(args) -> None:
 
 def cpu_baseline_sample():
     threads, _ = pick_cpu_threads()
-    rps, sec, cores = time_cpu(512, 3, 1, threads)
-    return {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"3 steps x 512 rays of the same workload (fwd+bwd+Adam), torch CPU fp32, {cores} threads"}
+    rps, sec, cores, kind = time_cpu(512, 3, 1, threads)
+    return {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind,
+            "sample": f"3 steps x 512 rays of the same workload (fwd+bwd+Adam; {'the unmodified reference model' if kind == 'reference' else 'oracle port'}), "
+                      f"torch CPU fp32, {cores} threads"}
 
 
 def main() -> None:

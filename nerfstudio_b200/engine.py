@@ -159,6 +159,7 @@ class NerfactoStep:
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._steps_since_update = 0
         self.fixed_jitter = None
+        self.fixed_bins = None  # tests: [(spacing bins, euclidean bins)] per level replacing the samplers' outputs
         if self.bg not in ("last_sample", "white", "black"):
             raise NotImplementedError("captured step: background_color must be last_sample / white / black")
 
@@ -235,11 +236,15 @@ class NerfactoStep:
         # ---------------- forward: proposal sampling
         call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), ptr(self.jitter[0]), 0, R, S0,
              lib.SPACING[self.spacing], ptr(self.sb[0]), ptr(self.eb[0]), st())
+        if self.fixed_bins is not None:
+            self.sb[0].copy_(self.fixed_bins[0][0]), self.eb[0].copy_(self.fixed_bins[0][1])
         for lvl in (0, 1):
             self._density_net_fwd(lvl, self.props[lvl])
             call("b2n_pdf_sample", ptr(self.sb[lvl]), ptr(self.w[lvl]), ptr(self.u_base[lvl]), ptr(self.jitter[lvl + 1]), 0,
                  ptr(self.nears), ptr(self.fars), R, self.S[lvl], self.S[lvl + 1] + 1, 1.0, _off(self.hyper, 3), 0.01, 1e-5,
                  lib.SPACING[self.spacing], ptr(self.sb[lvl + 1]), ptr(self.eb[lvl + 1]), NULL, NULL, st())
+            if self.fixed_bins is not None:  # staged parity tests: every level sees the reference's recorded samples
+                self.sb[lvl + 1].copy_(self.fixed_bins[lvl + 1][0]), self.eb[lvl + 1].copy_(self.fixed_bins[lvl + 1][1])
         # ---------------- forward: main field
         N2 = R * S2
         eb2 = self.eb[2]

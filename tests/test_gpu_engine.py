@@ -53,6 +53,72 @@ def test_engine_step_equals_reference_losses_and_grads(cuda, golden):
     assert_close(eng.acc[:, None], g["train_acc"], 1e-4)
 
 
+def test_engine_staged_levels_entrywise(cuda, golden):
+    """The hand-written backward held to the 1e-4 bar entry by entry: with every level fed the reference's recorded
+    samples (`train_sbins{i}` / `train_ebins{i}`) the captured step computes exactly the reference's graph, so weights,
+    all losses and every parameter gradient — hash tables and proposal networks included — must agree at 1e-4 of the
+    max-norm, no direction/norm comparison."""
+    from test_gpu_modules import _named_params
+
+    g = golden("nerfacto_pipeline")
+    model, eng = _mk(g, use_graph=False)
+    eng._anneal = lambda step: 0.7
+    eng.optim.lr = 0.0
+    eng.fixed_bins = [(g[f"train_sbins{i}"].cuda(), g[f"train_ebins{i}"].cuda()) for i in range(3)]
+    losses = eng.step().cpu()
+    for i in range(3):
+        assert_close(eng.w[i], g[f"train_w{i}"][..., 0], 1e-4, f"w{i}")
+    assert_close(losses[0], g["loss_rgb"], 1e-4), assert_close(losses[1], g["loss_interlevel"], 1e-4)
+    assert_close(losses[2], g["loss_distortion"], 1e-4), assert_close(losses[3], g["loss"], 1e-4)
+    assert_close(eng.rgb_out, g["train_rgb"], 1e-4), assert_close(eng.depth_exp[:, None], g["train_exp_depth"], 1e-4)
+    assert torch.equal(eng.depth_med.cpu()[:, None], g["train_depth"]), "median depth sample"
+    for k, p in _named_params(model).items():
+        assert_close(p.grad, g["g_" + k], 1e-4, "staged g_" + k)
+
+
+def test_frozen_proposal_networks_are_not_stepped(cuda, golden):
+    """Reference schedule: after step 10 the proposal networks are trained only every few steps; on the other steps
+    their gradients are None in the reference and Optimizers.optimizer_scaler_step_all skips the group
+    (engine/optimizers.py:142-159) — parameters and Adam moments stay bit-identical, and the group's bias-correction count
+    does not advance.  Checked for the captured step (eager and graph) and for the autograd Trainer."""
+    from nerfstudio_b200.nerfacto import Trainer
+
+    g = golden("nerfacto_pipeline")
+    for use_graph in (False, True):
+        model, eng = _mk(g, use_graph=use_graph, always=False)
+        model.proposal_sampler.update_sched = lambda step: 3  # update when 4+ steps have passed (or step < 10)
+        eng.fixed_jitter = None
+        a, b = eng.optim.segment_of("proposal_networks")
+        frozen_seen = 0
+        for it in range(16):
+            due = eng._update_due(it)
+            before = [t[a:b].clone() for t in (eng.optim.flat, eng.optim.exp_avg, eng.optim.exp_avg_sq)]
+            f_before = eng.optim.flat[:a].clone()
+            eng.step()
+            torch.cuda.synchronize()
+            after = [t[a:b] for t in (eng.optim.flat, eng.optim.exp_avg, eng.optim.exp_avg_sq)]
+            if due:
+                assert not torch.equal(before[0], after[0]), it
+            else:
+                frozen_seen += 1
+                assert all(torch.equal(x, y) for x, y in zip(before, after)), f"step {it}: frozen proposals moved"
+            assert not torch.equal(f_before, eng.optim.flat[:a]), it  # the field trains every step
+        assert frozen_seen >= 3 and eng.optim.group_steps["proposal_networks"] == 16 - frozen_seen
+        assert eng.optim.group_steps["fields"] == 16
+    model = _pipeline_model(g).train()
+    model.proposal_sampler.update_sched = lambda step: 3
+    tr = Trainer(model)
+    a, b = tr.optim.segment_of("proposal_networks")
+    frozen_seen = 0
+    for it in range(14):
+        before = tr.optim.flat[a:b].clone()
+        tr.train_iteration(_bundle(g["origins"], g["directions"], g["train_cams"]), {"image": g["gt"].cuda()})
+        if not model.proposal_sampler.last_updated:
+            frozen_seen += 1
+            assert torch.equal(before, tr.optim.flat[a:b]), it
+    assert frozen_seen >= 2
+
+
 def test_engine_matches_autograd_trainer_over_steps(cuda, golden):
     from nerfstudio_b200.nerfacto import Trainer
     from test_gpu_modules import FakeRand

@@ -215,6 +215,15 @@ int b2n_distortion_fwd_bwd(const float* t, const float* w, int64_t n_rays, int32
 int b2n_raygen(const float* c2w, const float* intr, const float* dist, const int64_t* ray_indices, int64_t n_rays,
                float* origins, float* directions, float* pixel_area, float* directions_norm, int64_t* camera_indices,
                void* stream);
+/* Cameras.generate_rays(camera_indices, coords, camera_opt_to_camera, distortion_params_delta, keep_shape)
+ * (cameras/cameras.py:321-503) for perspective cameras.  coords != NULL: ray i = camera cam_idx[i], pixel-centre
+ * coords[i] = (y, x) float.  coords == NULL: the whole images of the n_cams listed cameras, rays laid out
+ * [height, width, n_cams] (camera fastest — the reference's (h, w, num_rays) shape), n_rays = n_cams*height*width.
+ * cam_opt [n,3,4] / dist_delta [n,6] optional, n = n_rays (coords given) or n_cams (whole images). */
+int b2n_raygen_coords(const float* c2w, const float* intr, const float* dist, const int64_t* cam_idx,
+                      const float* coords, int64_t n_rays, int32_t n_cams, int32_t height, int32_t width,
+                      const float* cam_opt, const float* dist_delta, float* origins, float* directions,
+                      float* pixel_area, float* directions_norm, int64_t* camera_indices, void* stream);
 /* AABBBoxCollider (model_components/scene_colliders.py:47-108). */
 int b2n_aabb_collide(const float* origins, const float* directions, const float* aabb_host6, float near_plane,
                      int64_t n_rays, float* nears, float* fars, void* stream);

@@ -100,8 +100,20 @@ class RayBundle:
                        camera_indices=ix(self.camera_indices), nears=ix(self.nears), fars=ix(self.fars),
                        metadata={k: ix(v) for k, v in self.metadata.items()}, times=ix(self.times))
 
+    def reshape(self, shape) -> "RayBundle":
+        """Batch dims -> `shape` (utils/tensor_dataclass.py:reshape): trailing feature dims are kept."""
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        rs = lambda t: None if t is None else t.reshape(shape + t.shape[len(self.shape):])
+        return replace(self, origins=rs(self.origins), directions=rs(self.directions), pixel_area=rs(self.pixel_area),
+                       camera_indices=rs(self.camera_indices), nears=rs(self.nears), fars=rs(self.fars),
+                       metadata={k: rs(v) for k, v in self.metadata.items()}, times=rs(self.times))
+
+    def flatten(self) -> "RayBundle":
+        return self.reshape((-1,))
+
     def get_row_major_sliced_ray_bundle(self, start_idx: int, end_idx: int) -> "RayBundle":
-        return self[start_idx:end_idx]
+        """cameras/rays.py:235-249: rays [start, end) of the flattened (row-major) bundle."""
+        return self.flatten()[start_idx:end_idx]
 
     def get_ray_samples(self, bin_starts: Tensor, bin_ends: Tensor, spacing_starts: Optional[Tensor] = None,
                         spacing_ends: Optional[Tensor] = None,

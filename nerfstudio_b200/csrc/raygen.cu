@@ -27,32 +27,51 @@ __device__ __forceinline__ void undistort(float& x, float& y, const float* k) {
   }
 }
 
-__global__ void raygen_kernel(const float* __restrict__ c2w, const float* __restrict__ intr,
-                              const float* __restrict__ dist, int any_dist, const int64_t* __restrict__ ray_indices,
-                              int64_t n_rays, float* __restrict__ origins, float* __restrict__ directions,
-                              float* __restrict__ pixel_area, float* __restrict__ directions_norm,
-                              int64_t* __restrict__ camera_indices) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rays) return;
-  const int64_t cam = ray_indices[3 * i];
-  const float py = (float)ray_indices[3 * i + 1] + 0.5f, px = (float)ray_indices[3 * i + 2] + 0.5f;
+// One ray: pixel-centre coordinates (px, py) of camera `cam` -> origin, unit direction, pixel area, direction norm.
+// cam_opt (optional, 12 floats): camera_opt_to_camera, composed as pose_utils.multiply(c2w, opt) (cameras.py:884-885).
+__device__ __forceinline__ void ray_from_pixel(const float* __restrict__ c2w, const float* __restrict__ intr,
+                                               const float* __restrict__ dist, const float* __restrict__ dist_delta,
+                                               const float* __restrict__ cam_opt, int64_t cam, float px, float py, float* o,
+                                               float* dir, float* area, float* nrm_out) {
   const float fx = __ldg(intr + 4 * cam), fy = __ldg(intr + 4 * cam + 1), cx = __ldg(intr + 4 * cam + 2), cy = __ldg(intr + 4 * cam + 3);
   float ux[3], uy[3];
   ux[0] = div_rn(sub_rn(px, cx), fx), uy[0] = div_rn(sub_rn(py, cy), fy);
   ux[1] = div_rn(add_rn(sub_rn(px, cx), 1.f), fx), uy[1] = uy[0];
   ux[2] = ux[0], uy[2] = div_rn(add_rn(sub_rn(py, cy), 1.f), fy);
-  if (any_dist) {
+  if (dist != nullptr || dist_delta != nullptr) {
     float k[6];
+    bool any = false;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) k[j] = __ldg(dist + 6 * cam + j);
+    for (int j = 0; j < 6; ++j) {
+      k[j] = (dist ? __ldg(dist + 6 * cam + j) : 0.f) + (dist_delta ? __ldg(dist_delta + j) : 0.f);
+      any |= k[j] != 0.f;
+    }
+    if (any) {
 #pragma unroll
-    for (int v = 0; v < 3; ++v) undistort(ux[v], uy[v], k);
+      for (int v = 0; v < 3; ++v) undistort(ux[v], uy[v], k);
+    }
   }
-  float R[9];
+  float R[9], t[3];
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int a = 0; a < 3; ++a) {
 #pragma unroll
     for (int b = 0; b < 3; ++b) R[a * 3 + b] = __ldg(c2w + cam * 12 + a * 4 + b);
+    t[a] = __ldg(c2w + cam * 12 + a * 4 + 3);
+  }
+  if (cam_opt != nullptr) {  // R <- R * R_opt, t <- t + R * t_opt
+    float R2[9], t2[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        R2[a * 3 + b] = R[a * 3] * __ldg(cam_opt + b) + R[a * 3 + 1] * __ldg(cam_opt + 4 + b) + R[a * 3 + 2] * __ldg(cam_opt + 8 + b);
+      t2[a] = t[a] + (R[a * 3] * __ldg(cam_opt + 3) + R[a * 3 + 1] * __ldg(cam_opt + 7) + R[a * 3 + 2] * __ldg(cam_opt + 11));
+    }
+#pragma unroll
+    for (int a = 0; a < 9; ++a) R[a] = R2[a];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) t[a] = t2[a];
+  }
   float d[3][3];
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
@@ -64,7 +83,7 @@ __global__ void raygen_kernel(const float* __restrict__ c2w, const float* __rest
     nrm = fmaxf(nrm, 8.881784197001252e-16f);
 #pragma unroll
     for (int a = 0; a < 3; ++a) d[v][a] = div_rn(w[a], nrm);
-    if (v == 0 && directions_norm) directions_norm[i] = nrm;
+    if (v == 0) *nrm_out = nrm;
   }
   float sx = 0.f, sy = 0.f;
 #pragma unroll
@@ -73,11 +92,25 @@ __global__ void raygen_kernel(const float* __restrict__ c2w, const float* __rest
     sx += ex * ex, sy += ey * ey;
   }
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    origins[3 * i + a] = __ldg(c2w + cam * 12 + a * 4 + 3);
-    directions[3 * i + a] = d[0][a];
-  }
-  if (pixel_area) pixel_area[i] = mul_rn(__fsqrt_rn(sx), __fsqrt_rn(sy));
+  for (int a = 0; a < 3; ++a) o[a] = t[a], dir[a] = d[0][a];
+  *area = mul_rn(__fsqrt_rn(sx), __fsqrt_rn(sy));
+}
+
+__global__ void raygen_kernel(const float* __restrict__ c2w, const float* __restrict__ intr,
+                              const float* __restrict__ dist, int any_dist, const int64_t* __restrict__ ray_indices,
+                              int64_t n_rays, float* __restrict__ origins, float* __restrict__ directions,
+                              float* __restrict__ pixel_area, float* __restrict__ directions_norm,
+                              int64_t* __restrict__ camera_indices) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays) return;
+  const int64_t cam = ray_indices[3 * i];
+  const float py = (float)ray_indices[3 * i + 1] + 0.5f, px = (float)ray_indices[3 * i + 2] + 0.5f;
+  float o[3], d[3], area, nrm;
+  ray_from_pixel(c2w, intr, any_dist ? dist : nullptr, nullptr, nullptr, cam, px, py, o, d, &area, &nrm);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) origins[3 * i + a] = o[a], directions[3 * i + a] = d[a];
+  if (pixel_area) pixel_area[i] = area;
+  if (directions_norm) directions_norm[i] = nrm;
   if (camera_indices) camera_indices[i] = cam;
 }
 
@@ -89,6 +122,54 @@ extern "C" int b2n_raygen(const float* c2w, const float* intr, const float* dist
   if (n_rays == 0) return B2N_OK;
   raygen_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
       c2w, intr, dist, dist != nullptr, ray_indices, n_rays, origins, directions, pixel_area, directions_norm, camera_indices);
+  B2N_LAUNCH_CHECK();
+}
+
+// Cameras.generate_rays(camera_indices, coords, camera_opt_to_camera, distortion_params_delta, keep_shape, ...)
+// (cameras/cameras.py:321-503).  coords != NULL: ray i uses camera cam_idx[i] and pixel-centre coords[i] = (y, x).
+// coords == NULL: whole images — rays laid out (height, width, n_cams) with the camera index fastest, which is the
+// reference's (h, w, num_rays) shape for coords=None; pixel centres row + 0.5 / col + 0.5 (get_image_coords).
+// cam_opt / dist_delta: per ray (coords given) or per listed camera (whole images).
+__global__ void raygen_coords_kernel(const float* __restrict__ c2w, const float* __restrict__ intr,
+                                     const float* __restrict__ dist, const int64_t* __restrict__ cam_idx,
+                                     const float* __restrict__ coords, int64_t n_rays, int n_cams, int width,
+                                     const float* __restrict__ cam_opt, const float* __restrict__ dist_delta,
+                                     float* __restrict__ origins, float* __restrict__ directions,
+                                     float* __restrict__ pixel_area, float* __restrict__ directions_norm,
+                                     int64_t* __restrict__ camera_indices) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays) return;
+  int64_t cam, sel;
+  float px, py;
+  if (coords != nullptr) {
+    sel = i, cam = cam_idx[i];
+    py = __ldg(coords + 2 * i), px = __ldg(coords + 2 * i + 1);
+  } else {
+    sel = i % n_cams, cam = cam_idx[sel];
+    const int64_t pix = i / n_cams;
+    py = (float)(pix / width) + 0.5f, px = (float)(pix % width) + 0.5f;
+  }
+  float o[3], d[3], area, nrm;
+  ray_from_pixel(c2w, intr, dist, dist_delta ? dist_delta + 6 * sel : nullptr, cam_opt ? cam_opt + 12 * sel : nullptr, cam, px,
+                 py, o, d, &area, &nrm);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) origins[3 * i + a] = o[a], directions[3 * i + a] = d[a];
+  if (pixel_area) pixel_area[i] = area;
+  if (directions_norm) directions_norm[i] = nrm;
+  if (camera_indices) camera_indices[i] = cam;
+}
+
+extern "C" int b2n_raygen_coords(const float* c2w, const float* intr, const float* dist, const int64_t* cam_idx,
+                                 const float* coords, int64_t n_rays, int32_t n_cams, int32_t height, int32_t width,
+                                 const float* cam_opt, const float* dist_delta, float* origins, float* directions,
+                                 float* pixel_area, float* directions_norm, int64_t* camera_indices, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(c2w && intr && cam_idx && origins && directions, "null pointer");
+  B2N_REQUIRE(coords != nullptr || (n_cams >= 1 && height >= 1 && width >= 1 && n_rays == (int64_t)n_cams * height * width),
+              "whole-image mode needs n_rays == n_cams * height * width");
+  raygen_coords_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+      c2w, intr, dist, cam_idx, coords, n_rays, n_cams, width, cam_opt, dist_delta, origins, directions, pixel_area,
+      directions_norm, camera_indices);
   B2N_LAUNCH_CHECK();
 }
 

@@ -713,6 +713,32 @@ def generate_rays(c2w: Tensor, intrinsics: Tensor, distortion: Optional[Tensor],
     return dict(origins=o, directions=d, pixel_area=area, directions_norm=nrm, camera_indices=cam)
 
 
+def generate_rays_coords(c2w: Tensor, intrinsics: Tensor, distortion: Optional[Tensor], cam_idx: Tensor,
+                         coords: Optional[Tensor], height: int = 0, width: int = 0, cam_opt: Optional[Tensor] = None,
+                         dist_delta: Optional[Tensor] = None):
+    """Cameras.generate_rays on flattened arguments.  coords [R,2]=(y,x) with cam_idx [R]; or coords None for the whole
+    images of cam_idx [K] -> R = height*width*K rays laid out [height, width, K]."""
+    c2w, intr, ci = _c(c2w.float()), _c(intrinsics.float()), _c(cam_idx.long().reshape(-1))
+    dist = _c(distortion.float()) if distortion is not None else None
+    K = ci.shape[0]
+    if coords is not None:
+        coords = _c(coords.float().reshape(-1, 2))
+        R = coords.shape[0]
+        if K != R:
+            raise ValueError("camera_indices and coords must have the same number of rays")
+    else:
+        R = K * height * width
+    f = lambda t, w: None if t is None else _c(t.float().reshape(-1, w))
+    opt, dd = f(cam_opt, 12), f(dist_delta, 6)
+    dev = c2w.device
+    o, d = torch.empty(R, 3, device=dev), torch.empty(R, 3, device=dev)
+    area, nrm = torch.empty(R, 1, device=dev), torch.empty(R, 1, device=dev)
+    cam = torch.empty(R, 1, device=dev, dtype=torch.int64)
+    call("b2n_raygen_coords", ptr(c2w), ptr(intr), ptr(dist), ptr(ci, torch.int64), ptr(coords), R, K, int(height), int(width),
+         ptr(opt), ptr(dd), ptr(o), ptr(d), ptr(area), ptr(nrm), ptr(cam, torch.int64), stream())
+    return dict(origins=o, directions=d, pixel_area=area, directions_norm=nrm, camera_indices=cam)
+
+
 def aabb_collide(origins: Tensor, directions: Tensor, aabb: Sequence[float], near_plane: float):
     o, d = _c(origins.float()), _c(directions.float())
     R = o.shape[0]

@@ -16,7 +16,13 @@ What `install()` does (each step is the binding a nerfstudio maintainer would ot
    HashMLPDensityField, the samplers, RGB / accumulation / depth renderers, interlevel / distortion losses;
 3. patches `RaySamples.get_weights` (cameras/rays.py:129-152) to the warp-scan kernel;
 4. patches `CameraOptimizer.apply_to_raybundle` (cameras/camera_optimizers.py:148-153) to the fused SO3xR3 kernel
-   (the module, its `pose_adjustment` parameter and every other method stay the reference's).
+   (the module, its `pose_adjustment` parameter and every other method stay the reference's);
+5. patches `Cameras.generate_rays` (cameras/cameras.py:321-503) to the ray-generation kernel for perspective cameras on
+   the GPU — same signature (camera_indices, coords, camera_opt_to_camera, distortion_params_delta, keep_shape,
+   disable_distortion, aabb_box), the reference's own code for every other camera model.
+
+`install_fused_trainer(trainer)` additionally routes a reference `Trainer`'s `train_iteration` through the captured
+step (`pipeline.FusedTrainStep`) when its model is a nerfacto model.
 
 Everything replaced keeps the reference's constructor signature, attributes and state_dict keys, so configs and
 checkpoints are untouched.  `uninstall()` restores the originals.
@@ -121,6 +127,29 @@ def install(shim_third_party: bool = True, patch_get_weights: bool = True) -> Li
 
     _set(cam_opt.CameraOptimizer, "apply_to_raybundle", apply_to_raybundle)
     done.append("nerfstudio.cameras.camera_optimizers.CameraOptimizer.apply_to_raybundle")
+    # 5. Cameras.generate_rays (cameras/cameras.py:321-503): perspective cameras on the GPU -> one ray-generation kernel
+    #    behind the reference's own signature (training batches with coords, whole images with keep_shape); every other
+    #    camera model, multi-dimensional camera batches, oriented boxes and CPU cameras keep the reference's code
+    cams_mod = importlib.import_module("nerfstudio.cameras.cameras")
+    rays_mod = importlib.import_module("nerfstudio.cameras.rays")
+    from .cameras.cameras import fused_generate_rays
+
+    original_generate = cams_mod.Cameras.generate_rays
+
+    def generate_rays(self, camera_indices, coords=None, camera_opt_to_camera=None, distortion_params_delta=None,
+                      keep_shape=None, disable_distortion=False, aabb_box=None, obb_box=None):
+        cams = self if self.shape else self.reshape((1,))
+        out = None
+        if cams.camera_to_worlds.is_cuda and len(cams.shape) == 1 and obb_box is None:
+            out = fused_generate_rays(cams, camera_indices, coords, camera_opt_to_camera, distortion_params_delta, keep_shape,
+                                      disable_distortion, aabb_box, None, bundle_cls=rays_mod.RayBundle)
+        if out is None:
+            return original_generate(self, camera_indices, coords, camera_opt_to_camera, distortion_params_delta,
+                                     keep_shape, disable_distortion, aabb_box, obb_box)
+        return out
+
+    _set(cams_mod.Cameras, "generate_rays", generate_rays)
+    done.append("nerfstudio.cameras.cameras.Cameras.generate_rays")
     return done
 
 
@@ -138,3 +167,28 @@ def uninstall() -> None:
         mod = sys.modules.get(name)
         if mod is not None and getattr(mod, "__name__", "").startswith("nerfstudio_b200.shims"):
             del sys.modules[name]
+
+
+def install_fused_trainer(trainer, **engine_kwargs):
+    """Bind the captured step to a reference `Trainer` (engine/trainer.py): `trainer.train_iteration(step)` keeps its
+    signature and return tuple `(loss, loss_dict, metrics_dict)` but runs forward + losses + backward + optimiser as one
+    CUDA-graph replay; rays still come from `trainer.pipeline.datamanager.next_train(step)`.  The optimiser settings are
+    read from the trainer's own config (Adam lr / eps of the "fields" group, configs/method_configs.py:106-119).
+    Returns the `FusedTrainStep`; `trainer._b200_original_train_iteration` keeps the reference method."""
+    from .pipeline import FusedTrainStep
+
+    pipeline = trainer.pipeline
+    model = getattr(pipeline, "model", None) or pipeline._model
+    dm = pipeline.datamanager
+    n_rays = int(getattr(getattr(dm, "config", None), "train_num_rays_per_batch", 4096))
+    lr, eps = 1e-2, 1e-15
+    try:
+        oc = trainer.config.optimizers["fields"]["optimizer"]
+        lr, eps = float(oc.lr), float(oc.eps)
+    except Exception:  # noqa: BLE001
+        pass
+    fused = FusedTrainStep(model, dm, n_rays, lr=lr, eps=eps, **engine_kwargs)
+    trainer._b200_original_train_iteration = trainer.train_iteration
+    trainer.train_iteration = fused.train_iteration
+    pipeline.get_train_loss_dict = fused.get_train_loss_dict
+    return fused

@@ -293,6 +293,45 @@ def test_raygen_golden(F, golden):
         assert torch.equal(r["camera_indices"].cpu(), g[f"{nm}_camera_indices"])
 
 
+def test_cameras_generate_rays_reference_signature(F, golden):
+    """Cameras.generate_rays(camera_indices, coords, ..., keep_shape, aabb_box) on the kernel: training-batch form vs the
+    golden rays; whole-image form ([H, W] and [H, W, n]) consistent with the per-pixel form bit for bit."""
+    from nerfstudio_b200.cameras.cameras import Cameras
+
+    g = golden("raygen")
+    for nm, dist in (("nodist", None), ("dist", g["dist"])):
+        cams = Cameras(cu(g["c2w"]), cu(g["fx"]), cu(g["fy"]), cu(g["cx"]), cu(g["cy"]), width=cu(g["hw"][:, 1]),
+                       height=cu(g["hw"][:, 0]), distortion_params=None if dist is None else cu(dist))
+        ri = g[f"{nm}_ray_indices"]
+        coords = ri[:, 1:].float() + 0.5  # pixel centres, (y, x) — what get_image_coords / the pixel sampler produce
+        rb = cams.generate_rays(camera_indices=cu(ri[:, :1]), coords=cu(coords))
+        assert torch.equal(rb.origins.cpu(), g[f"{nm}_origins"])
+        assert_close(rb.directions, g[f"{nm}_directions"], TIGHT, nm)
+        assert_close(rb.pixel_area, g[f"{nm}_pixel_area"], REL, nm)
+        assert_close(rb.metadata["directions_norm"], g[f"{nm}_directions_norm"], TIGHT)
+        assert torch.equal(rb.camera_indices.cpu(), g[f"{nm}_camera_indices"])
+        ref = F.generate_rays(cu(g["c2w"]), cams.intrinsics(), None if dist is None else cu(dist), cu(ri))
+        assert torch.equal(rb.directions, ref["directions"]) and torch.equal(rb.pixel_area, ref["pixel_area"])
+    # whole images (coords=None): [H, W] for an int index, [H, W, n] for n listed cameras
+    H, W = 12, 20
+    cams = Cameras(cu(g["c2w"]), cu(g["fx"]), cu(g["fy"]), cu(g["cx"]), cu(g["cy"]), width=torch.full((5,), W).cuda(),
+                   height=torch.full((5,), H).cuda(), distortion_params=cu(g["dist"]))
+    img = cams.generate_rays(camera_indices=3, keep_shape=True)
+    assert tuple(img.shape) == (H, W) and img.origins.shape == (H, W, 3)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    ri = torch.stack([torch.full_like(yy, 3), yy, xx], -1).reshape(-1, 3)
+    per_px = F.generate_rays(cu(g["c2w"]), cams.intrinsics(), cu(g["dist"]), cu(ri))
+    assert torch.equal(img.directions.reshape(-1, 3), per_px["directions"])
+    assert torch.equal(img.pixel_area.reshape(-1, 1), per_px["pixel_area"])
+    multi = cams.generate_rays(camera_indices=torch.tensor([[3], [1]]).cuda())
+    assert tuple(multi.shape) == (H, W, 2) and torch.equal(multi.directions[:, :, 0], img.directions)
+    assert bool((multi.camera_indices[:, :, 1] == 1).all())
+    flat = cams.generate_rays(camera_indices=3, keep_shape=False, aabb_box=[-1.0, -1, -1, 1, 1, 1])
+    assert tuple(flat.shape) == (H * W,) and flat.nears.shape == (H * W, 1)
+    to, tx, ho = O.ray_aabb_intersect(flat.origins.cpu(), flat.directions.cpu(), torch.tensor([-1.0, -1, -1, 1, 1, 1]), 0.0, 1e10)
+    assert torch.equal(flat.nears.cpu()[ho][:, 0], to[ho]) and bool((flat.nears.cpu()[~ho] == 1e10).all())
+
+
 # ------------------------------------------------------------------------------------------------
 def test_packed_path_vs_oracle(F):
     torch.manual_seed(7)

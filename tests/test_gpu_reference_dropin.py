@@ -287,3 +287,54 @@ def test_psnr_parity_with_the_reference_torch_path(ref):
         integration.uninstall()
     assert psnr_ref > start + 8.0 and psnr_ours > start + 8.0, (start, psnr_ref, psnr_ours)
     assert abs(psnr_ours - psnr_ref) < 3.0, (start, psnr_ref, psnr_ours)
+
+
+def test_patched_cameras_generate_rays_equals_the_reference(ref, golden):
+    """install() patches nerfstudio.cameras.cameras.Cameras.generate_rays: same signature, same RayBundle class, same
+    rays as the reference's own torch code (run here on the CPU copy of the same Cameras object) for the training form
+    (coords), the whole-image forms, camera_opt_to_camera, distortion deltas, keep_shape=False and aabb_box."""
+    from nerfstudio_b200 import integration
+
+    from nerfstudio.cameras.cameras import Cameras, CameraType
+    from nerfstudio.cameras.rays import RayBundle
+    from nerfstudio.data.scene_box import SceneBox
+
+    g = golden("raygen")
+    H, W = 24, 32
+    kw = dict(camera_to_worlds=g["c2w"], fx=g["fx"], fy=g["fy"], cx=g["cx"], cy=g["cy"], width=W, height=H,
+              distortion_params=g["dist"], camera_type=CameraType.PERSPECTIVE)
+    cpu_cams = Cameras(**kw)
+    torch.manual_seed(21)
+    R = 300
+    ci = torch.randint(0, 5, (R, 1))
+    coords = torch.stack([torch.rand(R) * H, torch.rand(R) * W], -1)
+    opt = torch.eye(4)[:3][None].repeat(R, 1, 1) + 0.01 * torch.randn(R, 3, 4)
+    delta = 0.01 * torch.randn(R, 6)
+    box = SceneBox(aabb=torch.tensor([[-50.0, -50, -50], [50, 50, 50]]))  # cameras inside: every ray hits
+    cases = [dict(camera_indices=ci, coords=coords), dict(camera_indices=ci, coords=coords, camera_opt_to_camera=opt),
+             dict(camera_indices=ci, coords=coords, distortion_params_delta=delta),
+             dict(camera_indices=ci, coords=coords, disable_distortion=True), dict(camera_indices=2, keep_shape=True),
+             dict(camera_indices=torch.tensor([[4], [0], [2]])), dict(camera_indices=1, keep_shape=False),
+             dict(camera_indices=1, keep_shape=True, aabb_box=box)]  # (the reference's aabb_box branch needs [H, W] rays)
+    want = [cpu_cams.generate_rays(**c) for c in cases]  # the reference's own code (before install)
+    integration.install()
+    try:
+        gpu_cams = Cameras(**kw).to("cuda")
+        for c, w in zip(cases, want):
+            cg = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+            got = gpu_cams.generate_rays(**cg)
+            assert isinstance(got, RayBundle) and tuple(got.shape) == tuple(w.shape), (c.keys(), got.shape, w.shape)
+            assert_close(got.origins, w.origins, 2e-5), assert_close(got.directions, w.directions, 2e-5)
+            assert_close(got.pixel_area, w.pixel_area, 1e-4)
+            assert torch.equal(got.camera_indices.cpu(), w.camera_indices)
+            assert_close(got.metadata["directions_norm"], w.metadata["directions_norm"], 2e-5)
+            if w.nears is not None:
+                hit = w.nears < 1e9
+                assert torch.equal((got.nears.cpu() < 1e9), hit)
+                assert torch.allclose(got.nears.cpu()[hit], w.nears[hit], rtol=1e-3, atol=1e-5)
+                assert torch.allclose(got.fars.cpu()[hit], w.fars[hit], rtol=1e-3, atol=1e-5)
+        # CPU cameras keep the reference's code path
+        again = cpu_cams.generate_rays(camera_indices=ci, coords=coords)
+        assert torch.equal(again.directions, want[0].directions)
+    finally:
+        integration.uninstall()

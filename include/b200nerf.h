@@ -127,6 +127,19 @@ int b2n_mlp_tc_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const fl
                    const float* y, const float* hidden, const float* dy, int64_t n, float* dx, int64_t dx_stride,
                    void* stream);
 
+/* TMA staging of the weights: b2n_mlp_tc_pack writes (once per optimisation step) the exact shared-memory operand image
+ * of both directions — hi/lo tf32 split, UMMA core-matrix layout, hi and lo halves stacked, biases — into a caller
+ * workspace of b2n_mlp_tc_workspace_bytes() bytes (128-byte aligned); the *_ws calls then stage it into every persistent
+ * CTA with cp.async.bulk.tensor (tensor map built per call, mbarrier complete_tx) instead of per-CTA scalar loads.
+ * workspace == NULL: same as the calls above. */
+int64_t b2n_mlp_tc_workspace_bytes(const B2nMlp* mlp_host);
+int b2n_mlp_tc_pack(const B2nMlp* mlp_host, void* workspace, void* stream);
+int b2n_mlp_tc_fwd_ws(const B2nMlp* mlp_host, const float* x, int64_t x_stride, int64_t n, float* y, float* hidden,
+                      const void* workspace, void* stream);
+int b2n_mlp_tc_bwd_ws(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, int64_t x_stride,
+                      const float* y, const float* hidden, const float* dy, int64_t n, float* dx, int64_t dx_stride,
+                      const void* workspace, void* stream);
+
 /* ---- K5/K6: direction / frequency encodings ---------------------------------------------------------
  * SHEncoding (encodings.py:752-799, utils/spherical_harmonics.py:24-81): levels in 1..5, out [N,levels^2].
  * remap01 != 0 applies d <- (d+1)/2 first (fields/base_field.py:136-142 fused in). */

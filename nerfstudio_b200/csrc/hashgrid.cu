@@ -70,6 +70,83 @@ __global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const __grid_constant
   }
 }
 
+// Lane-pair variant of the F = 2 gather (default).  The L1TEX tag stage handles ONE 128-byte line per cycle per SM and
+// a warp-wide load costs as many cycles as it touches distinct lines (B300_MICROARCH: nL_j lines -> nL_j wavefronts).
+// With one thread per point every corner load of a fine level touches 32 lines, i.e. 8 line-cycles per (point, level)
+// — or 4 when the two x-neighbours happen to be an aligned 16-byte pair (x even).  But the x-neighbours ALWAYS sit in
+// the same 128-byte line 15 times out of 16: x enters the hash with prime 1, row = (x ^ h(y,z)) & mask, so all x of an
+// aligned block of 16 map into one aligned block of 16 rows = 128 B.  Here two adjacent lanes own one point — the even
+// lane the floor-x corners, the odd lane the ceil-x corners — so each of the 4 (y,z) loads is ONE instruction in which
+// both x-neighbours are requested together: 16 points x 1 line = 16 lines per instruction, 4 line-cycles per (point,
+// level) regardless of the parity of x.  The pair then exchanges the feature it does not blend (lane parity = feature
+// index), so every output is still formed with the reference's association (x, then y, then z) from all 8 corners —
+// bit-identical to the one-thread-per-point kernel.  Outputs of the block's level group are packed into one 16-byte
+// store per lane (pairs write 32 contiguous bytes).
+template <int MODE>
+__global__ void __launch_bounds__(256) hashgrid_fwd_pair_kernel(const __grid_constant__ GridParams gp,
+                                                                const float* __restrict__ x,
+                                                                const float* __restrict__ table, int64_t n,
+                                                                float* __restrict__ y, int levels_per_block) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t >> 1;
+  const bool live = i < n;
+  const int par = (int)(t & 1);  // 0: floor-x corners / feature 0, 1: ceil-x corners / feature 1
+  const int64_t ic = live ? i : n - 1;
+  const float px = __ldg(x + 3 * ic), py = __ldg(x + 3 * ic + 1), pz = __ldg(x + 3 * ic + 2);
+  const int l0 = blockIdx.y * levels_per_block;
+  const int l1 = min(gp.n_levels, l0 + levels_per_block);
+  float* yrow = y + ic * (int64_t)(gp.n_levels * 2);
+  // reference corner order k: x-corner c for k in {0,1,4,5}, f for {3,2,7,6}; (y,z) combos in the order
+  // q = 0:(yc,zc) 1:(yf,zc) 2:(yc,zf) 3:(yf,zf)  ->  ceil-x rows {0,1,4,5}, floor-x rows {3,2,7,6}
+  float pend[2];
+  int n_pend = 0;
+  for (int l = l0; l < l1; ++l) {
+    const Corners c = corners_of<MODE>(gp, l, px, py, pz);
+    uint32_t r4[4];
+    r4[0] = par ? c.row[0] : c.row[3], r4[1] = par ? c.row[1] : c.row[2];
+    r4[2] = par ? c.row[4] : c.row[7], r4[3] = par ? c.row[5] : c.row[6];
+    float2 f4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f4[q] = __ldg(reinterpret_cast<const float2*>(table) + r4[q]);
+    // I blend feature j = par and need the partner's x-corner values of that feature; the partner needs mine of 1 - par
+    float mine[4], theirs[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float send = par ? f4[q].x : f4[q].y;  // partner's feature index is 1 - par
+      mine[q] = par ? f4[q].y : f4[q].x;
+      theirs[q] = __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    // fc[q] / ff[q]: ceil-x / floor-x corner of (y,z) combo q, feature par
+    float fc[4], ff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fc[q] = par ? mine[q] : theirs[q], ff[q] = par ? theirs[q] : mine[q];
+    const float ox = c.ox, oy = c.oy, oz = c.oz;
+    const float rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
+    const float f03 = fc[0] * ox + ff[0] * rx;  // corners 0 (c,c,c) and 3 (f,c,c)
+    const float f12 = fc[1] * ox + ff[1] * rx;  // corners 1 (c,f,c) and 2 (f,f,c)
+    const float f47 = fc[2] * ox + ff[2] * rx;  // corners 4 (c,c,f) and 7 (f,c,f)
+    const float f56 = fc[3] * ox + ff[3] * rx;  // corners 5 (c,f,f) and 6 (f,f,f)
+    const float f0312 = f03 * oy + f12 * ry;
+    const float f4756 = f47 * oy + f56 * ry;
+    const float out = f0312 * oz + f4756 * rz;  // feature `par` of level l
+    // pack: two levels -> one float4 per lane.  Even lane stores level pair's first level (o0, o1), odd lane the second.
+    pend[n_pend++] = out;
+    if (n_pend == 2 || l == l1 - 1) {
+      if (n_pend == 2) {
+        // even lane keeps (o0[la], o1[la]), odd lane (o0[lb], o1[lb]):  exchange o_par[other level]
+        const float send = par ? pend[0] : pend[1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        const float a = par ? recv : pend[0], b = par ? pend[1] : recv;  // (feature 0, feature 1) of my level
+        if (live) *reinterpret_cast<float2*>(yrow + (l - 1 + par) * 2) = make_float2(a, b);
+      } else {
+        const float recv = __shfl_xor_sync(0xffffffffu, pend[0], 1);
+        if (live && par == 0) *reinterpret_cast<float2*>(yrow + l * 2) = make_float2(pend[0], recv);
+      }
+      n_pend = 0;
+    }
+  }
+}
+
 template <int F, int MODE, bool WITH_DX>
 __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(const __grid_constant__ GridParams gp,
                                                            const float* __restrict__ x,
@@ -201,10 +278,20 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_runs_kernel(const __grid_con
 }
 
 
+static int g_fwd_pair = 1;  // F = 2: two lanes per point (see hashgrid_fwd_pair_kernel); 0 = one thread per point
+
 template <int F>
 static void launch_fwd(const GridParams& gp, const float* x, const float* table, int64_t n, float* y, int64_t* idx,
                        cudaStream_t st) {
   int lpb = g_levels_per_block_fwd > 0 ? g_levels_per_block_fwd : gp.n_levels;
+  if (F == 2 && g_fwd_pair && idx == nullptr) {
+    dim3 grid((unsigned)div_up(2 * n, 256), (unsigned)div_up(gp.n_levels, lpb));
+    if (gp.mode == B2N_GRID_TORCH)
+      hashgrid_fwd_pair_kernel<B2N_GRID_TORCH><<<grid, 256, 0, st>>>(gp, x, table, n, y, lpb);
+    else
+      hashgrid_fwd_pair_kernel<B2N_GRID_TCNN><<<grid, 256, 0, st>>>(gp, x, table, n, y, lpb);
+    return;
+  }
   dim3 grid((unsigned)div_up(n, 256), (unsigned)div_up(gp.n_levels, lpb));
   if (gp.mode == B2N_GRID_TORCH)
     hashgrid_fwd_kernel<F, B2N_GRID_TORCH><<<grid, 256, 0, st>>>(gp, x, table, n, y, idx, lpb);
@@ -289,5 +376,6 @@ int b2n_tune_hashgrid(const char* key, int value) {
   if (!strcmp(key, "hash_levels_per_block_fwd")) { g_levels_per_block_fwd = value; return 1; }
   if (!strcmp(key, "hash_levels_per_block_bwd")) { g_levels_per_block_bwd = value; return 1; }
   if (!strcmp(key, "hash_bwd_chunk")) { g_bwd_chunk = value; return 1; }
+  if (!strcmp(key, "hash_fwd_pair")) { g_fwd_pair = value; return 1; }
   return 0;
 }

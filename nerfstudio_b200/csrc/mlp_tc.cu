@@ -23,6 +23,7 @@
 //                                        TMEM across all tiles of the CTA and are flushed once with REDs.
 // MN-major tf32 operands would need the SWIZZLE_128B_BASE32B layout (probed: the interleaved layout returns zeros),
 // hence the explicit transposed copies.
+#include <cuda.h>  // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is fetched at run time
 #include <string.h>
 
 #include "common.cuh"
@@ -51,6 +52,31 @@ struct TcParams {
   long long hid_off[TC_MAXL];          // feature offset (sum of previous real widths) of the saved activations
   uint32_t w_total;                    // bytes of the whole weight region
 };
+
+// ---- TMA staging of the packed weight image -----------------------------------------------------------------------
+// b2n_mlp_tc_pack writes, once per optimisation step, the exact shared-memory image the kernels want (hi/lo split,
+// canonical core-matrix layout, hi and lo halves stacked, zero padding, biases) into a caller-provided workspace; every
+// persistent CTA then pulls it with cp.async.bulk.tensor (a 2-D tensor map over [rows][64 floats], boxes of TC_WBOX_ROWS
+// rows) completing on an mbarrier — instead of 148 CTAs each re-reading, re-splitting and scatter-storing the weights.
+#define TC_WBOX_ROWS 16                       // rows of 256 B per TMA box (4 KB)
+#define TC_WBOX_BYTES (TC_WBOX_ROWS * 256)
+
+struct TcWeightsTma {
+  CUtensorMap map;  // 64-byte aligned by its typedef
+  int rows;         // rows of 256 B to copy (multiple of TC_WBOX_ROWS); 0 = stage with plain loads
+};
+
+__device__ __forceinline__ void tma_issue_weights(const TcWeightsTma& w, uint8_t* dst, uint64_t* bar) {
+  const uint32_t b = tc::smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((uint32_t)w.rows * 256u) : "memory");
+  for (int r0 = 0; r0 < w.rows; r0 += TC_WBOX_ROWS) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            tc::smem_u32(dst + (size_t)r0 * 256)),
+        "l"(&w.map), "r"(0), "r"(r0), "r"(b)
+        : "memory");
+  }
+}
 
 // The activation id is warp-uniform: switch once per slice, not per element (the per-element form compiled to a
 // branch ladder of ~12 instructions per value and made the epilogue the longest phase of the kernel).
@@ -420,17 +446,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_fwd_kernel(const __grid_
 #define TCF_THREADS (TCF_WORKERS + 32)
 
 __global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __grid_constant__ TcParams p,
+                                                                    const __grid_constant__ TcWeightsTma wt,
                                                                     const float* __restrict__ x, int64_t x_stride,
                                                                     int64_t n, float* __restrict__ y,
                                                                     float* __restrict__ hidden) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_full[2], bar_done[2];
+  __shared__ uint64_t bar_full[2], bar_done[2], bar_w;
   __shared__ uint32_t tmem_slot;
   uint8_t* Wr = smem + 4 * TC_TILE_BYTES;                        // weight region behind the two slots' hi/lo tiles
   float* bias = reinterpret_cast<float*>(Wr + p.w_total);        // [sum N]
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   constexpr int ISSUER_WARP = TCF_WORKERS / 32;
 
+  if (wt.rows > 0) {  // packed image (weights + biases) by TMA: one thread arms the barrier and issues the boxes
+    if (t == 0) {
+      tc::mbar_init(&bar_w, 1);
+      tma_issue_weights(wt, Wr, &bar_w);
+    }
+  } else {
   for (int l = 0; l < p.n_layers; ++l) {  // stage W as K-major canonical [2N rows][K cols] (hi rows, then lo rows)
     const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
     uint8_t* wst = Wr + p.w_off[l];
@@ -446,6 +479,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __gri
     }
     for (int j = t; j < N; j += TCF_THREADS) bias[p.bias_off[l] + j] = (j < nr && p.b[l]) ? __ldg(p.b[l] + j) : 0.f;
   }
+  }
   if (t == 0) {
     tc::mbar_init(&bar_full[0], TCF_SLOT_THREADS), tc::mbar_init(&bar_full[1], TCF_SLOT_THREADS);
     tc::mbar_init(&bar_done[0], 1), tc::mbar_init(&bar_done[1], 1);
@@ -455,6 +489,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __gri
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  if (wt.rows > 0) tc::mbar_wait(&bar_w, 0);  // weight image has landed (TMA complete_tx)
   const uint32_t tmem = tmem_slot;
   const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
   const int L = p.n_layers;
@@ -615,6 +650,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1) mlp_tc_fwd2_kernel(const __gri
 // backward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_constant__ TcParams p,
+                                                                  const __grid_constant__ TcWeightsTma wt,
                                                                   const float* __restrict__ x, int64_t x_stride,
                                                                   const float* __restrict__ y,
                                                                   const float* __restrict__ hidden,
@@ -632,7 +668,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
   const int t = threadIdx.x, warp = t >> 5, quarter = warp & 3;
   const int r = t & (TC_ROWS - 1), c0 = (t >> 7) * TC_HALF;
   const int L = p.n_layers;
+  __shared__ uint64_t bar_w;
 
+  if (wt.rows > 0) {  // packed W^T image by TMA
+    if (t == 0) {
+      tc::mbar_init(&bar_w, 1);
+      tma_issue_weights(wt, Wr, &bar_w);
+    }
+  } else {
   for (int l = 0; l < L; ++l) {
     const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
     // transposed (row = input index k, col = output index j), hi rows 0..K-1 and lo rows K..2K-1 stacked along the
@@ -649,11 +692,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
       *reinterpret_cast<float*>(wst + tc::canon_off(K + k, j, cs)) = lo;
     }
   }
+  }
   if (t == 0) tc::mbar_init(&bar, 1);
   if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+  if (wt.rows > 0) tc::mbar_wait(&bar_w, 0);  // W^T image has landed (TMA complete_tx)
   const uint32_t tmem = tmem_slot;
   uint32_t phase = 0;
   uint32_t dw_started = 0;  // bit l: the layer's dW accumulator has been written once (thread 0 only)
@@ -927,6 +972,93 @@ static int tc_build(const B2nMlp* m, const B2nMlpGrad* g, TcParams& p, bool tran
   return 0;
 }
 
+// ---- weight image: layout, pack kernel, tensor map ------------------------------------------------------------------
+static inline uint32_t pad_box(uint32_t bytes) { return (bytes + TC_WBOX_BYTES - 1) / TC_WBOX_BYTES * TC_WBOX_BYTES; }
+static uint32_t fwd_image_bytes(const TcParams& pf) {
+  uint32_t nb = 0;
+  for (int l = 0; l < pf.n_layers; ++l) nb += (uint32_t)pf.N[l];
+  return pad_box(pf.w_total + 4u * nb);
+}
+static uint32_t bwd_image_bytes(const TcParams& pb) { return pad_box(pb.w_total); }
+
+__global__ void __launch_bounds__(256) mlp_tc_pack_kernel(const __grid_constant__ TcParams pf,
+                                                          const __grid_constant__ TcParams pb, uint8_t* __restrict__ img_f,
+                                                          uint32_t bytes_f, uint8_t* __restrict__ img_b, uint32_t bytes_b) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  uint32_t nb = 0;
+  for (int l = 0; l < pf.n_layers; ++l) {
+    const int N = pf.N[l], K = pf.K[l], nr = pf.nr[l], kr = pf.kr[l];
+    uint8_t* wf = img_f + pf.w_off[l];
+    uint8_t* wb = img_b + pb.w_off[l];
+    const uint32_t csf = (uint32_t)(2 * N) * 16u, csb = (uint32_t)(2 * K) * 16u;
+    for (int idx = t; idx < N * K; idx += nt) {
+      const int j = idx / K, k = idx - j * K;
+      const float v = (j < nr && k < kr) ? __ldg(pf.w[l] + (size_t)j * kr + k) : 0.f;
+      float h, lo;
+      tc::split_tf32(v, h, lo);
+      *reinterpret_cast<float*>(wf + tc::canon_off(j, k, csf)) = h;      // forward: [2N rows][K cols], hi rows then lo rows
+      *reinterpret_cast<float*>(wf + tc::canon_off(N + j, k, csf)) = lo;
+      *reinterpret_cast<float*>(wb + tc::canon_off(k, j, csb)) = h;      // backward: W^T, [2K rows][N cols]
+      *reinterpret_cast<float*>(wb + tc::canon_off(K + k, j, csb)) = lo;
+    }
+    float* bias = reinterpret_cast<float*>(img_f + pf.w_total);
+    for (int j = t; j < N; j += nt) bias[pf.bias_off[l] + j] = (j < nr && pf.b[l]) ? __ldg(pf.b[l] + j) : 0.f;
+    nb += (uint32_t)N;
+  }
+  for (uint32_t o = pf.w_total + 4u * nb + 4u * t; o < bytes_f; o += 4u * nt) *reinterpret_cast<float*>(img_f + o) = 0.f;
+  for (uint32_t o = pb.w_total + 4u * t; o < bytes_b; o += 4u * nt) *reinterpret_cast<float*>(img_b + o) = 0.f;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+// tensor map over an image of `bytes` (multiple of TC_WBOX_BYTES): fp32 [bytes/256 rows][64], boxes of TC_WBOX_ROWS rows
+static int make_weight_map(TcWeightsTma& w, const void* image, uint32_t bytes) {
+  memset(&w, 0, sizeof(w));
+  EncodeTiledFn enc = encode_tiled();
+  if (enc == nullptr || image == nullptr || (reinterpret_cast<uintptr_t>(image) & 127) != 0) return -1;
+  const cuuint64_t dims[2] = {64, bytes / 256};
+  const cuuint64_t strides[1] = {256};
+  const cuuint32_t box[2] = {64, TC_WBOX_ROWS}, estr[2] = {1, 1};
+  if (enc(&w.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(image), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return -1;
+  w.rows = (int)(bytes / 256);
+  return 0;
+}
+
+extern "C" int64_t b2n_mlp_tc_workspace_bytes(const B2nMlp* mlp_host) {
+  TcParams pf, pb;
+  if (!mlp_host || tc_build(mlp_host, nullptr, pf, false) != 0 || tc_build(mlp_host, nullptr, pb, true) != 0) return -1;
+  return (int64_t)fwd_image_bytes(pf) + (int64_t)bwd_image_bytes(pb);
+}
+
+extern "C" int b2n_mlp_tc_pack(const B2nMlp* mlp_host, void* workspace, void* stream) {
+  B2N_REQUIRE(mlp_host && workspace, "null pointer");
+  B2N_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, "workspace must be 128-byte aligned");
+  TcParams pf, pb;
+  B2N_UNSUPPORTED(tc_build(mlp_host, nullptr, pf, false) != 0 || tc_build(mlp_host, nullptr, pb, true) != 0,
+                  "tensor-core MLP: needs <= 4 layers, widths <= 64 (hidden % 4 == 0), ReLU hidden, no skips");
+  const uint32_t bf = fwd_image_bytes(pf), bb = bwd_image_bytes(pb);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  mlp_tc_pack_kernel<<<16, 256, 0, (cudaStream_t)stream>>>(pf, pb, ws, bf, ws + bf, bb);
+  B2N_LAUNCH_CHECK();
+}
+
 static int g_tc_fwd_slots = 2;  // 2: warp-specialised two-slot kernel (default), 1: serial kernel
 int b2n_tune_mlp_tc(const char* key, int value) {
   if (strcmp(key, "tc_fwd_slots") == 0 && (value == 1 || value == 2)) {
@@ -946,8 +1078,8 @@ static int tc_smem_limit() {
   return lim;
 }
 
-extern "C" int b2n_mlp_tc_fwd(const B2nMlp* mlp_host, const float* x, int64_t x_stride, int64_t n, float* y,
-                              float* hidden, void* stream) {
+extern "C" int b2n_mlp_tc_fwd_ws(const B2nMlp* mlp_host, const float* x, int64_t x_stride, int64_t n, float* y,
+                                 float* hidden, const void* workspace, void* stream) {
   if (n == 0) return B2N_OK;
   B2N_REQUIRE(mlp_host && x && y, "null pointer");
   TcParams p;
@@ -955,10 +1087,12 @@ extern "C" int b2n_mlp_tc_fwd(const B2nMlp* mlp_host, const float* x, int64_t x_
                   "tensor-core MLP: needs <= 4 layers, widths <= 64 (hidden % 4 == 0), ReLU hidden, no skips");
   B2N_REQUIRE(x_stride >= mlp_host->in_dim, "x_stride smaller than in_dim");
   const int grid = (int)min(div_up(n, TC_ROWS), (int64_t)b2n_sm_count());
-  const size_t smem2 = 4 * TC_TILE_BYTES + p.w_total + 4 * 64 * TC_MAXL + 1024;
+  const size_t smem2 = 4 * TC_TILE_BYTES + fwd_image_bytes(p) + 1024;
   if (g_tc_fwd_slots == 2 && smem2 <= (size_t)tc_smem_limit()) {  // two tiles in flight (needs room for 4 operand tiles)
+    TcWeightsTma wt;
+    if (workspace == nullptr || make_weight_map(wt, workspace, fwd_image_bytes(p)) != 0) wt.rows = 0;
     cudaFuncSetAttribute(mlp_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    mlp_tc_fwd2_kernel<<<grid, TCF_THREADS, smem2, (cudaStream_t)stream>>>(p, x, x_stride, n, y, hidden);
+    mlp_tc_fwd2_kernel<<<grid, TCF_THREADS, smem2, (cudaStream_t)stream>>>(p, wt, x, x_stride, n, y, hidden);
     B2N_LAUNCH_CHECK();
   }
   const size_t smem = 2 * TC_TILE_BYTES + p.w_total + 4 * 64 * TC_MAXL + 1024;
@@ -968,9 +1102,14 @@ extern "C" int b2n_mlp_tc_fwd(const B2nMlp* mlp_host, const float* x, int64_t x_
   B2N_LAUNCH_CHECK();
 }
 
-extern "C" int b2n_mlp_tc_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, int64_t x_stride,
-                              const float* y, const float* hidden, const float* dy, int64_t n, float* dx,
-                              int64_t dx_stride, void* stream) {
+extern "C" int b2n_mlp_tc_fwd(const B2nMlp* mlp_host, const float* x, int64_t x_stride, int64_t n, float* y,
+                              float* hidden, void* stream) {
+  return b2n_mlp_tc_fwd_ws(mlp_host, x, x_stride, n, y, hidden, nullptr, stream);
+}
+
+extern "C" int b2n_mlp_tc_bwd_ws(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, int64_t x_stride,
+                                 const float* y, const float* hidden, const float* dy, int64_t n, float* dx,
+                                 int64_t dx_stride, const void* workspace, void* stream) {
   if (n == 0) return B2N_OK;
   B2N_REQUIRE(mlp_host && grad_host && x && y && dy, "null pointer");
   B2N_REQUIRE(mlp_host->n_layers == 1 || hidden != nullptr, "hidden activations required");
@@ -978,10 +1117,24 @@ extern "C" int b2n_mlp_tc_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_hos
   B2N_UNSUPPORTED(tc_build(mlp_host, grad_host, p, true) != 0,
                   "tensor-core MLP: needs <= 4 layers, widths <= 64 (hidden % 4 == 0), ReLU hidden, no skips");
   B2N_REQUIRE(dx == nullptr || dx_stride >= mlp_host->in_dim, "dx_stride smaller than in_dim");
-  const size_t smem = 2 * TC_TILE_BYTES + TC_TZ_BYTES + 2 * TC_TA_BYTES + p.w_total + 1024;
+  const size_t smem = 2 * TC_TILE_BYTES + TC_TZ_BYTES + 2 * TC_TA_BYTES + bwd_image_bytes(p) + 1024;
   B2N_UNSUPPORTED(smem > (size_t)tc_smem_limit(), "tensor-core MLP: shared memory");
+  TcWeightsTma wt;
+  wt.rows = 0;
+  if (workspace != nullptr) {
+    TcParams pf;
+    if (tc_build(mlp_host, nullptr, pf, false) != 0 ||
+        make_weight_map(wt, static_cast<const uint8_t*>(workspace) + fwd_image_bytes(pf), bwd_image_bytes(p)) != 0)
+      wt.rows = 0;
+  }
   cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = (int)min(div_up(n, TC_ROWS), (int64_t)b2n_sm_count());
-  mlp_tc_bwd_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, x, x_stride, y, hidden, dy, n, dx, dx_stride);
+  mlp_tc_bwd_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, wt, x, x_stride, y, hidden, dy, n, dx, dx_stride);
   B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_mlp_tc_bwd(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const float* x, int64_t x_stride,
+                              const float* y, const float* hidden, const float* dy, int64_t n, float* dx,
+                              int64_t dx_stride, void* stream) {
+  return b2n_mlp_tc_bwd_ws(mlp_host, grad_host, x, x_stride, y, hidden, dy, n, dx, dx_stride, nullptr, stream);
 }

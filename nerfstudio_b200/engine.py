@@ -97,6 +97,8 @@ class NerfactoStep:
             return mlp_backend == "tc" or max(sp.out_dims) >= 32
 
         self.tc_net = {id(sp): use_tc(sp) for sp in specs}
+        self._tc_ws: Dict[int, Tensor] = {}
+        self.tma_weights = True  # stage the tensor-core MLP weights by TMA from a per-step packed image
         self.fused_props = fused_proposals and all(F.density_field_supported(p_.grid, p_.spec) for p_ in self.props)
         self.tc = use_tc(self.head_spec)
         self.contraction = fld.spatial_distortion is not None
@@ -164,17 +166,39 @@ class NerfactoStep:
             raise NotImplementedError("captured step: background_color must be last_sample / white / black")
 
     # ------------------------------------------------------------------------------------------------
+    def _tc_workspace(self, m, spec) -> Tensor:
+        """Per-network device workspace for the packed weight images the tensor-core kernels stage with TMA."""
+        ws = self._tc_ws.get(id(spec))
+        if ws is None:
+            nbytes = int(lib.load().b2n_mlp_tc_workspace_bytes(C.byref(m)))
+            if nbytes <= 0:
+                raise RuntimeError("b2n_mlp_tc_workspace_bytes failed")
+            ws = torch.zeros(nbytes // 4 + 64, device=self.dev, dtype=torch.float32)
+            off = (-ws.data_ptr()) % 128 // 4  # 128-byte aligned start (TMA source)
+            ws = ws[off: off + nbytes // 4]
+            self._tc_ws[id(spec)] = ws
+        return ws
+
+    def _pack_weights(self) -> None:
+        """Once per step, before the first forward: operand images (hi/lo split, UMMA layout) of the current weights."""
+        nets = [(self.base.structs()[0], self.base.spec), (self.head_spec.struct(self.head_w, self.head_b), self.head_spec)]
+        nets += [(p_.structs()[0], p_.spec) for p_ in self.props]
+        for m, spec in nets:
+            if self.tc_net[id(spec)]:
+                call("b2n_mlp_tc_pack", C.byref(m), ptr(self._tc_workspace(m, spec)), stream())
+
     def _mlp_fwd(self, m, x: Tensor, x_stride: int, n: int, y: Tensor, hidden: Tensor, spec=None) -> None:
         if self.tc_net[id(spec)]:
-            call("b2n_mlp_tc_fwd", C.byref(m), ptr(x), x_stride, n, ptr(y), ptr(hidden), stream())
+            call("b2n_mlp_tc_fwd_ws", C.byref(m), ptr(x), x_stride, n, ptr(y), ptr(hidden),
+                 ptr(self._tc_workspace(m, spec)) if self.tma_weights else NULL, stream())
         else:
             call("b2n_mlp_fwd", C.byref(m), ptr(x), n, ptr(y), ptr(hidden), stream())
 
     def _mlp_bwd(self, m, g, x: Tensor, x_stride: int, y: Tensor, hidden: Tensor, dy: Tensor, n: int, dx: Tensor,
                  dx_stride: int, spec=None) -> None:
         if self.tc_net[id(spec)]:
-            call("b2n_mlp_tc_bwd", C.byref(m), C.byref(g), ptr(x), x_stride, ptr(y), ptr(hidden), ptr(dy), n, ptr(dx),
-                 dx_stride, stream())
+            call("b2n_mlp_tc_bwd_ws", C.byref(m), C.byref(g), ptr(x), x_stride, ptr(y), ptr(hidden), ptr(dy), n, ptr(dx),
+                 dx_stride, ptr(self._tc_workspace(m, spec)) if self.tma_weights else NULL, stream())
         else:
             call("b2n_mlp_bwd", C.byref(m), C.byref(g), ptr(x), ptr(y), ptr(hidden), ptr(dy), n, ptr(dx), stream())
 
@@ -233,6 +257,8 @@ class NerfactoStep:
         else:  # tests: replay recorded stratified draws
             for j, src in zip(self.jitter, self.fixed_jitter):
                 j.copy_(src)
+        if self.tma_weights:
+            self._pack_weights()
         # ---------------- forward: proposal sampling
         call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), ptr(self.jitter[0]), 0, R, S0,
              lib.SPACING[self.spacing], ptr(self.sb[0]), ptr(self.eb[0]), st())

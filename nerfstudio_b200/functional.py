@@ -216,26 +216,42 @@ def mlp_tc_supported(spec: MlpSpec) -> bool:
             and spec.out_act in ("none", "sigmoid", "relu"))
 
 
-def mlp_tc_forward(spec: MlpSpec, x: Tensor, weights, biases, save_hidden: bool, x_stride: Optional[int] = None):
-    """Tensor-core forward.  x [N, >=in_dim] row-major (row stride x_stride floats)."""
+def mlp_tc_pack(spec: MlpSpec, weights, biases) -> Tensor:
+    """Packed operand images (forward W and backward W^T: hi/lo split, UMMA layout) of the current weights in a fresh
+    128-byte aligned device workspace — what the *_ws kernels stage into shared memory with TMA."""
+    m = spec.struct([_c(w) for w in weights], [None if b is None else _c(b) for b in biases])
+    nbytes = int(lib.load().b2n_mlp_tc_workspace_bytes(C.byref(m)))
+    if nbytes <= 0:
+        raise ValueError("network outside the tensor-core MLP's shape range")
+    buf = torch.zeros(nbytes // 4 + 64, device=weights[0].device, dtype=torch.float32)
+    off = (-buf.data_ptr()) % 128 // 4
+    ws = buf[off: off + nbytes // 4]
+    call("b2n_mlp_tc_pack", C.byref(m), ptr(ws), stream())
+    return ws
+
+
+def mlp_tc_forward(spec: MlpSpec, x: Tensor, weights, biases, save_hidden: bool, x_stride: Optional[int] = None,
+                   workspace: Optional[Tensor] = None):
+    """Tensor-core forward.  x [N, >=in_dim] row-major (row stride x_stride floats).  workspace: mlp_tc_pack's image."""
     x = _c(x)
     n = x.shape[0]
     y = torch.empty(n, spec.out_dims[-1], device=x.device, dtype=torch.float32)
     hidden = torch.empty(max(spec.hidden_width, 1) * n, device=x.device, dtype=torch.float32) if save_hidden else None
     m = spec.struct([_c(w) for w in weights], [None if b is None else _c(b) for b in biases])
-    call("b2n_mlp_tc_fwd", C.byref(m), ptr(x), x_stride or x.shape[1], n, ptr(y), ptr(hidden), stream())
+    call("b2n_mlp_tc_fwd_ws", C.byref(m), ptr(x), x_stride or x.shape[1], n, ptr(y), ptr(hidden), ptr(workspace), stream())
     return y, hidden
 
 
-def mlp_tc_backward(spec: MlpSpec, x, y, hidden, dy, weights, biases, dws, dbs, want_dx: bool):
+def mlp_tc_backward(spec: MlpSpec, x, y, hidden, dy, weights, biases, dws, dbs, want_dx: bool,
+                    workspace: Optional[Tensor] = None):
     m = spec.struct(weights, biases)
     g = B2nMlpGrad()
     for i in range(len(spec.out_dims)):
         g.dw[i] = ptr(dws[i]).value if dws[i] is not None else None
         g.db[i] = ptr(dbs[i]).value if dbs[i] is not None else None
     dx = torch.empty(x.shape[0], spec.in_dim, device=x.device, dtype=torch.float32) if want_dx else None
-    call("b2n_mlp_tc_bwd", C.byref(m), C.byref(g), ptr(x), x.shape[1], ptr(y), ptr(hidden), ptr(_c(dy)), x.shape[0],
-         ptr(dx), spec.in_dim, stream())
+    call("b2n_mlp_tc_bwd_ws", C.byref(m), C.byref(g), ptr(x), x.shape[1], ptr(y), ptr(hidden), ptr(_c(dy)), x.shape[0],
+         ptr(dx), spec.in_dim, ptr(workspace), stream())
     return dx
 
 

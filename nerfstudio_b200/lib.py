@@ -56,6 +56,9 @@ _SIGNATURES = {
     "b2n_mlp_bwd": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _I64, _P, _P],
     "b2n_mlp_tc_fwd": [C.POINTER(B2nMlp), _P, _I64, _I64, _P, _P, _P],
     "b2n_mlp_tc_bwd": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _I64, _P, _P, _P, _I64, _P, _I64, _P],
+    "b2n_mlp_tc_pack": [C.POINTER(B2nMlp), _P, _P],
+    "b2n_mlp_tc_fwd_ws": [C.POINTER(B2nMlp), _P, _I64, _I64, _P, _P, _P, _P],
+    "b2n_mlp_tc_bwd_ws": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _P],
     "b2n_sh_fwd": [_P, _I64, _I32, _I32, _P, _P],
     "b2n_freq_fwd": [_P, _I64, _I32, _P, _I32, _I32, _P, _P],
     "b2n_freq_bwd": [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P],
@@ -104,8 +107,9 @@ _SIGNATURES = {
     "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P],
 }
 _RET = {"b2n_version": C.c_char_p, "b2n_last_error": C.c_char_p}
+_RET_ARGS = {"b2n_mlp_tc_workspace_bytes": ([C.POINTER(B2nMlp)], C.c_int64)}
 
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RET))
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RET) + list(_RET_ARGS))
 
 _lib: Optional[C.CDLL] = None
 
@@ -127,6 +131,9 @@ def load() -> C.CDLL:
     for name, ret in _RET.items():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = [], ret
+    for name, (argtypes, ret) in _RET_ARGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argtypes, ret
     _lib = lib
     # B2N_TUNE="key=value,key=value": launch-geometry / kernel-variant knobs applied once at load (see b2n_tune)
     for kv in filter(None, os.environ.get("B2N_TUNE", "").split(",")):
@@ -155,7 +162,7 @@ LAUNCHES = 0  # kernel-launching C-ABI calls made by this process (bench.py repo
 PROFILE = None  # set to {} to time every C-ABI launch with CUDA events on the launching stream (eager mode only)
 PROFILE_BY_SIZE = True  # False: one row per entry point (dynamic sizes, e.g. packed instant-ngp samples); n is summed
 _N_ARG = {"b2n_hashgrid_fwd": 3, "b2n_hashgrid_bwd": 4, "b2n_mlp_fwd": 2, "b2n_mlp_bwd": 6, "b2n_mlp_tc_fwd": 3,
-          "b2n_mlp_tc_bwd": 7}
+          "b2n_mlp_tc_bwd": 7, "b2n_mlp_tc_fwd_ws": 3, "b2n_mlp_tc_bwd_ws": 7}
 
 
 def call(name: str, *args) -> None:
@@ -177,7 +184,7 @@ def call(name: str, *args) -> None:
         key = f"{name}[n={args[9] * args[10]}]"
     elif name in _N_ARG and name.startswith("b2n_mlp"):
         m = args[0]._obj  # byref(B2nMlp): two networks of one model may share n (base / colour head)
-        key = f"{name}[n={args[_N_ARG[name]]},in={m.in_dim},out={m.out_dims[m.n_layers - 1]}]"
+        key = f"{name.replace('_ws', '')}[n={args[_N_ARG[name]]},in={m.in_dim},out={m.out_dims[m.n_layers - 1]}]"
     else:
         key = f"{name}[n={args[_N_ARG[name]]}]" if name in _N_ARG else name
     PROFILE.setdefault(key, []).append((e0, e1, n_arg))

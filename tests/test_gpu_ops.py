@@ -72,6 +72,29 @@ def test_hashgrid_full_size_properties(F):
     assert_close(y1[:2048], yo, TIGHT)
 
 
+def test_hashgrid_pair_kernel_bitwise_equals_thread_per_point(F):
+    """The lane-pair gather (default for F = 2) forms every output from the same 8 corners in the same association as the
+    one-thread-per-point kernel: bit-identical, at the BASELINE size, odd point counts, 5- and 16-level grids, both modes."""
+    from nerfstudio_b200 import lib
+
+    torch.manual_seed(2)
+    cases = [(F.GridSpec(O.hash_level_scalings(16, 16, 2048).tolist(), 19, 2), 16 << 19, 196608),
+             (F.GridSpec(O.hash_level_scalings(5, 16, 128).tolist(), 17, 2), 5 << 17, 100001),
+             (F.GridSpec(O.hash_level_scalings(7, 16, 512).tolist(), 12, 2), 7 << 12, 1)]
+    g = F.GridSpec.tcnn(8, 16, 1.3819, 12, 2)
+    cases.append((g, g.n_rows, 3333))
+    for grid, rows, N in cases:
+        x = torch.rand(N, 3, device="cuda")
+        x[: min(N, 7)] = torch.tensor([0.0, 0.5, 1.0])[:3]  # exact grid points: ceil == floor
+        table = torch.randn(rows, 2, device="cuda")
+        try:
+            assert lib.tune("hash_fwd_pair", 0)
+            ref = F.hashgrid_forward(x, table, grid)
+        finally:
+            lib.tune("hash_fwd_pair", 1)
+        assert torch.equal(F.hashgrid_forward(x, table, grid), ref), (grid.n_levels, N)
+
+
 def test_hashgrid_tcnn_mode(F):
     """tcnn-mode addressing vs the oracle's restatement of the published semantics (parity unpinned upstream)."""
     torch.manual_seed(1)

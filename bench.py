@@ -410,7 +410,7 @@ def run_b200(args) -> None:
 
     # ---- per-kernel durations (after the timed regions): the same launch sequence run eagerly with CUDA events around
     # every C-ABI call on the launching stream (a CUDA graph has no per-node events)
-    kernel_table, ms_prof, n_prof, prof, scatter_frac = None, ms / args.steps, args.steps, {}, {}
+    kernel_table, ms_prof, n_prof, prof, scatter_frac, dense_ms = None, ms / args.steps, args.steps, {}, {}, {}
     if engine is not None:
         was_graph, engine.use_graph = engine.use_graph, False
         lib.LAUNCHES, lib.PROFILE = 0, None
@@ -430,6 +430,19 @@ def run_b200(args) -> None:
         # others, so its algorithmic bytes are gather + frac * (read + write)
         for lvl in (0, 1):
             scatter_frac[RAYS_PER_GPU * engine.S[lvl]] = float((engine.d_dens[lvl] != 0).float().mean().item())
+        # the same kernel with a gradient on EVERY sample (the regime at the start of training / on scenes where the
+        # proposal histograms under-estimate everywhere): its time is data dependent, so both regimes are reported
+        if engine.fused_props:
+            for lvl in (0, 1):
+                engine.d_dens[lvl].fill_(1e-6)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                engine.density_field_bwd_launch(lvl)
+                e0.record()
+                for _ in range(5):
+                    engine.density_field_bwd_launch(lvl)
+                e1.record()
+                torch.cuda.synchronize()
+                dense_ms[f"b2n_density_field_bwd[n={RAYS_PER_GPU * engine.S[lvl]}]"] = e0.elapsed_time(e1) / 5
     sampler.stop()
     if rank != 0:
         return
@@ -512,7 +525,11 @@ def run_b200(args) -> None:
                    "params": n_params},
         "windows_ms": win_ms, "e2e_windows_ms": e2e_ms,
         "roofline": roofline, "roofline_hash_gather": gather_roof, "roofline_step": step_roof,
-        "hash_kernels": hash_rows or None, "kernel_ms_per_step": kernel_table, "cpu_baseline": cpu,
+        "hash_kernels": hash_rows or None, "kernel_ms_per_step": kernel_table,
+        "data_dependent_kernels": {"fraction_of_samples_with_gradient": scatter_frac or None, "ms_in_dense_gradient_regime": dense_ms or None,
+                                   "note": "density_field_bwd skips warps whose samples all have zero d_density (exact zeros from the "
+                                           "interlevel loss); kernel_ms_per_step is the regime of the timed windows"},
+        "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
                 "through": ("FusedTrainStep.train_iteration(step): the reference's Trainer.train_iteration / "

@@ -237,6 +237,16 @@ int b2n_raygen_coords(const float* c2w, const float* intr, const float* dist, co
                       const float* coords, int64_t n_rays, int32_t n_cams, int32_t height, int32_t width,
                       const float* cam_opt, const float* dist_delta, float* origins, float* directions,
                       float* pixel_area, float* directions_norm, int64_t* camera_indices, void* stream);
+/* Device-side training-ray pipeline: PixelSampler.sample_method + collate_image_dataset_batch
+ * (data/pixel_samplers.py:137-174,265-318) + RayGenerator (model_components/ray_generators.py:41-56) over a uint8 image
+ * cache resident in HBM: images uint8 [n_images, height, width, channels >= 3]; image_idx int64 [n_images] (absolute
+ * camera index of each cached image; NULL = identity); u [R,3] = the sampler's U(0,1) draws, indices = trunc(u * [n_images,
+ * height, width]).  Outputs (each optional): ray_indices int64 [R,3] (camera,row,col), the RayBundle fields as b2n_raygen,
+ * rgb [R,3] = pixel / 255 (get_image_float32). */
+int b2n_pixel_sample_raygen(const float* c2w, const float* intr, const float* dist, const uint8_t* images,
+                            int32_t n_images, int32_t height, int32_t width, int32_t channels, const int64_t* image_idx,
+                            const float* u, int64_t n_rays, int64_t* ray_indices, float* origins, float* directions,
+                            float* pixel_area, float* directions_norm, int64_t* camera_indices, float* rgb, void* stream);
 /* AABBBoxCollider (model_components/scene_colliders.py:47-108). */
 int b2n_aabb_collide(const float* origins, const float* directions, const float* aabb_host6, float near_plane,
                      int64_t n_rays, float* nears, float* fars, void* stream);

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
 #pragma unroll
   for (int j = 0; j <= DF_H; ++j) g2[j] = 0.f;
   if (t <= DF_H) red2[t] = 0.f;
+  for (int q = t; q < SC * CSW; q += DF_THREADS) stage[q] = 0.f;  // skipped warps leave columns untouched: start finite
   __syncthreads();
   float* my_denc = denc + t * DW;
 
@@ -182,13 +183,24 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
 #pragma unroll
     for (int s = 0; s < DF_CH; ++s) {
       const int64_t i = i0 + s;
+      // Every gradient this kernel produces is proportional to d_density of the sample.  The interlevel loss — the only
+      // loss that reaches the proposal networks — is zero wherever the proposal histogram already bounds the final
+      // weights, and weights_bwd turns that into exact zeros for whole rays / ray tails, so a warp (32 lanes = samples
+      // spaced DF_CH apart, i.e. one ray's neighbourhood) whose samples all have zero gradient skips the re-gather, the
+      // network and the staging; a CTA round with no live warp also skips the owners' reduction.
+      const float g = i < n ? __ldg(d_density + i) : 0.f;
+      const bool warp_live = __any_sync(0xffffffffu, g != 0.f);
       float dz2 = 0.f;
-      if (i < n) {
+      if (!warp_live) {
+#pragma unroll
+        for (int j = 0; j < DF_H; ++j) stage[j * CSW + t] = 0.f;  // dz1 = 0: stale encodings in the other columns are harmless
+#pragma unroll
+        for (int c = 0; c < IN; ++c) my_denc[s * IN + c] = 0.f;
+      } else if (i < n) {
         Sample<L> sm;
         encode_sample<L, MODE>(gp, pp, rg, table, i, sm);
         float z1[DF_H];
         const float z2 = mlp_forward<L>(ws, sm.enc, z1);
-        const float g = __ldg(d_density + i);
         // density = avg * exp(z2) * sel ; trunc_exp backward clamps the exponent (activations.py:36-41)
         if (sm.sel && g != 0.f) dz2 = g * net.avg_init * expf(fminf(fmaxf(z2, -15.f), 15.f));
         float de[IN];
@@ -222,7 +234,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
 #pragma unroll
         for (int a = 0; a < 3; ++a) xs[s][a] = 0.f;
       }
-      __syncthreads();
+      if (!__syncthreads_or(warp_live)) continue;  // CTA-uniform: nothing staged this round, nothing to reduce
       // ---- the owners reduce their product over this round's 256 staged samples (128-bit column reads)
       if (role == 0) {
         const float4* zc = reinterpret_cast<const float4*>(stage + oj * CSW);

@@ -46,19 +46,10 @@ __global__ void __launch_bounds__(256) hashgrid_fwd_kernel(const __grid_constant
 #pragma unroll
       for (int k = 0; k < 8; ++k) idx_out[(i * gp.n_levels + l) * 8 + k] = (int64_t)c.row[k];
     }
-    const float ox = c.ox, oy = c.oy, oz = c.oz;
-    const float rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
     float out[F];
 #pragma unroll
-    for (int j = 0; j < F; ++j) {
-      const float f03 = f[0].v[j] * ox + f[3].v[j] * rx;
-      const float f12 = f[1].v[j] * ox + f[2].v[j] * rx;
-      const float f56 = f[5].v[j] * ox + f[6].v[j] * rx;
-      const float f47 = f[4].v[j] * ox + f[7].v[j] * rx;
-      const float f0312 = f03 * oy + f12 * ry;
-      const float f4756 = f47 * oy + f56 * ry;
-      out[j] = f0312 * oz + f4756 * rz;
-    }
+    for (int j = 0; j < F; ++j)
+      out[j] = blend8(f[0].v[j], f[1].v[j], f[2].v[j], f[3].v[j], f[4].v[j], f[5].v[j], f[6].v[j], f[7].v[j], c.ox, c.oy, c.oz);
     if constexpr (F == 2) {
       *reinterpret_cast<float2*>(yrow + l * 2) = make_float2(out[0], out[1]);
     } else if constexpr (F == 4) {
@@ -120,15 +111,8 @@ __global__ void __launch_bounds__(256) hashgrid_fwd_pair_kernel(const __grid_con
     float fc[4], ff[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) fc[q] = par ? mine[q] : theirs[q], ff[q] = par ? theirs[q] : mine[q];
-    const float ox = c.ox, oy = c.oy, oz = c.oz;
-    const float rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
-    const float f03 = fc[0] * ox + ff[0] * rx;  // corners 0 (c,c,c) and 3 (f,c,c)
-    const float f12 = fc[1] * ox + ff[1] * rx;  // corners 1 (c,f,c) and 2 (f,f,c)
-    const float f47 = fc[2] * ox + ff[2] * rx;  // corners 4 (c,c,f) and 7 (f,c,f)
-    const float f56 = fc[3] * ox + ff[3] * rx;  // corners 5 (c,f,f) and 6 (f,f,f)
-    const float f0312 = f03 * oy + f12 * ry;
-    const float f4756 = f47 * oy + f56 * ry;
-    const float out = f0312 * oz + f4756 * rz;  // feature `par` of level l
+    // corners: 0 (c,c,c) 1 (c,f,c) 2 (f,f,c) 3 (f,c,c) 4 (c,c,f) 5 (c,f,f) 6 (f,f,f) 7 (f,c,f)
+    const float out = blend8(fc[0], fc[1], ff[1], ff[0], fc[2], fc[3], ff[3], ff[2], c.ox, c.oy, c.oz);  // feature `par`
     // pack: two levels -> one float4 per lane.  Even lane stores level pair's first level (o0, o1), odd lane the second.
     pend[n_pend++] = out;
     if (n_pend == 2 || l == l1 - 1) {

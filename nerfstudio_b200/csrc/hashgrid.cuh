@@ -123,6 +123,18 @@ __device__ __forceinline__ Corners corners_of(const GridParams& gp, int l, float
 }
 
 
+// Trilinear blend of the 8 corners in the reference's association (encodings.py:446-456: x pairs f03,f12,f56,f47 -> y
+// pairs f0312,f4756 -> z) with the FMA contraction written out, so every gather kernel that uses it produces the same
+// bits (the compiler otherwise picks the fused product per call site).
+__device__ __forceinline__ float blend8(float f0, float f1, float f2, float f3, float f4, float f5, float f6, float f7,
+                                        float ox, float oy, float oz) {
+  const float rx = __fsub_rn(1.f, ox), ry = __fsub_rn(1.f, oy), rz = __fsub_rn(1.f, oz);
+  const float f03 = __fmaf_rn(f0, ox, __fmul_rn(f3, rx)), f12 = __fmaf_rn(f1, ox, __fmul_rn(f2, rx));
+  const float f56 = __fmaf_rn(f5, ox, __fmul_rn(f6, rx)), f47 = __fmaf_rn(f4, ox, __fmul_rn(f7, rx));
+  const float f0312 = __fmaf_rn(f03, oy, __fmul_rn(f12, ry)), f4756 = __fmaf_rn(f47, oy, __fmul_rn(f56, ry));
+  return __fmaf_rn(f0312, oz, __fmul_rn(f4756, rz));
+}
+
 // the 8 corner feature rows of one (point, level), F = 2: 4 x 128-bit loads when the x-neighbours are paired
 __device__ __forceinline__ void gather_corners2(const float* __restrict__ table, const Corners& c, Vec<2> (&f)[8]) {
   if (c.xpair) {

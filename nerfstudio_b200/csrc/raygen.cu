@@ -173,6 +173,57 @@ extern "C" int b2n_raygen_coords(const float* c2w, const float* intr, const floa
   B2N_LAUNCH_CHECK();
 }
 
+// Device-side training-ray pipeline: PixelSampler.sample_method + collate (data/pixel_samplers.py:137-174,
+// 265-318) + RayGenerator (model_components/ray_generators.py:41-56) in one launch over a uint8 image cache that lives
+// in HBM.  u [R,3] are the reference's `torch.rand((R,3))` draws; indices = (u * [C,H,W]).long() — a separately rounded
+// fp32 multiply, then truncation, as torch evaluates it.  Pixel colours are converted like `get_image_float32`
+// (uint8 / 255).  Outputs are written where the captured step wants them (any of them may be NULL).
+__global__ void pixel_sample_raygen_kernel(const float* __restrict__ c2w, const float* __restrict__ intr,
+                                           const float* __restrict__ dist, const uint8_t* __restrict__ images,
+                                           int n_images, int height, int width, int channels,
+                                           const int64_t* __restrict__ image_idx, const float* __restrict__ u,
+                                           int64_t n_rays, int64_t* __restrict__ ray_indices, float* __restrict__ origins,
+                                           float* __restrict__ directions, float* __restrict__ pixel_area,
+                                           float* __restrict__ directions_norm, int64_t* __restrict__ camera_indices,
+                                           float* __restrict__ rgb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rays) return;
+  const int c = min((int)mul_rn(__ldg(u + 3 * i), (float)n_images), n_images - 1);
+  const int y = min((int)mul_rn(__ldg(u + 3 * i + 1), (float)height), height - 1);
+  const int x = min((int)mul_rn(__ldg(u + 3 * i + 2), (float)width), width - 1);
+  const int64_t cam = image_idx ? image_idx[c] : (int64_t)c;  // cached subset -> absolute camera index
+  if (rgb) {
+    const uint8_t* px = images + (((size_t)c * height + y) * width + x) * channels;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) rgb[3 * i + a] = div_rn((float)px[a], 255.f);
+  }
+  if (ray_indices) ray_indices[3 * i] = cam, ray_indices[3 * i + 1] = y, ray_indices[3 * i + 2] = x;
+  float o[3], d[3], area, nrm;
+  ray_from_pixel(c2w, intr, dist, nullptr, nullptr, cam, (float)x + 0.5f, (float)y + 0.5f, o, d, &area, &nrm);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (origins) origins[3 * i + a] = o[a];
+    if (directions) directions[3 * i + a] = d[a];
+  }
+  if (pixel_area) pixel_area[i] = area;
+  if (directions_norm) directions_norm[i] = nrm;
+  if (camera_indices) camera_indices[i] = cam;
+}
+
+extern "C" int b2n_pixel_sample_raygen(const float* c2w, const float* intr, const float* dist, const uint8_t* images,
+                                       int32_t n_images, int32_t height, int32_t width, int32_t channels,
+                                       const int64_t* image_idx, const float* u, int64_t n_rays, int64_t* ray_indices,
+                                       float* origins, float* directions, float* pixel_area, float* directions_norm,
+                                       int64_t* camera_indices, float* rgb, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(c2w && intr && u && (images || !rgb), "null pointer");
+  B2N_REQUIRE(n_images >= 1 && height >= 1 && width >= 1 && channels >= 3, "bad image cache shape");
+  pixel_sample_raygen_kernel<<<(unsigned)div_up(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+      c2w, intr, dist, images, n_images, height, width, channels, image_idx, u, n_rays, ray_indices, origins, directions,
+      pixel_area, directions_norm, camera_indices, rgb);
+  B2N_LAUNCH_CHECK();
+}
+
 struct Box {
   float lo[3], hi[3];
 };

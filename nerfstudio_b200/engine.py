@@ -231,11 +231,7 @@ class NerfactoStep:
         call("b2n_weights_bwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), ptr(self.d_w[lvl]), R, S,
              ptr(self.d_dens[lvl]), stream())
         if self.fused_props:
-            m, g = net.structs()
-            box = lib.host_floats(self.aabb)
-            call("b2n_density_field_bwd", C.byref(net.grid.c), C.byref(m), C.byref(g), ptr(net.table), ptr(self.origins),
-                 ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
-                 self.avg, ptr(self.d_dens[lvl]), ptr(net.table.grad), stream())
+            self.density_field_bwd_launch(lvl)
             return
         call("b2n_density_act_bwd", ptr(self.h[lvl]), 1, ptr(self.sel[lvl], torch.uint8), ptr(self.d_dens[lvl]), N, self.avg,
              ptr(self.d_h[lvl]), 1, stream())
@@ -244,6 +240,16 @@ class NerfactoStep:
                       self.d_enc[lvl], self.d_enc[lvl].shape[1], net.spec)
         call("b2n_hashgrid_bwd", C.byref(net.grid.c), ptr(self.x[lvl]), ptr(net.table), ptr(self.d_enc[lvl]), N,
              ptr(net.table.grad), NULL, stream())
+
+    def density_field_bwd_launch(self, lvl: int) -> None:
+        """The fused proposal-field backward of level `lvl` on the current `d_dens[lvl]` (also used by bench.py to time
+        the kernel in the dense-gradient regime: its cost depends on how many samples carry a gradient)."""
+        net, R, S, eb = self.props[lvl], self.R, self.S[lvl], self.eb[lvl]
+        m, g = net.structs()
+        box = lib.host_floats(self.aabb)
+        call("b2n_density_field_bwd", C.byref(net.grid.c), C.byref(m), C.byref(g), ptr(net.table), ptr(self.origins),
+             ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
+             self.avg, ptr(self.d_dens[lvl]), ptr(net.table.grad), stream())
 
     def _body(self, update_props: bool) -> None:
         R, S0, S1, S2 = self.R, *self.S

@@ -106,6 +106,17 @@ def install(shim_third_party: bool = True, patch_get_weights: bool = True) -> Li
                 if holder is not None and holder is not ref_mod and getattr(holder, attr, None) is original:
                     _set(holder, attr, ours)
                     done.append(f"{holder_name}.{attr}")
+    # our fields key their output dictionaries with FieldHeadNames; inside nerfstudio that must be the REFERENCE's enum
+    # object (models index field_outputs[FieldHeadNames.DENSITY], models/nerfacto.py:308).  When this package was imported
+    # before nerfstudio became importable it defined its own enum: re-bind the name everywhere it is held.
+    ref_heads = importlib.import_module("nerfstudio.field_components.field_heads")
+    for mod_name in ("nerfstudio_b200.field_components.field_heads", "nerfstudio_b200.fields.base_field",
+                     "nerfstudio_b200.fields.nerfacto_field", "nerfstudio_b200.fields.vanilla_nerf_field",
+                     "nerfstudio_b200.nerfacto", "nerfstudio_b200.instant_ngp"):
+        mod = importlib.import_module(mod_name)
+        if getattr(mod, "FieldHeadNames", None) is not ref_heads.FieldHeadNames:
+            _set(mod, "FieldHeadNames", ref_heads.FieldHeadNames)
+            done.append(f"{mod_name}.FieldHeadNames")
     if patch_get_weights:
         from .cameras.rays import RaySamples as OurSamples
 

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "b2n_distortion_fwd_bwd": [_P, _P, _I64, _I32, _F, _P, _P, _P],
     "b2n_raygen": [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P],
     "b2n_raygen_coords": [_P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b2n_pixel_sample_raygen": [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P],
     "b2n_aabb_collide": [_P, _P, _P, _F, _I64, _P, _P, _P],
     "b2n_pose_apply_fwd": [_P, _P, _P, _P, _P, _I64, _P, _P, _P],
     "b2n_pose_apply_bwd": [_P, _P, _P, _P, _P, _P, _I64, _P, _P],

@@ -74,8 +74,11 @@ class FusedTrainStep:
             e.set_batch(o, d, c, g)
 
     def get_train_loss_dict(self, step: int):
-        ray_bundle, batch = self.datamanager.next_train(step)
-        self._load(ray_bundle, batch)
+        if hasattr(self.datamanager, "fill_engine"):  # data.device_pipeline.DeviceRayPipeline: batch made on the device,
+            self.datamanager.fill_engine(self.engine)  # written straight into the step's input buffers
+        else:
+            ray_bundle, batch = self.datamanager.next_train(step)
+            self._load(ray_bundle, batch)
         e = self.engine
         losses = e.step()
         c = self.model.config

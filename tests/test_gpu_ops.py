@@ -355,6 +355,38 @@ def test_cameras_generate_rays_reference_signature(F, golden):
     assert torch.equal(flat.nears.cpu()[ho][:, 0], to[ho]) and bool((flat.nears.cpu()[~ho] == 1e10).all())
 
 
+def test_device_ray_pipeline(F, golden):
+    """pixel sampling + colour lookup + ray generation in one launch over a uint8 image cache in HBM, against
+    the reference's arithmetic: indices = (rand * [C,H,W]).long() (data/pixel_samplers.py:168-171), image[c,y,x] / 255
+    (get_image_float32), rays = RayGenerator on those indices (bit-identical to the ray-generation kernel)."""
+    from nerfstudio_b200.cameras.cameras import Cameras
+    from nerfstudio_b200.data.device_pipeline import DeviceRayPipeline
+
+    g = golden("raygen")
+    torch.manual_seed(31)
+    C_, H, W = 5, 37, 53
+    images = torch.randint(0, 256, (C_, H, W, 4), dtype=torch.uint8)  # RGBA cache: alpha ignored
+    cams = Cameras(cu(g["c2w"]), cu(g["fx"]), cu(g["fy"]), cu(g["cx"]), cu(g["cy"]), distortion_params=cu(g["dist"]))
+    pipe = DeviceRayPipeline(cams, images.cuda(), num_rays_per_batch=4096)
+    u = torch.rand(4096, 3)
+    u[0] = torch.tensor([0.0, 0.0, 0.0])
+    u[1] = torch.tensor([1.0 - 2 ** -24] * 3)
+    bundle, batch = pipe.sample(u.cuda())
+    idx = (u * torch.tensor([C_, H, W])).long()
+    assert torch.equal(batch["indices"].cpu(), idx)
+    assert torch.equal(batch["image"].cpu(), images[idx[:, 0], idx[:, 1], idx[:, 2], :3].float() / 255.0)
+    ref = F.generate_rays(cu(g["c2w"]), cams.intrinsics(), cu(g["dist"]), idx.cuda())
+    assert torch.equal(bundle.origins, ref["origins"]) and torch.equal(bundle.directions, ref["directions"])
+    assert torch.equal(bundle.pixel_area, ref["pixel_area"]) and torch.equal(bundle.camera_indices, ref["camera_indices"])
+    # a cached SUBSET of the cameras: indices are corrected to absolute camera ids (pixel_samplers.py:312)
+    sub = DeviceRayPipeline(cams, images[:2].cuda(), 64, image_idx=torch.tensor([4, 2]))
+    b2, batch2 = sub.sample(u[:64].cuda())
+    local = (u[:64, 0] * 2).long()
+    assert torch.equal(batch2["indices"][:, 0].cpu(), torch.tensor([4, 2])[local])
+    rb, bt = pipe.next_train(0)
+    assert rb.origins.shape == (4096, 3) and bt["image"].shape == (4096, 3) and float(bt["image"].max()) <= 1.0
+
+
 # ------------------------------------------------------------------------------------------------
 def test_packed_path_vs_oracle(F):
     torch.manual_seed(7)
@@ -411,6 +443,35 @@ def test_occgrid_march_bit_exact_vs_oracle(F):
     # empty grid -> no samples
     ri, ts, te = F.occgrid_march(o.cuda(), d.cuda(), torch.zeros_like(binaries).cuda(), aabb.tolist(), 0.05)
     assert ri.numel() == 0
+
+
+def test_occgrid_march_full_size_warp_equals_serial(F):
+    """BASELINE config 2 geometry (128^3 x 4 levels, aabb +-1.5, step = diag/1000, cone_angle 0.004, 4096 rays, sphere
+    occupancy): the warp-per-ray march emits exactly the serial march's samples (which is bit-exact vs the oracle)."""
+    from nerfstudio_b200 import lib
+    from nerfstudio_b200.scene import sphere_scene_rays
+
+    torch.manual_seed(9)
+    res, levels = 128, 4
+    idx = torch.stack(torch.meshgrid([torch.arange(res)] * 3, indexing="ij"), -1).float()
+    binaries = torch.zeros(levels, res, res, res, dtype=torch.bool)
+    for lvl in range(levels):
+        c = ((idx + 0.5) / res * 2 - 1) * 1.5 * 2 ** lvl
+        binaries[lvl] = c.norm(dim=-1) < 0.55
+    rays, _ = sphere_scene_rays(4096, seed=3)
+    o, d = rays["origins"].cuda(), rays["directions"].cuda()
+    step = (3 * 3.0 ** 2) ** 0.5 / 1000
+    jit = torch.rand(4096).cuda()
+    outs = []
+    for mode in (0, 1):
+        try:
+            assert lib.tune("march_warp", mode)
+            outs.append(F.occgrid_march(o, d, binaries.cuda(), [-1.5] * 3 + [1.5] * 3, step, 0.05, 1e3, 0.004, jit))
+        finally:
+            lib.tune("march_warp", 1)
+    assert outs[0][0].numel() > 10000
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
 
 
 def test_scan_counts(F):

@@ -443,6 +443,40 @@ def run_b200(args) -> None:
                 e1.record()
                 torch.cuda.synchronize()
                 dense_ms[f"b2n_density_field_bwd[n={RAYS_PER_GPU * engine.S[lvl]}]"] = e0.elapsed_time(e1) / 5
+    # ---- full-image eval path: 1920x1080 frame through the graph-captured chunk loop, rays generated on the
+    # device, chunks sharded over the ranks; ms per frame with CUDA events (median of 3), max over ranks
+    eval_line = None
+    if engine is not None and not args.no_eval:
+        from nerfstudio_b200.cameras.cameras import Cameras
+        from nerfstudio_b200.render_engine import NerfactoRender
+
+        Hh, Ww = 1080, 1920
+        c2w = torch.eye(4, device=dev)[:3][None].clone()
+        c2w[0, :, 3] = torch.tensor([0.0, 0.0, 1.2], device=dev)
+        cams = Cameras(c2w, torch.tensor([1200.0], device=dev), torch.tensor([1200.0], device=dev),
+                       torch.tensor([Ww / 2], device=dev), torch.tensor([Hh / 2], device=dev),
+                       width=torch.tensor([Ww], device=dev), height=torch.tensor([Hh], device=dev))
+        model.eval()
+        ren = NerfactoRender(model, chunk_rays=1 << 15, mlp_backend=args.mlp)
+        ren.render_camera(cams, 0, shard=world > 1)  # warm-up + graph capture
+        frame_ms = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            img = ren.render_camera(cams, 0, shard=world > 1)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            frame_ms.append(float(t.item()))
+        model.train()
+        fm = sorted(frame_ms)[1]
+        eval_line = {"frame": "1920x1080, one perspective camera, 32768-ray chunks (eval_num_rays_per_chunk)", "ms_per_frame": fm,
+                     "fps": 1e3 / fm, "rays_per_sec": Hh * Ww / (fm * 1e-3), "frames_ms": frame_ms,
+                     "finite": bool(torch.isfinite(img["rgb"]).all().item()),
+                     "through": "render_engine.NerfactoRender.render_camera (Model.get_outputs_for_camera surface)"}
     sampler.stop()
     if rank != 0:
         return
@@ -529,7 +563,7 @@ def run_b200(args) -> None:
         "data_dependent_kernels": {"fraction_of_samples_with_gradient": scatter_frac or None, "ms_in_dense_gradient_regime": dense_ms or None,
                                    "note": "density_field_bwd skips warps whose samples all have zero d_density (exact zeros from the "
                                            "interlevel loss); kernel_ms_per_step is the regime of the timed windows"},
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "eval_render": eval_line,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
                 "through": ("FusedTrainStep.train_iteration(step): the reference's Trainer.train_iteration / "
@@ -690,6 +724,7 @@ def main() -> None:
                     help="nerfacto = BASELINE configs[2], the metric's workload (default); ngp = configs[1] (instant-ngp)")
     ap.add_argument("--windows", type=int, default=3, help="timed windows of exactly --steps steps each (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eval", action="store_true", help="skip the full-image eval-render measurement")
     ap.add_argument("--mlp", default="auto", choices=["auto", "tc", "simt"],
                     help="tiny-MLP kernels of the graph/eager engine: tcgen05 3xTF32 (tc) or fp32 SIMT")
     ap.add_argument("--unfused-proposals", action="store_true", help="proposal networks as separate grid/MLP launches")

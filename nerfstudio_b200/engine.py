@@ -47,7 +47,7 @@ class _Net:
         m = self.spec.struct(self.weights, self.biases)
         g = B2nMlpGrad()
         for i, (w, b) in enumerate(zip(self.weights, self.biases)):
-            g.dw[i], g.db[i] = ptr(w.grad).value, ptr(b.grad).value
+            g.dw[i], g.db[i] = ptr(w.grad).value, ptr(b.grad).value  # NULL when there is no optimiser (render engine)
         return m, g
 
 
@@ -57,25 +57,27 @@ class NerfactoStep:
     def __init__(self, model: NerfactoModel, n_rays: int, lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-15,
                  lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
                  always_update_proposals: bool = False, mlp_backend: str = "auto",
-                 fused_proposals: bool = True) -> None:
+                 fused_proposals: bool = True, eval_mode: bool = False) -> None:
         cfg = model.config
         if cfg.implementation != "torch":
             raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
         if cfg.use_same_proposal_network or cfg.num_proposal_iterations != 2:
             raise NotImplementedError("captured step: two separate proposal networks (the nerfacto default)")
         self.model, self.cfg, self.R = model, cfg, n_rays
-        self.optim = FlatAdam(model, lr=lr, betas=betas, eps=eps, lr_schedule=lr_schedule)
+        # eval_mode (render_engine.NerfactoRender): forward only, deterministic samplers, no optimiser / gradient buffers
+        self.eval_mode = eval_mode
+        self.optim = None if eval_mode else FlatAdam(model, lr=lr, betas=betas, eps=eps, lr_schedule=lr_schedule)
         self.allreduce, self.use_graph = allreduce, use_graph
         # the proposal networks' segment of the flat buffer (FlatAdam groups parameters by Model.get_param_groups()).
         # When it is the tail of the buffer the gradient all-reduce is split there (field segment summed while the
         # proposal backward still runs); any other layout gets ONE all-reduce after the whole backward — never a
         # collective over memory the proposal backward is still accumulating into.
-        seg = self.optim.segment_of("proposal_networks")
-        total = self.optim.flat.numel()
+        seg = self.optim.segment_of("proposal_networks") if self.optim is not None else None
+        total = self.optim.flat.numel() if self.optim is not None else 0
         self.grad_split = seg[0] if seg is not None and seg[1] == total and seg[0] > 0 else None
         self._prop_steps = 0  # optimiser steps the proposal group has taken (its own bias-correction count)
         self.always_update = always_update_proposals
-        dev = self.optim.flat.device
+        dev = next(model.parameters()).device
         self.dev = dev
         self.S = list(cfg.num_proposal_samples_per_ray) + [cfg.num_nerf_samples_per_ray]
         self.props = [_Net(p.encoding, p.mlp_base[1]) for p in model.proposal_networks]
@@ -116,7 +118,8 @@ class NerfactoStep:
         self.origins = self.inputs[2 * R: 5 * R].view(R, 3)
         self.directions = self.inputs[5 * R: 8 * R].view(R, 3)
         self.gt = self.inputs[8 * R: 11 * R].view(R, 3)
-        self.nears = torch.full((R,), float(cfg.near_plane), **f32)
+        # NearFarCollider (scene_colliders.py:169-191): the near plane is reset to 0 outside training
+        self.nears = torch.full((R,), 0.0 if eval_mode else float(cfg.near_plane), **f32)
         self.fars = torch.full((R,), float(cfg.far_plane), **f32)
         # [lr/bc1, 1/sqrt(bc2), grad_scale, anneal | the same three for the proposal group's own step count, pad]
         self.hyper = torch.zeros(8, **f32)
@@ -154,6 +157,8 @@ class NerfactoStep:
         self.d_w_dist = torch.zeros(R, self.S[2], **f32)
         self.rgb_out, self.d_rgb_out = torch.zeros(R, 3, **f32), torch.zeros(R, 3, **f32)
         self.acc, self.depth_exp, self.depth_med = torch.zeros(R, **f32), torch.zeros(R, **f32), torch.zeros(R, **f32)
+        self.prop_depth = [torch.zeros(R, **f32) for _ in range(2)]  # median depth of the proposal levels (eval outputs)
+        self.emb_mean = torch.zeros(1, max(self.n_emb, 1), **f32)    # eval: mean appearance embedding (or zeros)
         self.rows = [torch.zeros(R, **f32) for _ in range(3)]
         self.losses = torch.zeros(4, **f32)  # rgb, interlevel, distortion, total
         self.jitter = [torch.zeros(R, 1, **f32) for _ in range(3)]
@@ -251,32 +256,33 @@ class NerfactoStep:
              ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
              self.avg, ptr(self.d_dens[lvl]), ptr(net.table.grad), stream())
 
-    def _body(self, update_props: bool) -> None:
+    def _forward(self) -> None:
+        """Rays in the static buffers -> samples of the three levels, densities, weights, colours, rendered outputs.
+        Training: stratified samplers, per-camera appearance embedding.  Eval: deterministic samplers
+        (ray_samplers.py:326-330), the mean embedding (or zeros), eval-mode compositing (renderers.py:225-231) and the
+        proposal levels' median depths (models/nerfacto.py:346-347)."""
         R, S0, S1, S2 = self.R, *self.S
-        cfg = self.cfg
         st = stream
-        self.optim.flat_grad.zero_()
-        self.losses.zero_()
-        if self.fixed_jitter is None:
-            for j in self.jitter:
-                j.copy_(torch.rand(R, 1, device=self.dev))
-        else:  # tests: replay recorded stratified draws
-            for j, src in zip(self.jitter, self.fixed_jitter):
-                j.copy_(src)
+        ev = self.eval_mode
         if self.tma_weights:
             self._pack_weights()
         # ---------------- forward: proposal sampling
-        call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), ptr(self.jitter[0]), 0, R, S0,
+        call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), NULL if ev else ptr(self.jitter[0]), 0, R, S0,
              lib.SPACING[self.spacing], ptr(self.sb[0]), ptr(self.eb[0]), st())
         if self.fixed_bins is not None:
             self.sb[0].copy_(self.fixed_bins[0][0]), self.eb[0].copy_(self.fixed_bins[0][1])
         for lvl in (0, 1):
             self._density_net_fwd(lvl, self.props[lvl])
-            call("b2n_pdf_sample", ptr(self.sb[lvl]), ptr(self.w[lvl]), ptr(self.u_base[lvl]), ptr(self.jitter[lvl + 1]), 0,
+            call("b2n_pdf_sample", ptr(self.sb[lvl]), ptr(self.w[lvl]), ptr(self.u_base[lvl]),
+                 NULL if ev else ptr(self.jitter[lvl + 1]), 0,
                  ptr(self.nears), ptr(self.fars), R, self.S[lvl], self.S[lvl + 1] + 1, 1.0, _off(self.hyper, 3), 0.01, 1e-5,
                  lib.SPACING[self.spacing], ptr(self.sb[lvl + 1]), ptr(self.eb[lvl + 1]), NULL, NULL, st())
             if self.fixed_bins is not None:  # staged parity tests: every level sees the reference's recorded samples
                 self.sb[lvl + 1].copy_(self.fixed_bins[lvl + 1][0]), self.eb[lvl + 1].copy_(self.fixed_bins[lvl + 1][1])
+            if ev:
+                eb = self.eb[lvl]
+                call("b2n_composite_fwd", NULL, ptr(self.w[lvl]), ptr(eb), _off(eb, 1), self.S[lvl] + 1, R, self.S[lvl],
+                     lib.BG_NONE, NULL, 0, NULL, NULL, NULL, ptr(self.prop_depth[lvl]), NULL, st())
         # ---------------- forward: main field
         N2 = R * S2
         eb2 = self.eb[2]
@@ -289,8 +295,14 @@ class NerfactoStep:
         bw = self.h[2].shape[1]
         call("b2n_density_act_fwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), N2, self.avg, ptr(self.dens[2]), st())
         call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), st())
-        call("b2n_head_input_fwd", ptr(self.sh), self.n_sh, ptr(self.h[2]), bw, self.geo, ptr(self.emb), ptr(self.cams, torch.int64),
-             self.n_emb, 1 if self.emb is not None else 0, R, S2, ptr(self.hin), self.hin_stride, st())
+        if self.emb is None:
+            emb_ptr, emb_mode = NULL, 0
+        elif ev:  # nerfacto_field.py:250-261: mean embedding (pre-averaged into emb_mean by the caller) or zeros
+            emb_ptr, emb_mode = (ptr(self.emb_mean), 2) if self.model.field.use_average_appearance_embedding else (NULL, 0)
+        else:
+            emb_ptr, emb_mode = ptr(self.emb), 1
+        call("b2n_head_input_fwd", ptr(self.sh), self.n_sh, ptr(self.h[2]), bw, self.geo, emb_ptr, ptr(self.cams, torch.int64),
+             self.n_emb, emb_mode, R, S2, ptr(self.hin), self.hin_stride, st())
         mh = self.head_spec.struct(self.head_w, self.head_b)
         gh = B2nMlpGrad()
         for i, (w, b) in enumerate(zip(self.head_w, self.head_b)):
@@ -298,8 +310,26 @@ class NerfactoStep:
         self._mlp_fwd(mh, self.hin, self.hin_stride, N2, self.rgb, self.hid_head, self.head_spec)
         call("b2n_weights_fwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), R, S2, ptr(self.w[2]), st())
         bg_mode, bg_ptr, _keep = F._bg_args(self.bg)
-        call("b2n_composite_fwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2, bg_mode, bg_ptr, 0,
-             ptr(self.rgb_out), ptr(self.acc), ptr(self.depth_exp), ptr(self.depth_med), NULL, st())
+        call("b2n_composite_fwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2, bg_mode, bg_ptr,
+             1 if ev else 0, ptr(self.rgb_out), ptr(self.acc), ptr(self.depth_exp), ptr(self.depth_med), NULL, st())
+        self._fw = (mb, gb, mh, gh, bw, bg_mode, bg_ptr, _keep)
+
+    def _body(self, update_props: bool) -> None:
+        R, S0, S1, S2 = self.R, *self.S
+        cfg = self.cfg
+        st = stream
+        self.optim.flat_grad.zero_()
+        self.losses.zero_()
+        if self.fixed_jitter is None:
+            for j in self.jitter:
+                j.copy_(torch.rand(R, 1, device=self.dev))
+        else:  # tests: replay recorded stratified draws
+            for j, src in zip(self.jitter, self.fixed_jitter):
+                j.copy_(src)
+        self._forward()
+        mb, gb, mh, gh, bw, bg_mode, bg_ptr, _keep = self._fw
+        N2 = R * S2
+        eb2 = self.eb[2]
         # ---------------- losses (+ their gradients)
         call("b2n_mse_fwd_bwd", ptr(self.rgb_out), ptr(self.gt), 3 * R, 1.0, ptr(self.losses), ptr(self.d_rgb_out), st())
         il = cfg.interlevel_loss_mult / float(R * S2)

@@ -244,3 +244,49 @@ def test_packed_batch_equals_set_batch(cuda, golden):
     torch.cuda.synchronize()
     for a, b in zip(ref, (eng.origins, eng.directions, eng.cams, eng.gt)):
         assert torch.equal(a, b)
+
+
+def test_render_engine_matches_golden_eval_and_module_path(cuda, golden):
+    """the graph-captured chunk loop (render_engine.NerfactoRender) vs the reference's recorded eval outputs
+    and vs the module path's chunked `get_outputs_for_camera_ray_bundle`, including a ragged last chunk."""
+    from nerfstudio_b200.render_engine import NerfactoRender
+    from test_gpu_modules import _bundle
+
+    g = golden("nerfacto_pipeline")
+    model = _pipeline_model(g).eval()
+    model.proposal_sampler.set_anneal(1.0)
+    R = g["origins"].shape[0]
+    for chunk, graph in ((R, False), (40, True), (64, True)):  # 96 rays: one chunk / 40+40+16 / 64+32
+        ren = NerfactoRender(model, chunk_rays=chunk, use_graph=graph)
+        out = ren.render_rays(g["origins"].cuda(), g["directions"].cuda(), g["eval_cams"].cuda())
+        assert_close(out["rgb"], g["eval_rgb"], 1e-4, f"rgb chunk={chunk}")
+        assert_close(out["accumulation"], g["eval_acc"], 1e-4)
+        assert_close(out["expected_depth"], g["eval_exp_depth"], 1e-4)
+        same = (out["depth"].cpu() == g["eval_depth"]).float().mean().item()
+        assert same >= 0.97, f"median depth identical on {same:.3f} of rays"
+    rb = _bundle(g["origins"], g["directions"], g["eval_cams"])
+    rb.nears = rb.fars = None
+    with torch.no_grad():
+        mod = model.get_outputs_for_camera_ray_bundle(rb)
+    for k in ("rgb", "accumulation", "depth", "expected_depth", "prop_depth_0", "prop_depth_1"):
+        assert_close(out[k], mod[k], 1e-5, k)
+
+
+def test_render_engine_whole_camera(cuda, golden):
+    """`get_outputs_for_camera`: keep_shape rays from the ray-generation kernel, [H, W, C] outputs, chunked == unchunked."""
+    from nerfstudio_b200.cameras.cameras import Cameras
+    from nerfstudio_b200.render_engine import NerfactoRender
+
+    g = golden("nerfacto_pipeline")
+    model = _pipeline_model(g).eval()
+    H, W = 24, 40
+    c2w = torch.eye(4)[:3][None].repeat(2, 1, 1)
+    c2w[:, :, 3] = torch.tensor([[0.0, 0.0, 1.5], [0.3, -0.2, 1.2]])
+    cams = Cameras(c2w.cuda(), torch.full((2,), 30.0).cuda(), torch.full((2,), 30.0).cuda(), torch.full((2,), W / 2).cuda(),
+                   torch.full((2,), H / 2).cuda(), width=torch.full((2,), W).cuda(), height=torch.full((2,), H).cuda())
+    a = NerfactoRender(model, chunk_rays=H * W, use_graph=False).render_camera(cams, 1)
+    b = NerfactoRender(model, chunk_rays=256, use_graph=True).render_camera(cams, 1)
+    assert a["rgb"].shape == (H, W, 3) and a["depth"].shape == (H, W, 1)
+    for k in a:
+        assert_close(b[k], a[k], 1e-6, k)
+    assert torch.isfinite(a["rgb"]).all() and float(a["accumulation"].max()) <= 1.0 + 1e-5

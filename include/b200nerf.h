@@ -375,6 +375,15 @@ int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, cons
                           int32_t contraction, const float* aabb_host6, float avg_init, const float* d_density,
                           float* dtable, void* stream);
 
+/* same, visiting only the samples with a non-zero d_density: live_ws (int32 [R*S + 1], scratch) receives their count and
+ * indices from a compaction pass.  Every gradient of the proposal field is proportional to d_density, which the interlevel
+ * loss leaves exactly zero wherever the proposal histogram already bounds the final weights. */
+int b2n_density_field_bwd_ws(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                             const float* table, const float* origins, const float* directions, const float* starts,
+                             const float* ends, int64_t bin_stride, int64_t n_rays, int32_t n_samples,
+                             int32_t contraction, const float* aabb_host6, float avg_init, const float* d_density,
+                             float* dtable, int32_t* live_ws, void* stream);
+
 /* ---- tcgen05 self-test (diagnostic; pins the tensor-core operand/TMEM semantics the MLP kernels rely on) -------
  * One 128-row tile.  mode 0: D = A[128][k] * B[n][k]^T (K-major x K-major);  mode 1: D = A[128][k] * W[k][n]
  * (K-major x MN-major);  mode 2: D = A[128][m]^T * B[128][n] (MN-major x MN-major, reduction over the 128 rows).

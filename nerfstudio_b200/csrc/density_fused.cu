@@ -141,6 +141,50 @@ __global__ void __launch_bounds__(DF_THREADS) density_fused_fwd_kernel(const __g
   density[i] = mul_rn(mul_rn(net.avg_init, expf(z2)), sm.sel ? 1.f : 0.f);
 }
 
+// Compaction of the samples that carry a gradient: live[0] = count (zeroed by the caller), live[1 + k] = sample index.
+// A block owns 4096 consecutive samples and appends its survivors in order (one atomic per block reserves the range), so
+// consecutive list entries are mostly consecutive samples of a ray — what the run-length scatter of the backward wants.
+__global__ void __launch_bounds__(1024) live_compact_kernel(const float* __restrict__ d_density, int64_t n,
+                                                            int32_t* __restrict__ live) {
+  __shared__ int warp_cnt[32];
+  __shared__ int block_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i0 = ((int64_t)blockIdx.x * 1024 + threadIdx.x) * 4;
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (i0 + 3 < n) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(d_density + i0));
+    g[0] = q.x, g[1] = q.y, g[2] = q.z, g[3] = q.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = i0 + k < n ? __ldg(d_density + i0 + k) : 0.f;
+  }
+  const int mine = (g[0] != 0.f) + (g[1] != 0.f) + (g[2] != 0.f) + (g[3] != 0.f);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_cnt[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = warp_cnt[lane];
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += v;
+    }
+    warp_cnt[lane] = wi - w;
+    if (lane == 31) block_base = wi > 0 ? atomicAdd(live, wi) : 0;
+  }
+  __syncthreads();
+  int dst = 1 + block_base + warp_cnt[warp] + incl - mine;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (g[k] != 0.f) live[dst++] = (int32_t)(i0 + k);
+}
+
 template <int L, int MODE>
 __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const __grid_constant__ GridParams gp,
                                                                        const __grid_constant__ PosParams pp,
@@ -148,6 +192,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
                                                                        const __grid_constant__ RayGeom rg,
                                                                        const float* __restrict__ table,
                                                                        const float* __restrict__ d_density,
+                                                                       const int32_t* __restrict__ live,
                                                                        float* __restrict__ dtable, float* __restrict__ dw1,
                                                                        float* __restrict__ db1, float* __restrict__ dw2,
                                                                        float* __restrict__ db2) {
@@ -162,7 +207,9 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
   __shared__ float red2[DF_H + 1];
   stage_net(net, ws);
   const int t = threadIdx.x;
-  const int64_t n = rg.n_rays * rg.n_samples;
+  // `live` (optional): live[0] = number of samples with a non-zero gradient, live[1..] = their indices (compacted by
+  // live_compact_kernel, order preserved inside 4096-sample blocks) — the kernel then only visits those
+  const int64_t n = live ? (int64_t)live[0] : rg.n_rays * rg.n_samples;
   const int64_t n_tiles = (n + DF_THREADS * DF_CH - 1) / (DF_THREADS * DF_CH);
   // weight-gradient owners (one register accumulator each, kept across all tiles of the CTA):
   //   t in [0, H*IN) owns dW1[j][c], the next H threads own db1[j]; dW2 / db2 are accumulated per thread
@@ -182,13 +229,15 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
     float xs[DF_CH][3];
 #pragma unroll
     for (int s = 0; s < DF_CH; ++s) {
-      const int64_t i = i0 + s;
+      const int64_t slot = i0 + s;
+      const bool in = slot < n;
+      const int64_t i = !in ? 0 : (live ? (int64_t)live[1 + slot] : slot);
       // Every gradient this kernel produces is proportional to d_density of the sample.  The interlevel loss — the only
       // loss that reaches the proposal networks — is zero wherever the proposal histogram already bounds the final
       // weights, and weights_bwd turns that into exact zeros for whole rays / ray tails, so a warp (32 lanes = samples
       // spaced DF_CH apart, i.e. one ray's neighbourhood) whose samples all have zero gradient skips the re-gather, the
       // network and the staging; a CTA round with no live warp also skips the owners' reduction.
-      const float g = i < n ? __ldg(d_density + i) : 0.f;
+      const float g = in ? __ldg(d_density + i) : 0.f;
       const bool warp_live = __any_sync(0xffffffffu, g != 0.f);
       float dz2 = 0.f;
       if (!warp_live) {
@@ -196,7 +245,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
         for (int j = 0; j < DF_H; ++j) stage[j * CSW + t] = 0.f;  // dz1 = 0: stale encodings in the other columns are harmless
 #pragma unroll
         for (int c = 0; c < IN; ++c) my_denc[s * IN + c] = 0.f;
-      } else if (i < n) {
+      } else if (in) {
         Sample<L> sm;
         encode_sample<L, MODE>(gp, pp, rg, table, i, sm);
         float z1[DF_H];
@@ -317,12 +366,12 @@ static int check_shape(const B2nGrid* g, const B2nMlp* m) {
 
 template <int L, int MODE>
 static void launch_fused_bwd(unsigned grid, cudaStream_t st, const GridParams& gp, const PosParams& pp, const DensityNet& net,
-                             const RayGeom& rg, const float* table, const float* d_density, float* dtable, float* dw1,
-                             float* db1, float* dw2, float* db2) {
+                             const RayGeom& rg, const float* table, const float* d_density, const int32_t* live,
+                             float* dtable, float* dw1, float* db1, float* dw2, float* db2) {
   constexpr size_t smem = sizeof(float) * ((DF_H + 2 * L) * (DF_THREADS + 4) + DF_THREADS * (DF_CH * 2 * L + 1));
   auto kernel = density_fused_bwd_kernel<L, MODE>;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, dtable, dw1, db1, dw2, db2);
+  kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, dtable, dw1, db1, dw2, db2);
 }
 
 #define DF_DISPATCH(KERNEL, ...)                                                          \
@@ -364,11 +413,11 @@ extern "C" int b2n_density_field_fwd(const B2nGrid* grid_host, const B2nMlp* mlp
   B2N_LAUNCH_CHECK();
 }
 
-extern "C" int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
-                                     const float* table, const float* origins, const float* directions,
-                                     const float* starts, const float* ends, int64_t bin_stride, int64_t n_rays,
-                                     int32_t n_samples, int32_t contraction, const float* aabb_host6, float avg_init,
-                                     const float* d_density, float* dtable, void* stream) {
+extern "C" int b2n_density_field_bwd_ws(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                                        const float* table, const float* origins, const float* directions,
+                                        const float* starts, const float* ends, int64_t bin_stride, int64_t n_rays,
+                                        int32_t n_samples, int32_t contraction, const float* aabb_host6, float avg_init,
+                                        const float* d_density, float* dtable, int32_t* live_ws, void* stream) {
   if (n_rays == 0) return B2N_OK;
   B2N_REQUIRE(grid_host && mlp_host && grad_host && table && origins && d_density && dtable, "null pointer");
   B2N_REQUIRE(directions == nullptr || (starts && ends), "ray form needs starts/ends");
@@ -385,7 +434,21 @@ extern "C" int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp
   const int64_t tiles = div_up(n, (int64_t)DF_THREADS * DF_CH);
   const unsigned grid = (unsigned)min(tiles, (int64_t)b2n_sm_count() * 3);
   cudaStream_t st = (cudaStream_t)stream;
-  DF_DISPATCH(launch_fused_bwd, (grid, st, gp, pp, net, rg, table, d_density, dtable, grad_host->dw[0], grad_host->db[0],
-                                 grad_host->dw[1], grad_host->db[1]));
+  if (live_ws != nullptr) {  // visit only the samples that carry a gradient
+    B2N_REQUIRE(n < (int64_t)1 << 31 && (reinterpret_cast<uintptr_t>(d_density) & 15) == 0, "live compaction: n < 2^31, aligned d_density");
+    cudaMemsetAsync(live_ws, 0, sizeof(int32_t), st);
+    live_compact_kernel<<<(unsigned)div_up(n, 4096), 1024, 0, st>>>(d_density, n, live_ws);
+  }
+  DF_DISPATCH(launch_fused_bwd, (grid, st, gp, pp, net, rg, table, d_density, live_ws, dtable, grad_host->dw[0],
+                                 grad_host->db[0], grad_host->dw[1], grad_host->db[1]));
   B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                                     const float* table, const float* origins, const float* directions,
+                                     const float* starts, const float* ends, int64_t bin_stride, int64_t n_rays,
+                                     int32_t n_samples, int32_t contraction, const float* aabb_host6, float avg_init,
+                                     const float* d_density, float* dtable, void* stream) {
+  return b2n_density_field_bwd_ws(grid_host, mlp_host, grad_host, table, origins, directions, starts, ends, bin_stride, n_rays,
+                                  n_samples, contraction, aabb_host6, avg_init, d_density, dtable, nullptr, stream);
 }

@@ -100,6 +100,8 @@ class NerfactoStep:
 
         self.tc_net = {id(sp): use_tc(sp) for sp in specs}
         self._tc_ws: Dict[int, Tensor] = {}
+        self._live_ws: Dict[int, Tensor] = {}
+        self.compact_live = True  # proposal backward visits only the samples whose density gradient is non-zero
         self.tma_weights = True  # stage the tensor-core MLP weights by TMA from a per-step packed image
         self.fused_props = fused_proposals and all(F.density_field_supported(p_.grid, p_.spec) for p_ in self.props)
         self.tc = use_tc(self.head_spec)
@@ -252,9 +254,12 @@ class NerfactoStep:
         net, R, S, eb = self.props[lvl], self.R, self.S[lvl], self.eb[lvl]
         m, g = net.structs()
         box = lib.host_floats(self.aabb)
-        call("b2n_density_field_bwd", C.byref(net.grid.c), C.byref(m), C.byref(g), ptr(net.table), ptr(self.origins),
+        if lvl not in self._live_ws:
+            self._live_ws[lvl] = torch.zeros(R * S + 4, device=self.dev, dtype=torch.int32)
+        call("b2n_density_field_bwd_ws", C.byref(net.grid.c), C.byref(m), C.byref(g), ptr(net.table), ptr(self.origins),
              ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
-             self.avg, ptr(self.d_dens[lvl]), ptr(net.table.grad), stream())
+             self.avg, ptr(self.d_dens[lvl]), ptr(net.table.grad),
+             ptr(self._live_ws[lvl], torch.int32) if self.compact_live else NULL, stream())
 
     def _forward(self) -> None:
         """Rays in the static buffers -> samples of the three levels, densities, weights, colours, rendered outputs.

@@ -417,7 +417,7 @@ def density_field_forward(grid: GridSpec, spec: MlpSpec, table, weights, biases,
 
 
 def density_field_backward(grid: GridSpec, spec: MlpSpec, table, weights, biases, origins, directions, iv, contraction,
-                           aabb, avg_init: float, d_density: Tensor, dtable: Tensor, dws, dbs) -> None:
+                           aabb, avg_init: float, d_density: Tensor, dtable: Tensor, dws, dbs, compact: bool = True) -> None:
     o, d, ps, pe, stride, R, S = _geom(origins, directions, iv)
     m = spec.struct(weights, biases)
     g = B2nMlpGrad()
@@ -425,9 +425,11 @@ def density_field_backward(grid: GridSpec, spec: MlpSpec, table, weights, biases
         g.dw[i] = ptr(dws[i]).value if dws[i] is not None else None
         g.db[i] = ptr(dbs[i]).value if dbs[i] is not None else None
     box = host_floats(aabb) if aabb is not None else None
-    call("b2n_density_field_bwd", C.byref(grid.c), C.byref(m), C.byref(g), ptr(_c(table)), ptr(o), ptr(d), ps, pe, stride,
+    dd = _c(d_density.float())
+    live = torch.empty(R * S + 4, device=dd.device, dtype=torch.int32) if compact else None  # scratch: count + indices
+    call("b2n_density_field_bwd_ws", C.byref(grid.c), C.byref(m), C.byref(g), ptr(_c(table)), ptr(o), ptr(d), ps, pe, stride,
          R, S, int(contraction), C.cast(box, C.c_void_p) if box is not None else C.c_void_p(0), float(avg_init),
-         ptr(_c(d_density.float())), ptr(dtable), stream())
+         ptr(dd), ptr(dtable), ptr(live, torch.int32), stream())
 
 
 class _DensityFieldFn(torch.autograd.Function):

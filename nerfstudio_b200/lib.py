@@ -98,6 +98,8 @@ _SIGNATURES = {
     "b2n_density_field_fwd": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _F, _P, _P],
     "b2n_density_field_bwd": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _P, _I64, _I64,
                               _I32, _I32, _P, _F, _P, _P, _P],
+    "b2n_density_field_bwd_ws": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _P, _I64, _I64,
+                                 _I32, _I32, _P, _F, _P, _P, _P, _P],
     "b2n_tc_selftest": [_I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b2n_tc_timing": [_I32, _I32, _I32, _P, _P],
     "b2n_adam_step_dev": [_P, _P, _P, _P, _I64, _P, C.c_double, C.c_double, C.c_double, _P],
@@ -181,8 +183,8 @@ def call(name: str, *args) -> None:
         key = name
     elif name == "b2n_density_field_fwd":
         key = f"{name}[n={args[8] * args[9]}]"
-    elif name == "b2n_density_field_bwd":
-        key = f"{name}[n={args[9] * args[10]}]"
+    elif name in ("b2n_density_field_bwd", "b2n_density_field_bwd_ws"):
+        key = f"b2n_density_field_bwd[n={args[9] * args[10]}]"
     elif name in _N_ARG and name.startswith("b2n_mlp"):
         m = args[0]._obj  # byref(B2nMlp): two networks of one model may share n (base / colour head)
         key = f"{name.replace('_ws', '')}[n={args[_N_ARG[name]]},in={m.in_dim},out={m.out_dims[m.n_layers - 1]}]"

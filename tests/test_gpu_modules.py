@@ -451,6 +451,20 @@ def test_fused_density_field_equals_unfused_and_golden(cuda, golden):
         gu = torch.autograd.grad(unf, params, dy)
         for n_, a, b in zip(names, gf, gu):
             assert_close(a, b, 2e-5, f"{nm} fused-vs-unfused {n_}")
+        # sparse gradients (what the interlevel loss produces): live-sample compaction == visiting every sample
+        for frac in (0.0, 0.004, 0.12):
+            dy = torch.randn_like(fused) * (torch.rand_like(fused) < frac)
+            outs = []
+            for compact in (True, False):
+                dtable = torch.zeros_like(f.encoding.hash_table)
+                dws, dbs = [torch.zeros_like(w) for w in ws], [torch.zeros_like(b) for b in bs]
+                F.density_field_backward(f.encoding.grid, net.spec, f.encoding.hash_table, ws, bs, o, d, iv, con, aabb, 0.01,
+                                         dy, dtable, dws, dbs, compact=compact)
+                outs.append([dtable] + dws + dbs)
+            for a, b in zip(*outs):
+                assert_close(a, b, 2e-5, f"{nm} compact-vs-full frac={frac}") if float(b.abs().max()) > 0 else None
+                if frac == 0.0:
+                    assert float(a.abs().max()) == 0.0
 
 
 def test_instant_ngp_model_trains(cuda):

@@ -385,7 +385,7 @@ def run_b200(args) -> None:
 
     # warm-up: at least the requested steps, and always up to the fixed training state STATE_STEP (also warms NCCL's
     # channels at N > 1: the driver asks for only 5 warm-up steps)
-    n_warm = max(args.warmup, 3, STATE_STEP)
+    n_warm = max(args.warmup, 3, args.state_step)
     for i in range(n_warm):
         step_resident(i)
     lib.LAUNCHES = 0
@@ -724,6 +724,8 @@ def main() -> None:
                     help="nerfacto = BASELINE configs[2], the metric's workload (default); ngp = configs[1] (instant-ngp)")
     ap.add_argument("--windows", type=int, default=3, help="timed windows of exactly --steps steps each (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--state-step", type=int, default=STATE_STEP,
+                    help="optimisation step at which the timed windows start (profiling runs under ncu use a small value)")
     ap.add_argument("--no-eval", action="store_true", help="skip the full-image eval-render measurement")
     ap.add_argument("--mlp", default="auto", choices=["auto", "tc", "simt"],
                     help="tiny-MLP kernels of the graph/eager engine: tcgen05 3xTF32 (tc) or fp32 SIMT")

@@ -160,6 +160,13 @@ int b2n_positions_fwd(const float* origins, const float* directions, const float
                       int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,
                       const float* aabb_host6, float* x_out, uint8_t* sel_out, void* stream);
 
+/* backward of the ray form: dx [R*S,3] (gradient w.r.t. x_out) -> d_origins [R,3], d_directions [R,3] (overwritten; either
+ * may be NULL), through the selector, the normalisation and the L-inf contraction's Jacobian.  Carries the photometric
+ * gradient to CameraOptimizer's pose corrections (cameras/camera_optimizers.py:148-153). */
+int b2n_positions_bwd(const float* origins, const float* directions, const float* starts, const float* ends,
+                      int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,
+                      const float* aabb_host6, const float* dx, float* d_origins, float* d_directions, void* stream);
+
 /* density = avg_init * exp(h) * sel, bwd: dh = g * avg_init * exp(clamp(h,-15,15)) * sel
  *   field_components/activations.py:28-41; fields/nerfacto_field.py:226-232.  h has row stride h_stride. */
 int b2n_density_act_fwd(const float* h, int64_t h_stride, const uint8_t* sel, int64_t n, float avg_init,

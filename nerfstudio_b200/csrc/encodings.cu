@@ -240,3 +240,79 @@ extern "C" int b2n_density_act_bwd(const float* h, int64_t h_stride, const uint8
   density_act_bwd_kernel<<<(unsigned)div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(h, h_stride, sel, g, n, avg_init, dh, dh_stride);
   B2N_LAUNCH_CHECK();
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// positions backward: d loss / d x (unit-cube sample positions, [R*S,3]) -> d origins [R,3], d directions [R,3].
+// x = sel * N(C(o + d t)) with t = (start + end)/2, C = L-inf scene contraction (identity inside the unit ball,
+// (2 - 1/m) p/m outside, m = |p|_inf: spatial_distortions.py:66-69), N = (x + 2)/4 or the aabb normalisation.  This is the
+// link that carries the photometric gradient back to the camera optimiser's pose corrections
+// (camera_optimizers.py:148-153) and what the reference's autograd does through Frustums.get_positions (rays.py:50-59).
+// One warp per ray: lanes stride over the samples, shuffle-reduce, one store per ray (no atomics).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) positions_bwd_kernel(const __grid_constant__ PosParams pp, const float* __restrict__ origins,
+                                                            const float* __restrict__ directions,
+                                                            const float* __restrict__ starts, const float* __restrict__ ends,
+                                                            int64_t bin_stride, int64_t n_rays, int n_samples,
+                                                            const float* __restrict__ dx, float* __restrict__ d_origins,
+                                                            float* __restrict__ d_directions) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rays) return;
+  float o[3], d[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) o[a] = __ldg(origins + 3 * r + a), d[a] = __ldg(directions + 3 * r + a);
+  float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+  for (int s = lane; s < n_samples; s += 32) {
+    const float t = 0.5f * (__ldg(starts + r * bin_stride + s) + __ldg(ends + r * bin_stride + s));
+    float p[3], q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) p[a] = fmaf(d[a], t, o[a]), q[a] = p[a];
+    if (!unit_cube_point(pp, q)) continue;  // x was multiplied by the selector: no gradient outside (0,1)^3
+    float g[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g[a] = __ldg(dx + 3 * (r * n_samples + s) + a);
+    if (pp.contraction) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) g[a] *= 0.25f;
+      const float ax = fabsf(p[0]), ay = fabsf(p[1]), az = fabsf(p[2]);
+      const float m = fmaxf(ax, fmaxf(ay, az));
+      if (!(m < 1.f)) {
+        const int k = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);  // first maximal component, as torch's max
+        const float inv = 1.f / m, c = (2.f - inv) * inv, dc = 2.f * inv * inv * (inv - 1.f);  // c(m) = 2/m - 1/m^2
+        const float dot = p[0] * g[0] + p[1] * g[1] + p[2] * g[2];
+        const float sgn = p[k] < 0.f ? -1.f : 1.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) g[a] *= c;
+        g[k] += sgn * dc * dot;
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) g[a] /= pp.len[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) go[a] += g[a], gd[a] = fmaf(t, g[a], gd[a]);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    go[a] = warp_sum(go[a]), gd[a] = warp_sum(gd[a]);
+    if (lane == 0) {
+      if (d_origins) d_origins[3 * r + a] = go[a];
+      if (d_directions) d_directions[3 * r + a] = gd[a];
+    }
+  }
+}
+
+extern "C" int b2n_positions_bwd(const float* origins, const float* directions, const float* starts, const float* ends,
+                                 int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,
+                                 const float* aabb_host6, const float* dx, float* d_origins, float* d_directions,
+                                 void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(origins && directions && starts && ends && dx && (d_origins || d_directions), "null pointer");
+  B2N_REQUIRE(contraction || aabb_host6, "aabb required without contraction");
+  PosParams pp;
+  fill_pos_params(pp, contraction, aabb_host6);
+  positions_bwd_kernel<<<(unsigned)div_up(n_rays, 4), 128, 0, (cudaStream_t)stream>>>(
+      pp, origins, directions, starts, ends, bin_stride, n_rays, n_samples, dx, d_origins, d_directions);
+  B2N_LAUNCH_CHECK();
+}

@@ -24,8 +24,12 @@ def unit_cube_points(ray_samples, spatial_distortion, aabb: Tensor) -> Tuple[Ten
     o, d, iv = ray_form(ray_samples)
     if spatial_distortion is None or (isinstance(spatial_distortion, SceneContraction) and spatial_distortion.is_linf) \
             or _is_reference_linf(spatial_distortion):
-        x, sel = F.positions_to_unit_cube(o, d, iv, spatial_distortion is not None,
-                                          aabb.flatten().tolist() if spatial_distortion is None else None)
+        box = aabb.flatten().tolist() if spatial_distortion is None else None
+        if torch.is_grad_enabled() and (o.requires_grad or d.requires_grad):
+            # rays that carry a gradient (behind the camera optimiser's pose correction): positions stay differentiable
+            x, sel = F.positions_to_unit_cube_diff(o, d, iv, spatial_distortion is not None, box)
+        else:
+            x, sel = F.positions_to_unit_cube(o, d, iv, spatial_distortion is not None, box)
         return x, sel, iv.R, iv.S
     # any other distortion module: evaluate it with its own torch ops, then normalise/select in the kernel
     pos = o[:, None, :] + d[:, None, :] * ((iv.starts() + iv.ends()) / 2)[..., None]
@@ -49,6 +53,7 @@ class Field(nn.Module):
         super().__init__()
         self._sample_locations = None
         self._density_before_activation = None
+        self._want_position_grad = False
 
     def density_fn(self, positions: Tensor, times: Optional[Tensor] = None) -> Tensor:
         """Density at raw positions [..., 3] -> [..., 1] (occupancy grid / proposal sampler hook)."""
@@ -67,13 +72,30 @@ class Field(nn.Module):
         raise NotImplementedError
 
     def get_normals(self) -> Tensor:
-        raise NotImplementedError("analytic normals need d(density)/d(position); not on the BASELINE path "
-                                  "(predict_normals defaults to False: models/nerfacto.py:119)")
+        """-normalize(d density_before_activation / d sample_locations) (fields/base_field.py:80-102).  The position
+        gradient runs through the kernels' own backward: `mlp_bwd` (d input) and `hashgrid_bwd` (d x)."""
+        assert self._sample_locations is not None, "Sample locations must be set before calling get_normals."
+        assert self._density_before_activation is not None, "Density must be set before calling get_normals."
+        assert self._sample_locations.shape[:-1] == self._density_before_activation.shape[:-1], (
+            "Sample locations and density must have the same shape besides the last dimension.")
+        normals = torch.autograd.grad(self._density_before_activation, self._sample_locations,
+                                      grad_outputs=torch.ones_like(self._density_before_activation), retain_graph=True)[0]
+        return -torch.nn.functional.normalize(normals, dim=-1)
 
     def forward(self, ray_samples, compute_normals: bool = False) -> Dict:
+        # sample locations only become a differentiable leaf when normals are asked for: the reference marks them
+        # unconditionally (nerfacto_field.py:215-217) and pays for an unused position gradient in every training step
+        self._want_position_grad = bool(compute_normals)
         if compute_normals:
-            self.get_normals()
-        density, density_embedding = self.get_density(ray_samples)
+            with torch.enable_grad():
+                density, density_embedding = self.get_density(ray_samples)
+        else:
+            density, density_embedding = self.get_density(ray_samples)
         outputs = self.get_outputs(ray_samples, density_embedding=density_embedding)
         outputs[FieldHeadNames.DENSITY] = density
+        if compute_normals:
+            with torch.enable_grad():
+                normals = self.get_normals()
+            outputs[FieldHeadNames.NORMALS] = normals.view(*density.shape[:-1], 3)
+        self._want_position_grad = False
         return outputs

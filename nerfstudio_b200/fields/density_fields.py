@@ -51,8 +51,11 @@ class HashMLPDensityField(Field):
         return linf and getattr(net, "_fused", False) and F.density_field_supported(self.encoding.grid, net.spec)
 
     def get_density(self, ray_samples) -> Tuple[Tensor, None]:
-        if self._fused_ok():  # one launch: samples -> unit cube -> grid -> 10->16->1 MLP -> trunc_exp
-            o, d, iv = ray_form(ray_samples)
+        o, d, iv = ray_form(ray_samples)
+        rays_need_grad = torch.is_grad_enabled() and (o.requires_grad or d.requires_grad)
+        # the fused kernel has no position gradient: rays behind a trainable camera optimiser take the unfused kernels,
+        # whose backward carries d x (hashgrid_bwd, mlp_bwd) to positions_bwd and on to the pose corrections
+        if self._fused_ok() and not rays_need_grad:  # one launch: samples -> unit cube -> grid -> 10->16->1 MLP -> trunc_exp
             net = self.mlp_base[1]
             contraction = self.spatial_distortion is not None
             density = F.density_field(self.encoding.grid, net.spec, self.encoding.hash_table,

@@ -67,6 +67,8 @@ class NerfactoField(Field):
         x, sel, R, S = unit_cube_points(ray_samples, self.spatial_distortion, self.aabb)
         assert x.numel() > 0, "positions is empty."
         shape = ray_samples.frustums.shape
+        if getattr(self, "_want_position_grad", False) and not x.requires_grad:
+            x.requires_grad_(True)  # analytic normals: d(density_pre)/d(x) through mlp_bwd (dx) and hashgrid_bwd (dx)
         h = self.mlp_base(x).float()
         density_pre, base_mlp_out = torch.split(h, [1, self.geo_feat_dim], dim=-1)
         self._sample_locations, self._density_before_activation = x, density_pre

@@ -359,6 +359,35 @@ def positions_to_unit_cube(origins: Tensor, directions: Optional[Tensor], ebins:
     return x, sel
 
 
+class _PositionsFn(torch.autograd.Function):
+    """Differentiable ray form of positions_to_unit_cube: gradients w.r.t. x flow to origins / directions (used when the
+    rays carry a gradient, i.e. behind CameraOptimizer.apply_to_raybundle)."""
+
+    @staticmethod
+    def forward(ctx, origins, directions, iv, contraction, aabb):
+        x, sel = positions_to_unit_cube(origins.detach(), directions.detach(), iv, contraction, aabb)
+        ctx.iv, ctx.contraction, ctx.aabb = iv, contraction, aabb
+        ctx.save_for_backward(origins.detach(), directions.detach())
+        ctx.mark_non_differentiable(sel)
+        return x, sel
+
+    @staticmethod
+    def backward(ctx, dx, _dsel):
+        o, d = ctx.saved_tensors
+        iv = ctx.iv
+        o, d = _c(o.float()), _c(d.float())
+        d_o, d_d = torch.empty_like(o), torch.empty_like(d)
+        box = host_floats(ctx.aabb) if ctx.aabb is not None else None
+        call("b2n_positions_bwd", ptr(o), ptr(d), iv.p_starts, iv.p_ends, iv.stride, iv.R, iv.S, int(ctx.contraction),
+             C.cast(box, C.c_void_p) if box is not None else C.c_void_p(0), ptr(_c(dx.float())), ptr(d_o), ptr(d_d), stream())
+        return d_o, d_d, None, None, None
+
+
+def positions_to_unit_cube_diff(origins: Tensor, directions: Tensor, ebins, contraction: bool, aabb) -> Tuple[Tensor, Tensor]:
+    iv = ebins if isinstance(ebins, Intervals) else Intervals.from_edges(ebins)
+    return _PositionsFn.apply(origins, directions, iv, contraction, aabb)
+
+
 class _DensityActFn(torch.autograd.Function):
     """density = avg_init * trunc_exp(h) * selector."""
 

@@ -63,6 +63,7 @@ _SIGNATURES = {
     "b2n_freq_fwd": [_P, _I64, _I32, _P, _I32, _I32, _P, _P],
     "b2n_freq_bwd": [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P],
     "b2n_positions_fwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P],
+    "b2n_positions_bwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P],
     "b2n_density_act_fwd": [_P, _I64, _P, _I64, _F, _P, _P],
     "b2n_density_act_bwd": [_P, _I64, _P, _P, _I64, _F, _P, _I64, _P],
     "b2n_spaced_sample": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P, _P],

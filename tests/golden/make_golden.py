@@ -262,6 +262,36 @@ def g_nerfacto_field():
     save("nerfacto_field", **out)
 
 
+def g_normals():
+    """Field.get_normals (fields/base_field.py:80-102): -normalize(d density_before_activation / d sample_locations) through
+    `forward(ray_samples, compute_normals=True)` — the position gradient of the hash grid + base MLP."""
+    torch.manual_seed(17)
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    out = {"aabb": aabb}
+    for name, contraction in (("contract", True), ("aabb", False)):
+        f = NerfactoField(aabb, num_images=8, num_levels=6, base_res=16, max_res=256, log2_hashmap_size=12,
+                          spatial_distortion=SceneContraction(order=float("inf")) if contraction else None,
+                          average_init_density=0.01, implementation="torch")
+        f.eval()
+        with torch.no_grad():
+            f.mlp_base.model[0].hash_table.mul_(300.0)
+        o, d = make_rays(40, 23)
+        rb = bundle(o, d)
+        eb = torch.sort(torch.rand(40, 13) * 3.0 + 0.05, dim=-1).values
+        fo = f(_samples_from_bins(rb, eb), compute_normals=True)
+        raw = torch.autograd.grad(f._density_before_activation, f._sample_locations,
+                                  grad_outputs=torch.ones_like(f._density_before_activation), retain_graph=True)[0]
+        out.update({f"{name}_origins": o, f"{name}_directions": d, f"{name}_cams": rb.camera_indices, f"{name}_ebins": eb,
+                    f"{name}_normals": fo[FieldHeadNames.NORMALS], f"{name}_density": fo[FieldHeadNames.DENSITY],
+                    f"{name}_grad_raw": raw, f"{name}_table": f.mlp_base.model[0].hash_table,
+                    f"{name}_emb": f.embedding_appearance.embedding.weight})
+        for i, l in enumerate(f.mlp_base.model[1].layers):
+            out[f"{name}_wb{i}"], out[f"{name}_bb{i}"] = l.weight, l.bias
+        for i, l in enumerate(f.mlp_head.layers):
+            out[f"{name}_wh{i}"], out[f"{name}_bh{i}"] = l.weight, l.bias
+    save("normals", **out)
+
+
 def g_samplers():
     torch.manual_seed(6)
     out = {}
@@ -509,6 +539,75 @@ def g_pipeline():
     save("nerfacto_pipeline", **out)
 
 
+def g_pipeline_camopt():
+    """nerfacto composition WITH the camera optimiser on (its default: models/nerfacto.py:131, get_outputs :300-301): the
+    SO3xR3 pose corrections move origins / directions, and the photometric + interlevel + distortion losses reach
+    `pose_adjustment` through the sample positions of all three levels (Frustums.get_positions, rays.py:50-59)."""
+    from nerfstudio.cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
+
+    torch.manual_seed(29)
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    con = SceneContraction(order=float("inf"))
+    props = torch.nn.ModuleList([
+        HashMLPDensityField(aabb, hidden_dim=16, num_levels=5, max_res=mr, base_res=16, log2_hashmap_size=12,
+                            spatial_distortion=con, average_init_density=0.01, implementation="torch")
+        for mr in (128, 256)])
+    field = NerfactoField(aabb, num_images=8, num_levels=8, base_res=16, max_res=512, log2_hashmap_size=13,
+                          spatial_distortion=con, average_init_density=0.01, implementation="torch")
+    with torch.no_grad():
+        for p in props:
+            p.encoding.hash_table.mul_(2000.0)
+        field.mlp_base.model[0].hash_table.mul_(1000.0)
+    C, R = 8, 96
+    opt = CameraOptimizer(CameraOptimizerConfig(mode="SO3xR3"), num_cameras=C, device="cpu")
+    with torch.no_grad():
+        opt.pose_adjustment.copy_(torch.randn(C, 6) * 0.02)
+    o, d = make_rays(R, 67)
+    gt = torch.rand(R, 3)
+    props.train(), field.train()
+    sampler = ProposalNetworkSampler(num_nerf_samples_per_ray=12, num_proposal_samples_per_ray=(32, 20),
+                                     num_proposal_network_iterations=2, single_jitter=True)
+    sampler.train()
+    sampler.set_anneal(0.7)
+    rb = bundle(o, d, cam_hi=C, seed=5)
+    opt.apply_to_raybundle(rb)
+    with Recorder() as rec:
+        rs, wl, rsl = sampler(rb, density_fns=[p.density_fn for p in props])
+    fo = field(rs)
+    w = rs.get_weights(fo[FieldHeadNames.DENSITY])
+    wl.append(w), rsl.append(rs)
+    ren = RGBRenderer(background_color="last_sample")
+    ren.train()
+    rgb = ren(rgb=fo[FieldHeadNames.RGB], weights=w)
+    l_rgb = torch.nn.functional.mse_loss(gt, rgb)
+    l_il = interlevel_loss(wl, rsl)
+    l_di = 0.002 * distortion_loss(wl, rsl)
+    reg = {}
+    opt.get_loss_dict(reg)
+    loss = l_rgb + l_il + l_di + reg["camera_opt_regularizer"]
+    out = dict(aabb=aabb, origins=o, directions=d, gt=gt, cams=rb.camera_indices, pose=opt.pose_adjustment, rgb=rgb,
+               loss=loss, loss_rgb=l_rgb, loss_interlevel=l_il, loss_distortion=l_di, regularizer=reg["camera_opt_regularizer"])
+    parts = dict(rgb=l_rgb, interlevel=l_il, distortion=l_di, total=loss)
+    for k, v in parts.items():
+        (gp,) = torch.autograd.grad(v, [opt.pose_adjustment], retain_graph=True)
+        out["g_pose_" + k] = gp
+    for i, rr in enumerate(rsl):
+        out[f"sbins{i}"] = torch.cat([rr.spacing_starts[..., 0], rr.spacing_ends[:, -1:, 0]], -1)
+        out[f"ebins{i}"] = torch.cat([rr.frustums.starts[..., 0], rr.frustums.ends[:, -1:, 0]], -1)
+    for i, r_ in enumerate(rec.rands):
+        out[f"rand{i}"] = r_
+    for j, p in enumerate(props):
+        out[f"p{j}_table"] = p.encoding.hash_table
+        for i, l in enumerate(p.mlp_base[1].layers):
+            out[f"p{j}_w{i}"], out[f"p{j}_b{i}"] = l.weight, l.bias
+    out["f_table"], out["f_emb"] = field.mlp_base.model[0].hash_table, field.embedding_appearance.embedding.weight
+    for i, l in enumerate(field.mlp_base.model[1].layers):
+        out[f"f_wb{i}"], out[f"f_bb{i}"] = l.weight, l.bias
+    for i, l in enumerate(field.mlp_head.layers):
+        out[f"f_wh{i}"], out[f"f_bh{i}"] = l.weight, l.bias
+    save("pipeline_camopt", **out)
+
+
 def g_samplers_extra():
     """The other SpacedSampler subclasses the reference tests (tests/model_components/test_ray_sampler.py:37-86):
     LinearDisparitySampler, SqrtSampler, LogSampler — that test's set-up (10 rays, near 2 / far 4, 15 samples) plus
@@ -591,7 +690,7 @@ def g_camera_opt():
 if __name__ == "__main__":
     torch.set_num_threads(4)
     fns = (g_hash, g_encodings, g_mlp, g_density_field, g_nerfacto_field, g_samplers, g_render, g_losses,
-           g_raygen, g_vanilla, g_pipeline, g_camera_opt, g_samplers_extra, g_aabb_intersect)
+           g_raygen, g_vanilla, g_pipeline, g_camera_opt, g_samplers_extra, g_aabb_intersect, g_normals, g_pipeline_camopt)
     only = set(sys.argv[1:])  # e.g. `python tests/golden/make_golden.py g_camera_opt` regenerates one fixture
     for fn in fns:
         if only and fn.__name__ not in only:

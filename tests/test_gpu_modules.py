@@ -111,6 +111,44 @@ def test_nerfacto_field_module(cuda, golden):
             assert_close(gr, g[f"{nm}_g_{k}"], REL, f"{nm} g_{k}")
 
 
+def test_nerfacto_field_analytic_normals(cuda, golden):
+    """a20 `Field.forward(compute_normals=True)` / `get_normals`: the position gradient of the hash grid + base MLP
+    (hashgrid_bwd dx, mlp_bwd dx) against the reference's autograd, contraction and aabb normalisation."""
+    from nerfstudio_b200.field_components.field_heads import FieldHeadNames
+    from nerfstudio_b200.field_components.spatial_distortions import SceneContraction
+    from nerfstudio_b200.fields.nerfacto_field import NerfactoField
+
+    g = golden("normals")
+    for nm, con in (("contract", True), ("aabb", False)):
+        f = NerfactoField(g["aabb"], num_images=8, num_levels=6, base_res=16, max_res=256, log2_hashmap_size=12,
+                          spatial_distortion=SceneContraction(order=float("inf")) if con else None,
+                          average_init_density=0.01, implementation="torch").eval()
+        sd = {"mlp_base.model.0.hash_table": g[f"{nm}_table"], "embedding_appearance.embedding.weight": g[f"{nm}_emb"]}
+        for i in range(2):
+            sd[f"mlp_base.model.1.layers.{i}.weight"], sd[f"mlp_base.model.1.layers.{i}.bias"] = g[f"{nm}_wb{i}"], g[f"{nm}_bb{i}"]
+        for i in range(3):
+            sd[f"mlp_head.layers.{i}.weight"], sd[f"mlp_head.layers.{i}.bias"] = g[f"{nm}_wh{i}"], g[f"{nm}_bh{i}"]
+        f.load_state_dict(sd, strict=False)
+        f = f.cuda()
+        R = g[f"{nm}_origins"].shape[0]
+        rb = _bundle(g[f"{nm}_origins"], g[f"{nm}_directions"], g[f"{nm}_cams"])
+        rs = rb.samples_from_bins(cu(g[f"{nm}_ebins"]), None, None)
+        with torch.no_grad():  # eval render context: forward re-enables grad for the normals, as the reference does
+            fo = f(rs, compute_normals=True)
+        assert_close(fo[FieldHeadNames.DENSITY], g[f"{nm}_density"], REL, nm)
+        raw = torch.autograd.grad(f._density_before_activation, f._sample_locations,
+                                  grad_outputs=torch.ones_like(f._density_before_activation))[0]
+        assert_close(raw.view(R, -1, 3), g[f"{nm}_grad_raw"], REL, nm + " d density_pre / d x")
+        n = fo[FieldHeadNames.NORMALS]
+        assert n.shape == g[f"{nm}_normals"].shape
+        # unit vectors: compare where the raw gradient is not vanishing (normalising a ~0 vector amplifies round-off)
+        big = g[f"{nm}_grad_raw"].norm(dim=-1) > 1e-3 * g[f"{nm}_grad_raw"].norm(dim=-1).max()
+        assert int(big.sum()) > 0.5 * big.numel()
+        assert float((n.cpu() - g[f"{nm}_normals"])[big].abs().max()) < 1e-3
+        f2 = f(rs)  # plain forward: no position gradient is requested from the kernels
+        assert FieldHeadNames.NORMALS not in f2 and not f._sample_locations.requires_grad
+
+
 def _load_pipeline(model, g):
     sd = {}
     for j in range(2):
@@ -260,6 +298,53 @@ def test_nerfacto_pipeline_staged_levels(cuda, golden):
         # the proposal MLPs' gradients are sums of ~3000 signed terms that cancel to ~1e-6 (|sum| / sum|terms| ~ 1e-2):
         # fp32 summation order alone moves them by 1e-4 of their max-norm in either implementation -> 3e-4 there
         assert_close(gr, g["g_" + k], 3e-4 if (k.startswith("p") and "table" not in k) else REL, "staged g_" + k)
+
+
+def test_camera_optimizer_receives_photometric_gradient(cuda, golden):
+    """a4 with the camera optimiser ON (nerfacto's default): rgb, interlevel and distortion losses reach `pose_adjustment`
+    through the sample positions of all three levels — pose_apply -> positions (positions_bwd: contraction Jacobian) ->
+    hash grids (hashgrid_bwd d x) -> MLPs.  Every level is fed the reference's recorded samples (staged, as in
+    test_nerfacto_pipeline_staged_levels); gradients of each loss term w.r.t. the poses against the reference's autograd."""
+    from nerfstudio_b200.cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
+    from nerfstudio_b200.field_components.field_heads import FieldHeadNames
+    from nerfstudio_b200.model_components.losses import distortion_loss, interlevel_loss
+
+    g = golden("pipeline_camopt")
+    model = _pipeline_model(g).train()
+    opt = CameraOptimizer(CameraOptimizerConfig(mode="SO3xR3"), num_cameras=8, device="cuda")
+    with torch.no_grad():
+        opt.pose_adjustment.copy_(cu(g["pose"]))
+    rb = model.collider(_bundle(g["origins"], g["directions"], g["cams"]))
+    opt.apply_to_raybundle(rb)
+    assert rb.origins.requires_grad and rb.directions.requires_grad
+    nets = list(model.proposal_networks) + [model.field]
+    weights_list, samples_list, field_out = [], [], None
+    for i in range(3):
+        rs = rb.samples_from_bins(cu(g[f"ebins{i}"]), cu(g[f"sbins{i}"]), None)
+        if i < 2:
+            density, _ = nets[i].get_density(rs)
+        else:
+            field_out = model.field.forward(rs)
+            density = field_out[FieldHeadNames.DENSITY]
+        weights_list.append(rs.get_weights(density)), samples_list.append(rs)
+    rgb = model.renderer_rgb(rgb=field_out[FieldHeadNames.RGB], weights=weights_list[2])
+    assert_close(rgb, g["rgb"], REL, "rgb behind the pose correction")
+    l_rgb = model.rgb_loss(cu(g["gt"]), rgb)
+    l_il = interlevel_loss(weights_list, samples_list)
+    l_di = 0.002 * distortion_loss(weights_list, samples_list)
+    reg = {}
+    opt.get_loss_dict(reg)
+    assert_close(l_rgb, g["loss_rgb"], REL), assert_close(l_il, g["loss_interlevel"], REL)
+    assert_close(l_di, g["loss_distortion"], REL), assert_close(reg["camera_opt_regularizer"], g["regularizer"], REL)
+    total = l_rgb + l_il + l_di + reg["camera_opt_regularizer"]
+    for name, term in (("rgb", l_rgb), ("interlevel", l_il), ("distortion", l_di), ("total", total)):
+        (gp,) = torch.autograd.grad(term, [opt.pose_adjustment], retain_graph=True)
+        assert float(g["g_pose_" + name].abs().max()) > 0
+        # sums over ~100 rays x 3 levels of signed position gradients (d feature / d x ~ table scale x resolution)
+        assert_close(gp, g["g_pose_" + name], 1e-3, "d " + name + " / d pose")
+    # parameters still get their gradients on this path (the unfused proposal kernels)
+    gt_table = torch.autograd.grad(total, [model.proposal_networks[0].encoding.hash_table])[0]
+    assert float(gt_table.abs().max()) > 0
 
 
 def test_trainer_step_matches_torch_adam(cuda, golden):

@@ -104,6 +104,11 @@ int b2n_hashgrid_fwd(const B2nGrid* grid_host, const float* x, const float* tabl
 int b2n_hashgrid_bwd(const B2nGrid* grid_host, const float* x, const float* table, const float* dy, int64_t n,
                      float* dtable, float* dx, void* stream);
 
+/* position gradient only: dx [N,3] = d<dy, y>/dx (overwritten), no table scatter — for callers that get dtable from the
+ * run-length scatter of b2n_hashgrid_bwd(dx = NULL) and need d x as well (camera optimiser: positions_bwd -> poses). */
+int b2n_hashgrid_dx(const B2nGrid* grid_host, const float* x, const float* table, const float* dy, int64_t n, float* dx,
+                    void* stream);
+
 /* ---- K3: tiny fused MLP (fp32 SIMT) -----------------------------------------------------------------
  * replaces MLP.pytorch_fwd / tcnn.Network   field_components/mlp.py:110-114,160-184
  * x [N,in] row-major, y [N,out_last].  `hidden` (optional workspace, required for bwd) receives the
@@ -160,12 +165,13 @@ int b2n_positions_fwd(const float* origins, const float* directions, const float
                       int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,
                       const float* aabb_host6, float* x_out, uint8_t* sel_out, void* stream);
 
-/* backward of the ray form: dx [R*S,3] (gradient w.r.t. x_out) -> d_origins [R,3], d_directions [R,3] (overwritten; either
- * may be NULL), through the selector, the normalisation and the L-inf contraction's Jacobian.  Carries the photometric
+/* backward of the ray form: dx [R*S,3] (gradient w.r.t. x_out) -> d_origins [R,3], d_directions [R,3] (overwritten, or
+ * added to when accumulate != 0; either may be NULL), through the selector, the normalisation and the L-inf contraction's Jacobian.  Carries the photometric
  * gradient to CameraOptimizer's pose corrections (cameras/camera_optimizers.py:148-153). */
 int b2n_positions_bwd(const float* origins, const float* directions, const float* starts, const float* ends,
                       int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,
-                      const float* aabb_host6, const float* dx, float* d_origins, float* d_directions, void* stream);
+                      const float* aabb_host6, const float* dx, int32_t accumulate, float* d_origins, float* d_directions,
+                      void* stream);
 
 /* density = avg_init * exp(h) * sel, bwd: dh = g * avg_init * exp(clamp(h,-15,15)) * sel
  *   field_components/activations.py:28-41; fields/nerfacto_field.py:226-232.  h has row stride h_stride. */
@@ -268,6 +274,11 @@ int b2n_pose_apply_fwd(const float* pose_adjustment, const int64_t* camera_indic
 int b2n_pose_apply_bwd(const float* pose_adjustment, const int64_t* camera_indices, const uint8_t* frozen,
                        const float* directions, const float* d_out_origins, const float* d_out_directions,
                        int64_t n_rays, float* d_pose_adjustment, void* stream);
+
+/* CameraOptimizer.get_loss_dict (cameras/camera_optimizers.py:155-162): loss_out[0] += mean_c |t_c| trans_pen + mean_c |w_c|
+ * rot_pen; d_pose_adjustment [C,6] += gscale * its gradient (either output may be NULL). */
+int b2n_pose_regularizer(const float* pose_adjustment, int32_t n_cams, float trans_l2_penalty, float rot_l2_penalty,
+                         float gscale, float* loss_out, float* d_pose_adjustment, void* stream);
 
 /* ---- K7-K12: packed (instant-ngp) path; nerfacc 0.5.2 call sites models/instant_ngp.py:120-198 ----------
  * pack_info: ray_indices int64 [M] sorted -> packed_info int64 [R,2] (start,count). */
@@ -390,6 +401,15 @@ int b2n_density_field_bwd_ws(const B2nGrid* grid_host, const B2nMlp* mlp_host, c
                              const float* ends, int64_t bin_stride, int64_t n_rays, int32_t n_samples,
                              int32_t contraction, const float* aabb_host6, float avg_init, const float* d_density,
                              float* dtable, int32_t* live_ws, void* stream);
+
+/* same with the position gradient: every live sample adds d loss / d (sample position), through the unit-cube map's Jacobian,
+ * to its ray's d_origins [R,3] and (times the sample's mid-point distance) d_directions [R,3] — ACCUMULATED with atomics
+ * (either may be NULL; ray form only).  This is how the interlevel loss reaches CameraOptimizer's pose corrections. */
+int b2n_density_field_bwd_rays(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                               const float* table, const float* origins, const float* directions, const float* starts,
+                               const float* ends, int64_t bin_stride, int64_t n_rays, int32_t n_samples,
+                               int32_t contraction, const float* aabb_host6, float avg_init, const float* d_density,
+                               float* dtable, int32_t* live_ws, float* d_origins, float* d_directions, void* stream);
 
 /* ---- tcgen05 self-test (diagnostic; pins the tensor-core operand/TMEM semantics the MLP kernels rely on) -------
  * One 128-row tile.  mode 0: D = A[128][k] * B[n][k]^T (K-major x K-major);  mode 1: D = A[128][k] * W[k][n]

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(1024) live_compact_kernel(const float* __restr
     if (g[k] != 0.f) live[dst++] = (int32_t)(i0 + k);
 }
 
-template <int L, int MODE>
+template <int L, int MODE, bool DX>
 __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const __grid_constant__ GridParams gp,
                                                                        const __grid_constant__ PosParams pp,
                                                                        const __grid_constant__ DensityNet net,
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
                                                                        const int32_t* __restrict__ live,
                                                                        float* __restrict__ dtable, float* __restrict__ dw1,
                                                                        float* __restrict__ db1, float* __restrict__ dw2,
-                                                                       float* __restrict__ db2) {
+                                                                       float* __restrict__ db2, float* __restrict__ d_origins,
+                                                                       float* __restrict__ d_directions) {
   constexpr int IN = 2 * L;
   constexpr int SC = DF_H + IN;                 // staging columns: dz1[16] | enc[IN], stored column-major
   constexpr int CSW = DF_THREADS + 4;           // column stride (+16 B: columns read together sit in different banks)
@@ -271,6 +272,39 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
           }
         }
         g2[DF_H] += dz2;
+        if constexpr (DX) {
+          // position gradient (camera optimiser): d enc / d x from the 8 corners of every level, through the unit-cube
+          // map's Jacobian, added to the ray's d(origin) and d(direction) (ray form only)
+          if (dz2 != 0.f && rg.directions != nullptr) {
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+              const Corners c = corners_of<MODE>(gp, l, sm.x[0], sm.x[1], sm.x[2]);
+              Vec<2> f[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[k] = ldg_row<2>(table, c.row[k]);
+              float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+              for (int j = 0; j < 2; ++j)
+                blend8_dpos(f[0].v[j], f[1].v[j], f[2].v[j], f[3].v[j], f[4].v[j], f[5].v[j], f[6].v[j], f[7].v[j], c.ox, c.oy,
+                            c.oz, de[2 * l + j], ax, ay, az);
+              const float sc = gp.scale[l];
+              gx = fmaf(ax, sc, gx), gy = fmaf(ay, sc, gy), gz = fmaf(az, sc, gz);
+            }
+            const int64_t r = i / rg.n_samples;
+            const int sidx = (int)(i - r * rg.n_samples);
+            const float tm = 0.5f * (__ldg(rg.starts + r * rg.bin_stride + sidx) + __ldg(rg.ends + r * rg.bin_stride + sidx));
+            float praw[3], gp3[3] = {gx, gy, gz};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) praw[a] = fmaf(__ldg(rg.directions + 3 * r + a), tm, __ldg(rg.origins + 3 * r + a));
+            unit_cube_point_bwd(pp, praw, gp3);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+              if (d_origins) atomicAdd(d_origins + 3 * r + a, gp3[a]);
+              if (d_directions) atomicAdd(d_directions + 3 * r + a, tm * gp3[a]);
+            }
+          }
+        }
 #pragma unroll
         for (int c = 0; c < IN; ++c) stage[(DF_H + c) * CSW + t] = sm.enc[c], my_denc[s * IN + c] = de[c];
 #pragma unroll
@@ -367,11 +401,19 @@ static int check_shape(const B2nGrid* g, const B2nMlp* m) {
 template <int L, int MODE>
 static void launch_fused_bwd(unsigned grid, cudaStream_t st, const GridParams& gp, const PosParams& pp, const DensityNet& net,
                              const RayGeom& rg, const float* table, const float* d_density, const int32_t* live,
-                             float* dtable, float* dw1, float* db1, float* dw2, float* db2) {
+                             float* dtable, float* dw1, float* db1, float* dw2, float* db2, float* d_origins,
+                             float* d_directions) {
   constexpr size_t smem = sizeof(float) * ((DF_H + 2 * L) * (DF_THREADS + 4) + DF_THREADS * (DF_CH * 2 * L + 1));
-  auto kernel = density_fused_bwd_kernel<L, MODE>;
-  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, dtable, dw1, db1, dw2, db2);
+  if (d_origins != nullptr || d_directions != nullptr) {
+    auto kernel = density_fused_bwd_kernel<L, MODE, true>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, dtable, dw1, db1, dw2, db2, d_origins,
+                                           d_directions);
+  } else {
+    auto kernel = density_fused_bwd_kernel<L, MODE, false>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, dtable, dw1, db1, dw2, db2, nullptr, nullptr);
+  }
 }
 
 #define DF_DISPATCH(KERNEL, ...)                                                          \
@@ -413,11 +455,12 @@ extern "C" int b2n_density_field_fwd(const B2nGrid* grid_host, const B2nMlp* mlp
   B2N_LAUNCH_CHECK();
 }
 
-extern "C" int b2n_density_field_bwd_ws(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
-                                        const float* table, const float* origins, const float* directions,
-                                        const float* starts, const float* ends, int64_t bin_stride, int64_t n_rays,
-                                        int32_t n_samples, int32_t contraction, const float* aabb_host6, float avg_init,
-                                        const float* d_density, float* dtable, int32_t* live_ws, void* stream) {
+extern "C" int b2n_density_field_bwd_rays(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                                          const float* table, const float* origins, const float* directions,
+                                          const float* starts, const float* ends, int64_t bin_stride, int64_t n_rays,
+                                          int32_t n_samples, int32_t contraction, const float* aabb_host6, float avg_init,
+                                          const float* d_density, float* dtable, int32_t* live_ws, float* d_origins,
+                                          float* d_directions, void* stream) {
   if (n_rays == 0) return B2N_OK;
   B2N_REQUIRE(grid_host && mlp_host && grad_host && table && origins && d_density && dtable, "null pointer");
   B2N_REQUIRE(directions == nullptr || (starts && ends), "ray form needs starts/ends");
@@ -440,8 +483,18 @@ extern "C" int b2n_density_field_bwd_ws(const B2nGrid* grid_host, const B2nMlp* 
     live_compact_kernel<<<(unsigned)div_up(n, 4096), 1024, 0, st>>>(d_density, n, live_ws);
   }
   DF_DISPATCH(launch_fused_bwd, (grid, st, gp, pp, net, rg, table, d_density, live_ws, dtable, grad_host->dw[0],
-                                 grad_host->db[0], grad_host->dw[1], grad_host->db[1]));
+                                 grad_host->db[0], grad_host->dw[1], grad_host->db[1], d_origins, d_directions));
   B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_density_field_bwd_ws(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,
+                                        const float* table, const float* origins, const float* directions,
+                                        const float* starts, const float* ends, int64_t bin_stride, int64_t n_rays,
+                                        int32_t n_samples, int32_t contraction, const float* aabb_host6, float avg_init,
+                                        const float* d_density, float* dtable, int32_t* live_ws, void* stream) {
+  return b2n_density_field_bwd_rays(grid_host, mlp_host, grad_host, table, origins, directions, starts, ends, bin_stride, n_rays,
+                                    n_samples, contraction, aabb_host6, avg_init, d_density, dtable, live_ws, nullptr, nullptr,
+                                    stream);
 }
 
 extern "C" int b2n_density_field_bwd(const B2nGrid* grid_host, const B2nMlp* mlp_host, const B2nMlpGrad* grad_host,

@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(128) positions_bwd_kernel(const __grid_constan
                                                             const float* __restrict__ directions,
                                                             const float* __restrict__ starts, const float* __restrict__ ends,
                                                             int64_t bin_stride, int64_t n_rays, int n_samples,
-                                                            const float* __restrict__ dx, float* __restrict__ d_origins,
+                                                            const float* __restrict__ dx, int accumulate,
+                                                            float* __restrict__ d_origins,
                                                             float* __restrict__ d_directions) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -265,54 +266,33 @@ __global__ void __launch_bounds__(128) positions_bwd_kernel(const __grid_constan
   float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
   for (int s = lane; s < n_samples; s += 32) {
     const float t = 0.5f * (__ldg(starts + r * bin_stride + s) + __ldg(ends + r * bin_stride + s));
-    float p[3], q[3];
+    float p[3], g[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) p[a] = fmaf(d[a], t, o[a]), q[a] = p[a];
-    if (!unit_cube_point(pp, q)) continue;  // x was multiplied by the selector: no gradient outside (0,1)^3
-    float g[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) g[a] = __ldg(dx + 3 * (r * n_samples + s) + a);
-    if (pp.contraction) {
-#pragma unroll
-      for (int a = 0; a < 3; ++a) g[a] *= 0.25f;
-      const float ax = fabsf(p[0]), ay = fabsf(p[1]), az = fabsf(p[2]);
-      const float m = fmaxf(ax, fmaxf(ay, az));
-      if (!(m < 1.f)) {
-        const int k = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);  // first maximal component, as torch's max
-        const float inv = 1.f / m, c = (2.f - inv) * inv, dc = 2.f * inv * inv * (inv - 1.f);  // c(m) = 2/m - 1/m^2
-        const float dot = p[0] * g[0] + p[1] * g[1] + p[2] * g[2];
-        const float sgn = p[k] < 0.f ? -1.f : 1.f;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) g[a] *= c;
-        g[k] += sgn * dc * dot;
-      }
-    } else {
-#pragma unroll
-      for (int a = 0; a < 3; ++a) g[a] /= pp.len[a];
-    }
+    for (int a = 0; a < 3; ++a) p[a] = fmaf(d[a], t, o[a]), g[a] = __ldg(dx + 3 * (r * n_samples + s) + a);
+    unit_cube_point_bwd(pp, p, g);  // zero outside (0,1)^3: x was multiplied by the selector
 #pragma unroll
     for (int a = 0; a < 3; ++a) go[a] += g[a], gd[a] = fmaf(t, g[a], gd[a]);
   }
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     go[a] = warp_sum(go[a]), gd[a] = warp_sum(gd[a]);
-    if (lane == 0) {
-      if (d_origins) d_origins[3 * r + a] = go[a];
-      if (d_directions) d_directions[3 * r + a] = gd[a];
+    if (lane == 0) {  // this warp is the only writer of ray r in this launch
+      if (d_origins) d_origins[3 * r + a] = accumulate ? d_origins[3 * r + a] + go[a] : go[a];
+      if (d_directions) d_directions[3 * r + a] = accumulate ? d_directions[3 * r + a] + gd[a] : gd[a];
     }
   }
 }
 
 extern "C" int b2n_positions_bwd(const float* origins, const float* directions, const float* starts, const float* ends,
                                  int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,
-                                 const float* aabb_host6, const float* dx, float* d_origins, float* d_directions,
-                                 void* stream) {
+                                 const float* aabb_host6, const float* dx, int32_t accumulate, float* d_origins,
+                                 float* d_directions, void* stream) {
   if (n_rays == 0) return B2N_OK;
   B2N_REQUIRE(origins && directions && starts && ends && dx && (d_origins || d_directions), "null pointer");
   B2N_REQUIRE(contraction || aabb_host6, "aabb required without contraction");
   PosParams pp;
   fill_pos_params(pp, contraction, aabb_host6);
   positions_bwd_kernel<<<(unsigned)div_up(n_rays, 4), 128, 0, (cudaStream_t)stream>>>(
-      pp, origins, directions, starts, ends, bin_stride, n_rays, n_samples, dx, d_origins, d_directions);
+      pp, origins, directions, starts, ends, bin_stride, n_rays, n_samples, dx, accumulate, d_origins, d_directions);
   B2N_LAUNCH_CHECK();
 }

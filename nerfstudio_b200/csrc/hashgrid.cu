@@ -197,6 +197,44 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_kernel(const __grid_constant
   }
 }
 
+// Position gradient only (no table scatter): dx[i] = sum over levels and features of dy * d(encoding)/d(x).  Used by the
+// captured step when the camera optimiser trains (the table gradient goes through the run-length scatter kernel, which
+// has no use for the corner values; this kernel has no use for atomics).  One thread per sample, all levels in-thread.
+template <int F, int MODE>
+__global__ void __launch_bounds__(256) hashgrid_dx_kernel(const __grid_constant__ GridParams gp, const float* __restrict__ x,
+                                                          const float* __restrict__ table, const float* __restrict__ dy,
+                                                          int64_t n, float* __restrict__ dx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float px = __ldg(x + 3 * i), py = __ldg(x + 3 * i + 1), pz = __ldg(x + 3 * i + 2);
+  const float* grow = dy + i * (int64_t)(gp.n_levels * F);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 2
+  for (int l = 0; l < gp.n_levels; ++l) {
+    float g[F];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < F; ++j) g[j] = __ldg(grow + l * F + j), any |= g[j] != 0.f;
+    if (!any) continue;
+    const Corners c = corners_of<MODE>(gp, l, px, py, pz);
+    Vec<F> f[8];
+    if constexpr (F == 2) {
+      gather_corners2(table, c, f);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = ldg_row<F>(table, c.row[k]);
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+    for (int j = 0; j < F; ++j)
+      blend8_dpos(f[0].v[j], f[1].v[j], f[2].v[j], f[3].v[j], f[4].v[j], f[5].v[j], f[6].v[j], f[7].v[j], c.ox, c.oy, c.oz, g[j],
+                  ax, ay, az);
+    const float sc = gp.scale[l];
+    gx = fmaf(ax, sc, gx), gy = fmaf(ay, sc, gy), gz = fmaf(az, sc, gz);
+  }
+  dx[3 * i] = gx, dx[3 * i + 1] = gy, dx[3 * i + 2] = gz;
+}
+
 // Run-length variant of the scatter: a thread walks CH consecutive samples of one level.  Consecutive samples along a
 // ray stay in the same grid cell for many steps at the coarse levels, so the 8 corner contributions are accumulated in
 // registers while the cell does not change and flushed with one vector RED per corner when it does — this removes
@@ -353,6 +391,31 @@ extern "C" int b2n_hashgrid_bwd(const B2nGrid* grid_host, const float* x, const 
     default: B2N_UNSUPPORTED(true, "n_features must be 1, 2, 4 or 8");
   }
 #undef B2N_BWD_CASE
+  B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_hashgrid_dx(const B2nGrid* grid_host, const float* x, const float* table, const float* dy, int64_t n,
+                               float* dx, void* stream) {
+  if (n == 0) return B2N_OK;
+  B2N_REQUIRE(grid_host && x && table && dy && dx, "null pointer");
+  GridParams gp;
+  B2N_REQUIRE(fill_params(grid_host, gp) == 0, "bad grid description");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)div_up(n, 256);
+  const bool tm = gp.mode == B2N_GRID_TORCH;
+#define B2N_DX_CASE(F)                                                                                  \
+  case F:                                                                                               \
+    if (tm) hashgrid_dx_kernel<F, B2N_GRID_TORCH><<<grid, 256, 0, st>>>(gp, x, table, dy, n, dx);      \
+    else hashgrid_dx_kernel<F, B2N_GRID_TCNN><<<grid, 256, 0, st>>>(gp, x, table, dy, n, dx);          \
+    break;
+  switch (grid_host->n_features) {
+    B2N_DX_CASE(1)
+    B2N_DX_CASE(2)
+    B2N_DX_CASE(4)
+    B2N_DX_CASE(8)
+    default: B2N_UNSUPPORTED(true, "n_features must be 1, 2, 4 or 8");
+  }
+#undef B2N_DX_CASE
   B2N_LAUNCH_CHECK();
 }
 

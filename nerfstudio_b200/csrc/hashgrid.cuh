@@ -135,6 +135,19 @@ __device__ __forceinline__ float blend8(float f0, float f1, float f2, float f3, 
   return __fmaf_rn(f0312, oz, __fmul_rn(f4756, rz));
 }
 
+// d(blend8)/d(ox, oy, oz) times g, accumulated into (ax, ay, az): the position gradient of one feature of one level in
+// grid units (multiply by the level's scale for unit-cube units).
+__device__ __forceinline__ void blend8_dpos(float f0, float f1, float f2, float f3, float f4, float f5, float f6, float f7,
+                                            float ox, float oy, float oz, float g, float& ax, float& ay, float& az) {
+  const float rx = 1.f - ox, ry = 1.f - oy, rz = 1.f - oz;
+  const float d03 = f0 - f3, d12 = f1 - f2, d56 = f5 - f6, d47 = f4 - f7;
+  const float f03 = f0 * ox + f3 * rx, f12 = f1 * ox + f2 * rx, f56 = f5 * ox + f6 * rx, f47 = f4 * ox + f7 * rx;
+  const float f0312 = f03 * oy + f12 * ry, f4756 = f47 * oy + f56 * ry;
+  ax += g * ((d03 * oy + d12 * ry) * oz + (d47 * oy + d56 * ry) * rz);
+  ay += g * ((f03 - f12) * oz + (f47 - f56) * rz);
+  az += g * (f0312 - f4756);
+}
+
 // the 8 corner feature rows of one (point, level), F = 2: 4 x 128-bit loads when the x-neighbours are paired
 __device__ __forceinline__ void gather_corners2(const float* __restrict__ table, const Corners& c, Vec<2> (&f)[8]) {
   if (c.xpair) {

@@ -47,3 +47,32 @@ __device__ __forceinline__ void frustum_centre(const float* __restrict__ o, cons
 #pragma unroll
   for (int a = 0; a < 3; ++a) p[a] = add_rn(__ldg(o + a), div_rn(mul_rn(__ldg(d + a), t), 2.f));
 }
+
+// Backward of unit_cube_point at raw position p: g (gradient w.r.t. the unit-cube position) -> gradient w.r.t. p, in place.
+// Selector 0 -> zero; normalisation scale; L-inf contraction Jacobian  c(m) I + c'(m) sign(p_k) p e_k^T  with m = |p_k| the
+// max-norm, c(m) = 2/m - 1/m^2 (spatial_distortions.py:66-69; torch.linalg.norm(ord=inf) back-propagates to the arg-max).
+__device__ __forceinline__ void unit_cube_point_bwd(const PosParams& pp, const float (&p)[3], float (&g)[3]) {
+  float q[3] = {p[0], p[1], p[2]};
+  if (!unit_cube_point(pp, q)) {
+    g[0] = g[1] = g[2] = 0.f;
+    return;
+  }
+  if (pp.contraction) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g[a] *= 0.25f;
+    const float ax = fabsf(p[0]), ay = fabsf(p[1]), az = fabsf(p[2]);
+    const float m = fmaxf(ax, fmaxf(ay, az));
+    if (!(m < 1.f)) {
+      const int k = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+      const float inv = 1.f / m, c = (2.f - inv) * inv, dc = 2.f * inv * inv * (inv - 1.f);
+      const float dot = p[0] * g[0] + p[1] * g[1] + p[2] * g[2];
+      const float sgn = p[k] < 0.f ? -1.f : 1.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) g[a] *= c;
+      g[k] += sgn * dc * dot;
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g[a] /= pp.len[a];
+  }
+}

@@ -173,6 +173,44 @@ extern "C" int b2n_raygen_coords(const float* c2w, const float* intr, const floa
   B2N_LAUNCH_CHECK();
 }
 
+// CameraOptimizer.get_loss_dict (cameras/camera_optimizers.py:155-162): loss += mean_c |t_c| * trans_pen + mean_c |w_c| *
+// rot_pen, with its gradient accumulated into d_pose (the norm's sub-gradient at 0 is 0, as torch's).  One block.
+__global__ void __launch_bounds__(256) pose_regularizer_kernel(const float* __restrict__ pose, int n_cams, float trans_pen,
+                                                               float rot_pen, float gscale, float* __restrict__ loss,
+                                                               float* __restrict__ d_pose) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < n_cams; c += blockDim.x) {
+    const float* p = pose + 6 * c;
+    const float nt = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]), nw = sqrtf(p[3] * p[3] + p[4] * p[4] + p[5] * p[5]);
+    acc += (nt * trans_pen + nw * rot_pen) / (float)n_cams;
+    if (d_pose) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        if (nt > 0.f) d_pose[6 * c + a] += gscale * trans_pen * p[a] / (nt * (float)n_cams);
+        if (nw > 0.f) d_pose[6 * c + 3 + a] += gscale * rot_pen * p[3 + a] / (nw * (float)n_cams);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    *loss += t;
+  }
+}
+
+extern "C" int b2n_pose_regularizer(const float* pose_adjustment, int32_t n_cams, float trans_l2_penalty, float rot_l2_penalty,
+                                    float gscale, float* loss_out, float* d_pose_adjustment, void* stream) {
+  if (n_cams == 0) return B2N_OK;
+  B2N_REQUIRE(pose_adjustment && (loss_out || d_pose_adjustment), "null pointer");
+  pose_regularizer_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pose_adjustment, n_cams, trans_l2_penalty, rot_l2_penalty, gscale,
+                                                                loss_out, d_pose_adjustment);
+  B2N_LAUNCH_CHECK();
+}
+
 // Device-side training-ray pipeline: PixelSampler.sample_method + collate (data/pixel_samplers.py:137-174,
 // 265-318) + RayGenerator (model_components/ray_generators.py:41-56) in one launch over a uint8 image cache that lives
 // in HBM.  u [R,3] are the reference's `torch.rand((R,3))` draws; indices = (u * [C,H,W]).long() — a separately rounded

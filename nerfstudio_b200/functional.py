@@ -379,7 +379,7 @@ class _PositionsFn(torch.autograd.Function):
         d_o, d_d = torch.empty_like(o), torch.empty_like(d)
         box = host_floats(ctx.aabb) if ctx.aabb is not None else None
         call("b2n_positions_bwd", ptr(o), ptr(d), iv.p_starts, iv.p_ends, iv.stride, iv.R, iv.S, int(ctx.contraction),
-             C.cast(box, C.c_void_p) if box is not None else C.c_void_p(0), ptr(_c(dx.float())), ptr(d_o), ptr(d_d), stream())
+             C.cast(box, C.c_void_p) if box is not None else C.c_void_p(0), ptr(_c(dx.float())), 0, ptr(d_o), ptr(d_d), stream())
         return d_o, d_d, None, None, None
 
 

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "b2n_tune": [C.c_char_p, C.c_int],
     "b2n_hashgrid_fwd": [C.POINTER(B2nGrid), _P, _P, _I64, _P, _P, _P],
     "b2n_hashgrid_bwd": [C.POINTER(B2nGrid), _P, _P, _P, _I64, _P, _P, _P],
+    "b2n_hashgrid_dx": [C.POINTER(B2nGrid), _P, _P, _P, _I64, _P, _P],
     "b2n_mlp_fwd": [C.POINTER(B2nMlp), _P, _I64, _P, _P, _P],
     "b2n_mlp_bwd": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _I64, _P, _P],
     "b2n_mlp_tc_fwd": [C.POINTER(B2nMlp), _P, _I64, _I64, _P, _P, _P],
@@ -63,7 +64,7 @@ _SIGNATURES = {
     "b2n_freq_fwd": [_P, _I64, _I32, _P, _I32, _I32, _P, _P],
     "b2n_freq_bwd": [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P],
     "b2n_positions_fwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P],
-    "b2n_positions_bwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P, _P],
+    "b2n_positions_bwd": [_P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _I32, _P, _P, _P],
     "b2n_density_act_fwd": [_P, _I64, _P, _I64, _F, _P, _P],
     "b2n_density_act_bwd": [_P, _I64, _P, _P, _I64, _F, _P, _I64, _P],
     "b2n_spaced_sample": [_P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P, _P],
@@ -101,6 +102,9 @@ _SIGNATURES = {
                               _I32, _I32, _P, _F, _P, _P, _P],
     "b2n_density_field_bwd_ws": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _P, _I64, _I64,
                                  _I32, _I32, _P, _F, _P, _P, _P, _P],
+    "b2n_density_field_bwd_rays": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _P, _I64,
+                                   _I64, _I32, _I32, _P, _F, _P, _P, _P, _P, _P, _P],
+    "b2n_pose_regularizer": [_P, _I32, _F, _F, _F, _P, _P, _P],
     "b2n_tc_selftest": [_I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b2n_tc_timing": [_I32, _I32, _I32, _P, _P],
     "b2n_adam_step_dev": [_P, _P, _P, _P, _I64, _P, C.c_double, C.c_double, C.c_double, _P],
@@ -165,7 +169,7 @@ LAUNCHES = 0  # kernel-launching C-ABI calls made by this process (bench.py repo
 
 PROFILE = None  # set to {} to time every C-ABI launch with CUDA events on the launching stream (eager mode only)
 PROFILE_BY_SIZE = True  # False: one row per entry point (dynamic sizes, e.g. packed instant-ngp samples); n is summed
-_N_ARG = {"b2n_hashgrid_fwd": 3, "b2n_hashgrid_bwd": 4, "b2n_mlp_fwd": 2, "b2n_mlp_bwd": 6, "b2n_mlp_tc_fwd": 3,
+_N_ARG = {"b2n_hashgrid_fwd": 3, "b2n_hashgrid_bwd": 4, "b2n_hashgrid_dx": 4, "b2n_mlp_fwd": 2, "b2n_mlp_bwd": 6, "b2n_mlp_tc_fwd": 3,
           "b2n_mlp_tc_bwd": 7, "b2n_mlp_tc_fwd_ws": 3, "b2n_mlp_tc_bwd_ws": 7}
 
 
@@ -184,7 +188,7 @@ def call(name: str, *args) -> None:
         key = name
     elif name == "b2n_density_field_fwd":
         key = f"{name}[n={args[8] * args[9]}]"
-    elif name in ("b2n_density_field_bwd", "b2n_density_field_bwd_ws"):
+    elif name in ("b2n_density_field_bwd", "b2n_density_field_bwd_ws", "b2n_density_field_bwd_rays"):
         key = f"b2n_density_field_bwd[n={args[9] * args[10]}]"
     elif name in _N_ARG and name.startswith("b2n_mlp"):
         m = args[0]._obj  # byref(B2nMlp): two networks of one model may share n (base / colour head)

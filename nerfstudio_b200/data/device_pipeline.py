@@ -71,4 +71,4 @@ class DeviceRayPipeline:
         """Write the batch straight into a `NerfactoStep`'s static input buffers: no host round trip, no copies."""
         if u is None:
             u = torch.rand(engine.R, 3, device=self.images.device)
-        self._launch(u.float().contiguous(), None, engine.origins, engine.directions, None, None, engine.cams, engine.gt)
+        self._launch(u.float().contiguous(), None, engine.origins_in, engine.directions_in, None, None, engine.cams, engine.gt)

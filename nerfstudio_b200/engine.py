@@ -57,7 +57,8 @@ class NerfactoStep:
     def __init__(self, model: NerfactoModel, n_rays: int, lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-15,
                  lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
                  always_update_proposals: bool = False, mlp_backend: str = "auto",
-                 fused_proposals: bool = True, eval_mode: bool = False) -> None:
+                 fused_proposals: bool = True, eval_mode: bool = False, camera_lr: float = 1e-3,
+                 camera_lr_schedule: Optional[Callable[[int], float]] = None) -> None:
         cfg = model.config
         if cfg.implementation != "torch":
             raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
@@ -72,9 +73,27 @@ class NerfactoStep:
         # When it is the tail of the buffer the gradient all-reduce is split there (field segment summed while the
         # proposal backward still runs); any other layout gets ONE all-reduce after the whole backward — never a
         # collective over memory the proposal backward is still accumulating into.
-        seg = self.optim.segment_of("proposal_networks") if self.optim is not None else None
+        # camera optimiser (nerfacto's default: models/nerfacto.py:131, applied in get_outputs :300-301).  Mode SO3xR3 trains in
+        # the captured step: pose_apply at the head of the forward, position gradients of all three levels back to the
+        # rays, pose_apply_bwd + the regulariser at the tail, its own Adam group (lr 1e-3: method_configs.py:114-117).
+        cam = getattr(model, "camera_optimizer", None)
+        cam_mode = getattr(getattr(cam, "config", None), "mode", "off") if cam is not None else "off"
+        if cam_mode not in ("off", "SO3xR3"):
+            raise NotImplementedError(f"captured step: camera optimizer mode {cam_mode!r} (only off / SO3xR3)")
+        self.camopt = cam if (cam_mode == "SO3xR3" and not eval_mode) else None
+        self.camera_lr, self.camera_lr_schedule = camera_lr, camera_lr_schedule
+        # gradient all-reduce layout: the flat buffer is [... | segments that are complete only after the proposal / pose
+        # backward].  When "camera_opt" and "proposal_networks" form the tail, the head (the field) is summed over NVLink
+        # while that backward still runs; any other layout gets ONE all-reduce after the whole backward.
         total = self.optim.flat.numel() if self.optim is not None else 0
-        self.grad_split = seg[0] if seg is not None and seg[1] == total and seg[0] > 0 else None
+        self.grad_split, self._cam_seg, self._prop_seg = None, None, None
+        if self.optim is not None:
+            self._prop_seg = self.optim.segment_of("proposal_networks")
+            self._cam_seg = self.optim.segment_of("camera_opt") if self.camopt is not None else None
+            late = sorted(sg for sg in (self._cam_seg, self._prop_seg) if sg is not None)
+            if late and late[-1][1] == total and all(a[1] == b[0] for a, b in zip(late, late[1:])) and late[0][0] > 0 \
+                    and (self._prop_seg is not None):
+                self.grad_split = late[0][0]
         self._prop_steps = 0  # optimiser steps the proposal group has taken (its own bias-correction count)
         self.always_update = always_update_proposals
         dev = next(model.parameters()).device
@@ -117,17 +136,28 @@ class NerfactoStep:
         # (pack_batch) reaches the GPU with a single async copy; the four tensors are views of it
         self.inputs = torch.zeros(11 * R, **f32)
         self.cams = self.inputs[: 2 * R].view(torch.int64)
-        self.origins = self.inputs[2 * R: 5 * R].view(R, 3)
-        self.directions = self.inputs[5 * R: 8 * R].view(R, 3)
+        self.origins_in = self.inputs[2 * R: 5 * R].view(R, 3)      # what the data manager delivers
+        self.directions_in = self.inputs[5 * R: 8 * R].view(R, 3)
         self.gt = self.inputs[8 * R: 11 * R].view(R, 3)
+        if self.camopt is not None:  # rays after the per-camera pose correction (what every kernel downstream reads)
+            self.origins, self.directions = torch.zeros(R, 3, **f32), torch.zeros(R, 3, **f32)
+            self.d_rays = torch.zeros(2, R, 3, **f32)           # d loss / d (corrected origins | directions)
+            self.d_x2 = torch.zeros(R * cfg.num_nerf_samples_per_ray, 3, **f32)
+            from .cameras.camera_optimizers import _frozen_mask
+
+            self.cam_frozen = _frozen_mask(self.camopt)
+            self.cam_pose = self.camopt.pose_adjustment
+        else:
+            self.origins, self.directions = self.origins_in, self.directions_in
         # NearFarCollider (scene_colliders.py:169-191): the near plane is reset to 0 outside training
         self.nears = torch.full((R,), 0.0 if eval_mode else float(cfg.near_plane), **f32)
         self.fars = torch.full((R,), float(cfg.far_plane), **f32)
-        # [lr/bc1, 1/sqrt(bc2), grad_scale, anneal | the same three for the proposal group's own step count, pad]
-        self.hyper = torch.zeros(8, **f32)
+        # [lr/bc1, 1/sqrt(bc2), grad_scale, anneal | the same three for the proposal group's own step count, pad |
+        #  the same three with the camera optimiser's learning rate, pad]
+        self.hyper = torch.zeros(12, **f32)
         # pinned staging ring for the per-step scalars: a slot is rewritten only after the async H2D copy that read it
         # has completed (the CPU may run many steps ahead of the stream)
-        self._hyper_ring = torch.zeros(self.HYPER_SLOTS, 8, dtype=torch.float32).pin_memory()
+        self._hyper_ring = torch.zeros(self.HYPER_SLOTS, 12, dtype=torch.float32).pin_memory()
         self._hyper_np = self._hyper_ring.numpy()  # same memory; one vectorised write per step
         self._hyper_events: List[Optional[torch.cuda.Event]] = [None] * self.HYPER_SLOTS
         self.lin0 = torch.linspace(0.0, 1.0, self.S[0] + 1).to(dev)
@@ -162,7 +192,7 @@ class NerfactoStep:
         self.prop_depth = [torch.zeros(R, **f32) for _ in range(2)]  # median depth of the proposal levels (eval outputs)
         self.emb_mean = torch.zeros(1, max(self.n_emb, 1), **f32)    # eval: mean appearance embedding (or zeros)
         self.rows = [torch.zeros(R, **f32) for _ in range(3)]
-        self.losses = torch.zeros(4, **f32)  # rgb, interlevel, distortion, total
+        self.losses = torch.zeros(5, **f32)  # rgb, interlevel, distortion, total, camera-optimiser regulariser
         self.jitter = [torch.zeros(R, 1, **f32) for _ in range(3)]
         self.step_count = 0
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
@@ -256,10 +286,12 @@ class NerfactoStep:
         box = lib.host_floats(self.aabb)
         if lvl not in self._live_ws:
             self._live_ws[lvl] = torch.zeros(R * S + 4, device=self.dev, dtype=torch.int32)
-        call("b2n_density_field_bwd_ws", C.byref(net.grid.c), C.byref(m), C.byref(g), ptr(net.table), ptr(self.origins),
+        cam = self.camopt is not None
+        call("b2n_density_field_bwd_rays", C.byref(net.grid.c), C.byref(m), C.byref(g), ptr(net.table), ptr(self.origins),
              ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
              self.avg, ptr(self.d_dens[lvl]), ptr(net.table.grad),
-             ptr(self._live_ws[lvl], torch.int32) if self.compact_live else NULL, stream())
+             ptr(self._live_ws[lvl], torch.int32) if self.compact_live else NULL,
+             ptr(self.d_rays[0]) if cam else NULL, ptr(self.d_rays[1]) if cam else NULL, stream())
 
     def _forward(self) -> None:
         """Rays in the static buffers -> samples of the three levels, densities, weights, colours, rendered outputs.
@@ -271,6 +303,9 @@ class NerfactoStep:
         ev = self.eval_mode
         if self.tma_weights:
             self._pack_weights()
+        if self.camopt is not None:  # CameraOptimizer.apply_to_raybundle (camera_optimizers.py:148-153)
+            call("b2n_pose_apply_fwd", ptr(self.cam_pose), ptr(self.cams, torch.int64), ptr(self.cam_frozen, torch.uint8),
+                 ptr(self.origins_in), ptr(self.directions_in), R, ptr(self.origins), ptr(self.directions), st())
         # ---------------- forward: proposal sampling
         call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), NULL if ev else ptr(self.jitter[0]), 0, R, S0,
              lib.SPACING[self.spacing], ptr(self.sb[0]), ptr(self.eb[0]), st())
@@ -325,6 +360,8 @@ class NerfactoStep:
         st = stream
         self.optim.flat_grad.zero_()
         self.losses.zero_()
+        if self.camopt is not None:
+            self.d_rays.zero_()
         if self.fixed_jitter is None:
             for j in self.jitter:
                 j.copy_(torch.rand(R, 1, device=self.dev))
@@ -360,13 +397,26 @@ class NerfactoStep:
                       self.d_enc[2].shape[1], self.base.spec)
         call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
              ptr(self.base.table.grad), NULL, st())
-        self.losses[3:4].copy_(self.losses[0:3].sum(0, keepdim=True))
+        if self.camopt is not None:
+            # main level: d enc -> d x (gather-only kernel) -> contraction Jacobian -> the ray's d origin / d direction
+            box = lib.host_floats(self.aabb)
+            call("b2n_hashgrid_dx", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
+                 ptr(self.d_x2), st())
+            call("b2n_positions_bwd", ptr(self.origins), ptr(self.directions), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2,
+                 int(self.contraction), C.cast(box, C.c_void_p), ptr(self.d_x2), 1, ptr(self.d_rays[0]), ptr(self.d_rays[1]), st())
+            cc = self.camopt.config  # regulariser (camera_optimizers.py:155-162): value into losses[4], gradient into the poses
+            call("b2n_pose_regularizer", ptr(self.cam_pose), self.cam_pose.shape[0], float(cc.trans_l2_penalty),
+                 float(cc.rot_l2_penalty), 1.0, _off(self.losses, 4), ptr(self.cam_pose.grad), st())
+        self.losses[3:4].copy_(self.losses[0:3].sum(0, keepdim=True) + self.losses[4:5])
 
     def _body_props(self, update_props: bool) -> None:
         """backward of the proposal networks (only the interlevel loss reaches them)."""
         if update_props:
             for lvl in (0, 1):
                 self._density_net_bwd(lvl, self.props[lvl], None)
+        if self.camopt is not None:  # all three levels have added their d origin / d direction: on to the poses
+            call("b2n_pose_apply_bwd", ptr(self.cam_pose), ptr(self.cams, torch.int64), ptr(self.cam_frozen, torch.uint8),
+                 ptr(self.directions_in), ptr(self.d_rays[0]), ptr(self.d_rays[1]), self.R, ptr(self.cam_pose.grad), stream())
 
     def _adam(self, update: bool = True) -> None:
         """Fused Adam over the flat buffer.  Frozen proposal networks are NOT stepped (reference: their grads are None
@@ -377,7 +427,7 @@ class NerfactoStep:
             is_prop = name == "proposal_networks"
             if is_prop and not update:
                 continue
-            slot = 4 if (is_prop and not self.always_update) else 0
+            slot = 8 if name == "camera_opt" else (4 if (is_prop and not self.always_update) else 0)
             if runs and runs[-1][1] == a and runs[-1][2] == slot:
                 runs[-1][1] = b
             else:
@@ -389,8 +439,8 @@ class NerfactoStep:
     # ------------------------------------------------------------------------------------------------
     def set_batch(self, origins: Tensor, directions: Tensor, camera_indices: Tensor, gt_rgb: Tensor) -> None:
         """Copy one ray batch into the static input buffers (H2D when the sources are pinned host tensors)."""
-        self.origins.copy_(origins, non_blocking=True)
-        self.directions.copy_(directions, non_blocking=True)
+        self.origins_in.copy_(origins, non_blocking=True)
+        self.directions_in.copy_(directions, non_blocking=True)
         self.cams.copy_(camera_indices.reshape(-1), non_blocking=True)
         self.gt.copy_(gt_rgb, non_blocking=True)
 
@@ -432,9 +482,12 @@ class NerfactoStep:
         if self._hyper_events[slot] is not None:
             self._hyper_events[slot].synchronize()
         pt = self._prop_steps
+        clr = self.camera_lr_schedule(t) if self.camera_lr_schedule is not None else self.camera_lr
         self._hyper_np[slot] = (lr / (1.0 - o.betas[0] ** (t + 1)), 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1)),
                                 1.0 / world, self._anneal(t),
                                 lr / (1.0 - o.betas[0] ** (pt + 1)), 1.0 / math.sqrt(1.0 - o.betas[1] ** (pt + 1)),
+                                1.0 / world, 0.0,
+                                clr / (1.0 - o.betas[0] ** (t + 1)), 1.0 / math.sqrt(1.0 - o.betas[1] ** (t + 1)),
                                 1.0 / world, 0.0)
         self.hyper.copy_(self._hyper_ring[slot], non_blocking=True)
         ev = torch.cuda.Event()
@@ -467,7 +520,9 @@ class NerfactoStep:
         if overlap and split is None:
             h_rest = self.allreduce.start(o.flat_grad)  # unknown layout: one collective after the whole backward
         elif overlap and update:
-            h_rest = self.allreduce.start(o.flat_grad[split:])  # frozen proposals: nothing to sum, nothing stepped
+            h_rest = self.allreduce.start(o.flat_grad[split:])
+        elif overlap and self._cam_seg is not None:  # frozen proposals: nothing to sum there; the poses still train
+            h_rest = self.allreduce.start(o.flat_grad[self._cam_seg[0]: self._cam_seg[1]])
         if overlap:
             self.allreduce.finish(h_field, h_rest)
         run(2)
@@ -504,7 +559,7 @@ class NerfactoStep:
             g_all = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_all):
                 self._body(update)
-                if update:
+                if update or self.camopt is not None:
                     self._body_props(update)
                 self._adam(update)
             self._graphs[update] = (None, None, None, g_all)
@@ -512,7 +567,7 @@ class NerfactoStep:
         g_main, g_props, g_adam = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g_main):
             self._body(update)
-        if update:
+        if update or self.camopt is not None:
             with torch.cuda.graph(g_props, pool=g_main.pool()):
                 self._body_props(update)
         else:

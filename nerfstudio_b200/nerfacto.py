@@ -15,6 +15,7 @@ import numpy as np
 import torch
 from torch import Tensor, nn
 
+from .cameras.camera_optimizers import CameraOptimizer, CameraOptimizerConfig
 from .cameras.rays import RayBundle
 from .field_components.spatial_distortions import SceneContraction
 from .fields.density_fields import HashMLPDensityField
@@ -64,6 +65,7 @@ class NerfactoModelConfig:
     appearance_embed_dim: int = 32
     average_init_density: float = 1.0
     eval_num_rays_per_chunk: int = 1 << 15
+    camera_optimizer: CameraOptimizerConfig = field(default_factory=lambda: CameraOptimizerConfig(mode="SO3xR3"))
 
 
 class NerfactoModel(nn.Module):
@@ -80,6 +82,9 @@ class NerfactoModel(nn.Module):
             use_average_appearance_embedding=c.use_average_appearance_embedding,
             appearance_embedding_dim=c.appearance_embed_dim if c.use_appearance_embedding else 0,
             average_init_density=c.average_init_density, implementation=c.implementation)
+        # models/nerfacto.py:176-178: built between the field and the proposal networks (parameter order matters for the
+        # flat gradient buffer: [field | camera_opt | proposal_networks])
+        self.camera_optimizer = CameraOptimizer(c.camera_optimizer, num_cameras=num_train_data, device="cpu")
         self.proposal_networks = nn.ModuleList()
         n_nets = 1 if c.use_same_proposal_network else c.num_proposal_iterations
         for i in range(n_nets):
@@ -121,7 +126,9 @@ class NerfactoModel(nn.Module):
         self.proposal_sampler.step_cb(step)
 
     def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
-        return {"proposal_networks": list(self.proposal_networks.parameters()), "fields": list(self.field.parameters())}
+        groups = {"proposal_networks": list(self.proposal_networks.parameters()), "fields": list(self.field.parameters())}
+        self.camera_optimizer.get_param_groups(param_groups=groups)  # adds "camera_opt" unless the mode is "off"
+        return groups
 
     # ---- forward (models/base_model.py:132-143, models/nerfacto.py:298-348) ----
     def forward(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
@@ -129,6 +136,8 @@ class NerfactoModel(nn.Module):
         return self.get_outputs(ray_bundle)
 
     def get_outputs(self, ray_bundle: RayBundle) -> Dict:
+        if self.training:  # models/nerfacto.py:300-301
+            self.camera_optimizer.apply_to_raybundle(ray_bundle)
         ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns)
         field_outputs = self.field.forward(ray_samples)
         weights = ray_samples.get_weights(field_outputs[FieldHeadNames.DENSITY])
@@ -153,6 +162,7 @@ class NerfactoModel(nn.Module):
         metrics = {"psnr": -10.0 * torch.log10(torch.mean((outputs["rgb"].detach() - gt) ** 2))}
         if self.training:
             metrics["distortion"] = distortion_loss(outputs["weights_list"], outputs["ray_samples_list"])
+        self.camera_optimizer.get_metrics_dict(metrics)
         return metrics
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
@@ -164,6 +174,7 @@ class NerfactoModel(nn.Module):
                 outputs["weights_list"], outputs["ray_samples_list"])
             assert metrics_dict is not None and "distortion" in metrics_dict
             loss["distortion_loss"] = self.config.distortion_loss_mult * metrics_dict["distortion"]
+            self.camera_optimizer.get_loss_dict(loss)  # models/nerfacto.py:389-390
         return loss
 
     @torch.no_grad()
@@ -185,11 +196,12 @@ class Trainer:
     Gradient averaging across ranks (the DDP allreduce of pipelines/base_pipeline.py:280-281) is done by
     `nerfstudio_b200.distributed.FlatGradAllReduce` when world_size > 1."""
 
-    def __init__(self, model: NerfactoModel, lr: float = 1e-2, eps: float = 1e-15, allreduce=None) -> None:
+    def __init__(self, model: NerfactoModel, lr: float = 1e-2, eps: float = 1e-15, allreduce=None,
+                 camera_lr: float = 1e-3) -> None:
         from .optim import FlatAdam
 
         self.model = model
-        self.optim = FlatAdam(model, lr=lr, eps=eps)
+        self.optim = FlatAdam(model, lr=lr, eps=eps, group_lr={"camera_opt": camera_lr})
         self.allreduce = allreduce
         self.step = 0
 

@@ -25,7 +25,7 @@ class FlatAdam:
     ALIGN = 4  # elements (16 B): keeps float2/float4 table rows and the vectorised Adam kernel aligned
 
     def __init__(self, module: nn.Module, lr: float = 1e-2, betas=(0.9, 0.999), eps: float = 1e-15,
-                 lr_schedule: Optional[Callable[[int], float]] = None) -> None:
+                 lr_schedule: Optional[Callable[[int], float]] = None, group_lr: Optional[dict] = None) -> None:
         seen, params = set(), []
         for p in module.parameters():
             if p.requires_grad and id(p) not in seen:
@@ -65,6 +65,7 @@ class FlatAdam:
             else:
                 self.segments.append([name, off, end])
         self.group_steps = {name: 0 for name, _, _ in self.segments}
+        self.group_lr = dict(group_lr or {})  # per-group learning rate overrides (e.g. camera_opt: 1e-3)
 
     def zero_grad(self) -> None:
         self.flat_grad.zero_()
@@ -88,11 +89,11 @@ class FlatAdam:
         for name, a, b in self.segments:
             if name not in names:
                 continue
-            t = self.group_steps[name]
-            if runs and runs[-1][1] == a and runs[-1][2] == t:
+            t, glr = self.group_steps[name], self.group_lr.get(name, lr)
+            if runs and runs[-1][1] == a and runs[-1][2] == t and runs[-1][3] == glr:
                 runs[-1][1] = b
             else:
-                runs.append([a, b, t])
-        for a, b, t in runs:
-            F.adam_step(self.flat[a:b], self.flat_grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], t, lr, self.betas,
+                runs.append([a, b, t, glr])
+        for a, b, t, glr in runs:
+            F.adam_step(self.flat[a:b], self.flat_grad[a:b], self.exp_avg[a:b], self.exp_avg_sq[a:b], t, glr, self.betas,
                         self.eps, grad_scale)

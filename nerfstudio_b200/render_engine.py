@@ -84,8 +84,8 @@ class NerfactoRender:
             if ci % world != rank:
                 continue
             n = min(self.chunk, N - i)
-            e.origins[:n].copy_(o[i: i + n], non_blocking=True)
-            e.directions[:n].copy_(d[i: i + n], non_blocking=True)
+            e.origins_in[:n].copy_(o[i: i + n], non_blocking=True)
+            e.directions_in[:n].copy_(d[i: i + n], non_blocking=True)
             if cams is not None:
                 e.cams[:n].copy_(cams[i: i + n], non_blocking=True)
             self._run_chunk()  # rows >= n of a ragged last chunk hold the previous chunk's rays: computed, never read

@@ -67,6 +67,18 @@ def run() -> None:
     torch.cuda.synchronize()
     assert torch.isfinite(stats["loss"]).item()
 
+    # the captured step (hand-written backward, tcgen05 MLPs, TMA-staged weights, camera optimiser) on the same rays
+    from .engine import NerfactoStep
+
+    eng = NerfactoStep(model, R, use_graph=True)
+    eng.set_batch(rays["origins"].cuda(), rays["directions"].cuda(), rays["camera_indices"].cuda(), gt.cuda())
+    first = float(eng.step()[3])
+    for _ in range(5):
+        eng.step()
+    torch.cuda.synchronize()
+    last = float(eng.losses[3])
+    assert first == first and last == last and last < first * 1.5, f"smoke: captured step diverged ({first} -> {last})"
+
 
 def _eval_rgb(O, P, rays, cfg):
     import torch as _t

@@ -182,10 +182,12 @@ def _named_params(model):
     return named
 
 
-def _pipeline_model(g):
+def _pipeline_model(g, camera_optimizer: str = "off"):
+    from nerfstudio_b200.cameras.camera_optimizers import CameraOptimizerConfig
     from nerfstudio_b200.nerfacto import NerfactoModel, NerfactoModelConfig
 
     cfg = NerfactoModelConfig(
+        camera_optimizer=CameraOptimizerConfig(mode=camera_optimizer),
         num_levels=8, max_res=512, log2_hashmap_size=13, num_proposal_samples_per_ray=(32, 20),
         num_nerf_samples_per_ray=12, average_init_density=0.01, implementation="torch",
         use_average_appearance_embedding=False,

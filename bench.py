@@ -711,6 +711,90 @@ def run_ngp(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def run_splat(args) -> None:
+    """--workload splat: BASELINE configs[4] — splatfacto's rasteriser behind the gsplat API: 1 000 000 Gaussians (means
+    U(-1,1)^3, scales exp(N(-4,0.5)), random unit quaternions, opacities sigmoid(N(0,1)), SH degree 3), one 1920x1080 camera
+    at z = -3, fx = fy = 1200.  A step = one forward render (projection + SH + binning + sort + tile
+    rasterisation); `--splat-train` adds the backward.  Reported as Gaussians/s and frames/s."""
+    from nerfstudio_b200 import lib
+    from nerfstudio_b200.shims import gsplat as G
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the B200 core has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    lib.load()
+    sampler = ClockSampler(dev.index)
+    N, W, H = 1_000_000, 1920, 1080
+    g = torch.Generator().manual_seed(0)
+    means = (torch.rand(N, 3, generator=g) * 2 - 1).to(dev)
+    quats = torch.randn(N, 4, generator=g).to(dev)
+    scales = torch.exp(torch.randn(N, 3, generator=g) * 0.5 - 4.0).to(dev)
+    opac = torch.sigmoid(torch.randn(N, generator=g)).to(dev)
+    sh = (torch.randn(N, 16, 3, generator=g) * 0.2).to(dev)
+    view = torch.eye(4)
+    view[2, 3] = 3.0
+    K = torch.tensor([[1200.0, 0, W / 2], [0, 1200.0, H / 2], [0, 0, 1]])
+    vm, kk = view[None].to(dev), K[None].to(dev)
+    leaves = [means, quats, scales, opac, sh]
+    if args.splat_train:
+        leaves = [t.requires_grad_(True) for t in leaves]
+
+    def step(_i):
+        out, alpha, info = G.rasterization(*leaves, vm, kk, W, H, sh_degree=3)
+        if args.splat_train:
+            for t in leaves:
+                t.grad = None
+            (out.mean() + alpha.mean()).backward()
+        return out
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    spans, win = [], []
+    lib.LAUNCHES = 0
+    for _w in range(args.windows):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(args.steps):
+            out = step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        spans.append((t0, time.perf_counter()))
+        win.append(e0.elapsed_time(e1))
+    launches = lib.LAUNCHES
+    ms = sorted(win)[len(win) // 2] / args.steps
+    lib.PROFILE_BY_SIZE, lib.PROFILE = False, {}
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    prof = lib.profile_summary()
+    lib.PROFILE, lib.PROFILE_BY_SIZE = None, True
+    clocks = sampler.window(spans)
+    sampler.stop()
+    hbm_peak, peak_src = peaks()
+    # algorithmic bytes of the projection: read 10 floats + 48 SH floats, write 2+1+3+1+1+3 per Gaussian
+    proj_bytes = N * 4 * (3 + 4 + 3 + 48 + 11)
+    kt = {k: round(t / 3, 4) for k, (c, t) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    pj = prof.get("b2n_gs_project_fwd")
+    line = {"metric": "gaussians_per_sec", "value": N / (ms * 1e-3), "unit": "gaussians/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "splatfacto rasteriser (gsplat API): 1M Gaussians, SH degree 3, 1920x1080, one camera "
+                                   "(BASELINE configs[4])", "mode": "forward + backward" if args.splat_train else "forward render",
+                       "sort": "64-bit key radix sort = torch.sort (library primitive, as gsplat uses cub)"},
+            "fps": 1e3 / ms, "windows_ms": win, "kernel_ms_per_step": kt, "alpha_mean": float(out.abs().mean().item()),
+            "roofline": {"bound": "hbm", "kernel": "b2n_gs_project_fwd", "achieved": proj_bytes / (pj[1] / pj[0] * 1e-3) / 1e9 if pj else None,
+                         "peak": hbm_peak, "unit": "GB/s", "frac": (proj_bytes / (pj[1] / pj[0] * 1e-3) / 1e9 / hbm_peak) if pj else None,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "projection + SH: 268 B per Gaussian; the tile rasteriser is latency/occupancy bound (see kernel_ms_per_step)"},
+            "cpu_baseline": None, "e2e": {"value": N / (ms * 1e-3), "unit": "gaussians/s", "h2d_bytes_per_step": 128, "d2h_bytes_per_step": 0,
+                                          "through": "shims.gsplat.rasterization (gsplat.rendering.rasterization surface)"},
+            "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
 def cpu_baseline_sample():
     threads, _ = pick_cpu_threads()
     rps, sec, cores, kind = time_cpu(512, 3, 1, threads)
@@ -725,8 +809,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="nerfacto", choices=["nerfacto", "ngp"],
-                    help="nerfacto = BASELINE configs[2], the metric's workload (default); ngp = configs[1] (instant-ngp)")
+    ap.add_argument("--workload", default="nerfacto", choices=["nerfacto", "ngp", "splat"],
+                    help="nerfacto = BASELINE configs[2], the metric's workload (default); ngp = configs[1] (instant-ngp); "
+                         "splat = configs[4] (3DGS rasteriser behind the gsplat API)")
+    ap.add_argument("--splat-train", action="store_true", help="splat workload: include the backward pass")
     ap.add_argument("--windows", type=int, default=3, help="timed windows of exactly --steps steps each (median reported)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--state-step", type=int, default=STATE_STEP,
@@ -750,6 +836,8 @@ def main() -> None:
         run_reference(args)
     elif args.workload == "ngp":
         run_ngp(args)
+    elif args.workload == "splat":
+        run_splat(args)
     else:
         run_b200(args)
     if torch.distributed.is_available() and torch.distributed.is_initialized():

@@ -347,6 +347,44 @@ int b2n_ray_aabb_intersect(const float* origins, const float* directions, const 
                            int32_t n_boxes, float near_plane, float far_plane, float miss_value, float* t_mins,
                            float* t_maxs, uint8_t* hits, void* stream);
 
+/* ---- 3D Gaussian splatting (gsplat.rendering.rasterization as models/splatfacto.py:555-581 calls it) -----
+ * gsplat 1.4.0's sources are unavailable: the stages restate its published algorithm (oracle/splat_oracle.py) — PARITY
+ * UNPINNED.  One camera per call: viewmat_host16 = world->camera 4x4 (row-major, host), k_host9 = intrinsics 3x3 (host).
+ *  project_fwd  means [N,3], quats [N,4] (w,x,y,z; normalised inside), scales [N,3] -> means2d [N,2], depths [N], conics
+ *               [N,3] (inverse of the eps2d-blurred 2-D covariance: a, b, c of [[a,b],[b,c]]), radii int32 [N] (3 sigma,
+ *               pixels; 0 = culled), tiles_touched int32 [N] (16x16 tiles in the radius box); sh [N,K,3] != NULL also
+ *               writes colors [N,3] = max(SH_degree(dir) + 0.5, 0).
+ *  emit         per (Gaussian, tile) key = tile << 32 | depth bits at offsets = exclusive scan of tiles_touched
+ *               (b2n_scan_counts); the caller sorts the keys (any stable 64-bit sort) and permutes gaussian_ids with them.
+ *  tile_ranges  tile_lo / tile_hi int32 [tiles] (caller zero-fills): range of each tile in the sorted list.
+ *  rasterize    front-to-back blending per pixel centre: alpha = min(0.999, opacity exp(-sigma)), skip alpha < 1/255,
+ *               stop before T <= 1e-4.  out [H,W,3] (or [H,W,4] with `extra` [N], e.g. depth), out_alpha [H,W],
+ *               last_idx int32 [H,W] (for the backward).  The backward ACCUMULATES v_means2d / v_conics / v_opacities /
+ *               v_colors (/ v_extra): caller zero-fills.
+ *  project_bwd  (v_means2d, v_depths | NULL, v_conics, v_colors | NULL) -> v_means, v_quats, v_scales, v_sh (overwritten). */
+int b2n_gs_project_fwd(const float* means, const float* quats, const float* scales, const float* sh, int32_t sh_k,
+                       int32_t sh_degree, int64_t n, const float* viewmat_host16, const float* k_host9, int32_t width,
+                       int32_t height, float near_plane, float far_plane, float eps2d, float radius_clip, float* means2d,
+                       float* depths, float* conics, int32_t* radii, int32_t* tiles_touched, float* colors, void* stream);
+int b2n_gs_project_bwd(const float* means, const float* quats, const float* scales, const float* sh, int32_t sh_k,
+                       int32_t sh_degree, int64_t n, const float* viewmat_host16, const float* k_host9, int32_t width,
+                       int32_t height, float near_plane, float far_plane, float eps2d, float radius_clip,
+                       const int32_t* radii, const float* conics, const float* colors, const float* v_means2d,
+                       const float* v_depths, const float* v_conics, const float* v_colors, float* v_means, float* v_quats,
+                       float* v_scales, float* v_sh, void* stream);
+int b2n_gs_emit(const float* means2d, const int32_t* radii, const float* depths, const int64_t* offsets, int64_t n,
+                int32_t width, int32_t height, int64_t* keys, int32_t* gaussian_ids, void* stream);
+int b2n_gs_tile_ranges(const int64_t* sorted_keys, int64_t m, int32_t* tile_lo, int32_t* tile_hi, void* stream);
+int b2n_gs_rasterize_fwd(int32_t width, int32_t height, const int32_t* tile_lo, const int32_t* tile_hi,
+                         const int32_t* sorted_ids, const float* means2d, const float* conics, const float* opacities,
+                         const float* colors, const float* extra, float* out, float* out_alpha, int32_t* last_idx,
+                         void* stream);
+int b2n_gs_rasterize_bwd(int32_t width, int32_t height, const int32_t* tile_lo, const int32_t* tile_hi,
+                         const int32_t* sorted_ids, const float* means2d, const float* conics, const float* opacities,
+                         const float* colors, const float* extra, const float* out_alpha, const int32_t* last_idx,
+                         const float* v_out, const float* v_out_alpha, float* v_means2d, float* v_conics,
+                         float* v_opacities, float* v_colors, float* v_extra, void* stream);
+
 /* ---- optimiser step either side of the path: torch.optim.Adam semantics ---------------
  * p,g,m,v flat fp32 [n]; step is the 1-based step count; grads are multiplied by grad_scale first
  * (1/world_size after a sum-allreduce, or 1/loss_scale).  Hyper-parameters are doubles: 1-beta and the bias

@@ -18,6 +18,7 @@
 
 static int g_levels_per_block_fwd = 4;  // levels looped per thread (blockIdx.y picks the group); 0 = all
 static int g_levels_per_block_bwd = 1;
+static int g_fwd_pair = 1;  // F = 2: two lanes per point (hashgrid_fwd_pair_kernel / hashgrid_dx_pair_kernel); 0 = one thread per point
 static int g_bwd_chunk = 8;  // samples per thread of the run-length backward kernel (0 = one sample per thread)
 
 template <int F, int MODE>
@@ -235,6 +236,48 @@ __global__ void __launch_bounds__(256) hashgrid_dx_kernel(const __grid_constant_
   dx[3 * i] = gx, dx[3 * i + 1] = gy, dx[3 * i + 2] = gz;
 }
 
+// Lane-pair variant of the position gradient for F = 2 (see hashgrid_fwd_pair_kernel: 4 instead of 6-8 L1 line cycles per
+// (point, level)): lane parity = x-corner for the loads and = feature index for the derivative; the pair sums its two
+// features' contributions with one shuffle per component.  All levels in-thread: no atomics.
+template <int MODE>
+__global__ void __launch_bounds__(256) hashgrid_dx_pair_kernel(const __grid_constant__ GridParams gp,
+                                                               const float* __restrict__ x, const float* __restrict__ table,
+                                                               const float* __restrict__ dy, int64_t n,
+                                                               float* __restrict__ dx) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t >> 1;
+  const bool live = i < n;
+  const int par = (int)(t & 1);
+  const int64_t ic = live ? i : n - 1;
+  const float px = __ldg(x + 3 * ic), py = __ldg(x + 3 * ic + 1), pz = __ldg(x + 3 * ic + 2);
+  const float* grow = dy + ic * (int64_t)(gp.n_levels * 2);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll 2
+  for (int l = 0; l < gp.n_levels; ++l) {
+    const float g = __ldg(grow + 2 * l + par);  // upstream gradient of MY feature
+    const Corners c = corners_of<MODE>(gp, l, px, py, pz);
+    uint32_t r4[4];
+    r4[0] = par ? c.row[0] : c.row[3], r4[1] = par ? c.row[1] : c.row[2];
+    r4[2] = par ? c.row[4] : c.row[7], r4[3] = par ? c.row[5] : c.row[6];
+    float2 f4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f4[q] = __ldg(reinterpret_cast<const float2*>(table) + r4[q]);
+    float fc[4], ff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float send = par ? f4[q].x : f4[q].y, mine = par ? f4[q].y : f4[q].x;
+      const float theirs = __shfl_xor_sync(0xffffffffu, send, 1);
+      fc[q] = par ? mine : theirs, ff[q] = par ? theirs : mine;
+    }
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    blend8_dpos(fc[0], fc[1], ff[1], ff[0], fc[2], fc[3], ff[3], ff[2], c.ox, c.oy, c.oz, g, ax, ay, az);
+    const float sc = gp.scale[l];
+    gx = fmaf(ax, sc, gx), gy = fmaf(ay, sc, gy), gz = fmaf(az, sc, gz);
+  }
+  gx += __shfl_xor_sync(0xffffffffu, gx, 1), gy += __shfl_xor_sync(0xffffffffu, gy, 1), gz += __shfl_xor_sync(0xffffffffu, gz, 1);
+  if (live && par == 0) dx[3 * i] = gx, dx[3 * i + 1] = gy, dx[3 * i + 2] = gz;
+}
+
 // Run-length variant of the scatter: a thread walks CH consecutive samples of one level.  Consecutive samples along a
 // ray stay in the same grid cell for many steps at the coarse levels, so the 8 corner contributions are accumulated in
 // registers while the cell does not change and flushed with one vector RED per corner when it does — this removes
@@ -299,8 +342,6 @@ __global__ void __launch_bounds__(256) hashgrid_bwd_runs_kernel(const __grid_con
   if (have) flush();
 }
 
-
-static int g_fwd_pair = 1;  // F = 2: two lanes per point (see hashgrid_fwd_pair_kernel); 0 = one thread per point
 
 template <int F>
 static void launch_fwd(const GridParams& gp, const float* x, const float* table, int64_t n, float* y, int64_t* idx,
@@ -403,6 +444,12 @@ extern "C" int b2n_hashgrid_dx(const B2nGrid* grid_host, const float* x, const f
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)div_up(n, 256);
   const bool tm = gp.mode == B2N_GRID_TORCH;
+  if (grid_host->n_features == 2 && g_fwd_pair) {
+    const unsigned g2 = (unsigned)div_up(2 * n, 256);
+    if (tm) hashgrid_dx_pair_kernel<B2N_GRID_TORCH><<<g2, 256, 0, st>>>(gp, x, table, dy, n, dx);
+    else hashgrid_dx_pair_kernel<B2N_GRID_TCNN><<<g2, 256, 0, st>>>(gp, x, table, dy, n, dx);
+    B2N_LAUNCH_CHECK();
+  }
 #define B2N_DX_CASE(F)                                                                                  \
   case F:                                                                                               \
     if (tm) hashgrid_dx_kernel<F, B2N_GRID_TORCH><<<grid, 256, 0, st>>>(gp, x, table, dy, n, dx);      \

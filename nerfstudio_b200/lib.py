@@ -105,6 +105,13 @@ _SIGNATURES = {
     "b2n_density_field_bwd_rays": [C.POINTER(B2nGrid), C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _P, _P, _P, _P, _I64,
                                    _I64, _I32, _I32, _P, _F, _P, _P, _P, _P, _P, _P],
     "b2n_pose_regularizer": [_P, _I32, _F, _F, _F, _P, _P, _P],
+    "b2n_gs_project_fwd": [_P, _P, _P, _P, _I32, _I32, _I64, _P, _P, _I32, _I32, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    "b2n_gs_project_bwd": [_P, _P, _P, _P, _I32, _I32, _I64, _P, _P, _I32, _I32, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P,
+                           _P, _P, _P, _P, _P],
+    "b2n_gs_emit": [_P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P],
+    "b2n_gs_tile_ranges": [_P, _I64, _P, _P, _P],
+    "b2n_gs_rasterize_fwd": [_I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b2n_gs_rasterize_bwd": [_I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "b2n_tc_selftest": [_I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _I32, _I32, _I32, _P, _P],
     "b2n_tc_timing": [_I32, _I32, _I32, _P, _P],
     "b2n_adam_step_dev": [_P, _P, _P, _P, _I64, _P, C.c_double, C.c_double, C.c_double, _P],

@@ -95,6 +95,30 @@ def test_hashgrid_pair_kernel_bitwise_equals_thread_per_point(F):
         assert torch.equal(F.hashgrid_forward(x, table, grid), ref), (grid.n_levels, N)
 
 
+def test_hashgrid_dx_kernels(F):
+    """b2n_hashgrid_dx (gather-only position gradient; lane-pair and thread-per-point variants) == the dx of hashgrid_bwd."""
+    from nerfstudio_b200 import lib
+    from nerfstudio_b200.lib import call, ptr, stream
+    import ctypes as C
+
+    torch.manual_seed(4)
+    for grid, rows, N in ((F.GridSpec(O.hash_level_scalings(16, 16, 2048).tolist(), 19, 2), 16 << 19, 50001),
+                          (F.GridSpec.tcnn(8, 16, 1.3819, 12, 2), None, 777)):
+        rows = rows or grid.n_rows
+        x = torch.rand(N, 3, device="cuda")
+        table = torch.randn(rows, 2, device="cuda")
+        dy = torch.randn(N, grid.out_dim, device="cuda")
+        _, ref = F.hashgrid_backward(x, table, dy, grid, want_dx=True)
+        for pair in (1, 0):
+            try:
+                assert lib.tune("hash_fwd_pair", pair)
+                dx = torch.empty(N, 3, device="cuda")
+                call("b2n_hashgrid_dx", C.byref(grid.c), ptr(x), ptr(table), ptr(dy), N, ptr(dx), stream())
+            finally:
+                lib.tune("hash_fwd_pair", 1)
+            assert_close(dx, ref, 1e-5, f"dx pair={pair}")
+
+
 def test_hashgrid_tcnn_mode(F):
     """tcnn-mode addressing vs the oracle's restatement of the published semantics (parity unpinned upstream)."""
     torch.manual_seed(1)

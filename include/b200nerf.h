@@ -145,6 +145,17 @@ int b2n_mlp_tc_bwd_ws(const B2nMlp* mlp_host, const B2nMlpGrad* grad_host, const
                       const float* y, const float* hidden, const float* dy, int64_t n, float* dx, int64_t dx_stride,
                       const void* workspace, void* stream);
 
+/* ---- wide dense layers (vanilla-nerf 8 x 256 with skip: fields/vanilla_nerf_field.py:84-107, mlp.py:160-179) --------------
+ * One layer per call on a register-tiled fp32 GEMM with fused bias + activation (networks too wide for the fused kernels).
+ *  fwd: y [n,out] = act(x [n,in] (row stride x_stride) w[out,in]^T + b).
+ *  bwd: dz_scratch [n,out] receives dy * act'(y); dx [n,in] (row stride dx_stride, overwritten; NULL = skip);
+ *       dw [out,in] and db [out] are ACCUMULATED into (NULL = skip). */
+int b2n_linear_fwd(const float* x, int64_t n, int32_t in_dim, int64_t x_stride, const float* w, const float* b,
+                   int32_t out_dim, int32_t act, float* y, void* stream);
+int b2n_linear_bwd(const float* x, int64_t n, int32_t in_dim, int64_t x_stride, const float* w, int32_t out_dim, int32_t act,
+                   const float* y, const float* dy, float* dz_scratch, float* dx, int64_t dx_stride, float* dw, float* db,
+                   void* stream);
+
 /* ---- K5/K6: direction / frequency encodings ---------------------------------------------------------
  * SHEncoding (encodings.py:752-799, utils/spherical_harmonics.py:24-81): levels in 1..5, out [N,levels^2].
  * remap01 != 0 applies d <- (d+1)/2 first (fields/base_field.py:136-142 fused in). */

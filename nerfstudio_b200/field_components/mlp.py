@@ -81,15 +81,16 @@ class MLP(nn.Module):
         return out.view(*in_tensor.shape[:-1], self.out_dim)
 
     def _wide_forward(self, x: Tensor) -> Tensor:
-        """Layer-by-layer library GEMMs for widths beyond the fused kernel (vanilla-nerf 8x256)."""
-        h = x
+        """Widths beyond the fused kernels' shared memory (vanilla-nerf 8 x 256 with a skip): one tiled fp32 GEMM launch per
+        layer with the bias and activation fused into its epilogue (csrc/wide_mlp.cu) — no library GEMM."""
+        h = x.float()
+        last = len(self.layers) - 1
         for i, layer in enumerate(self.layers):
             if i in self._skip_connections:
-                h = torch.cat([x, h], -1)
-            h = layer(h)
-            if self.activation is not None and i < len(self.layers) - 1:
-                h = self.activation(h)
-        return self.out_activation(h) if self.out_activation is not None else h
+                h = torch.cat([x.float(), h], -1)
+            act = _act_name(self.out_activation) if i == last else _act_name(self.activation)
+            h = F.linear(h, layer.weight, layer.bias, act)
+        return h
 
 
 class MLPWithHashEncoding(nn.Module):

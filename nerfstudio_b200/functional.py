@@ -290,6 +290,40 @@ def mlp(spec: MlpSpec, x: Tensor, weights: Sequence[Tensor], biases: Sequence[Op
     return _MlpFn.apply(spec, x, *params)
 
 
+class _LinearFn(torch.autograd.Function):
+    """One wide dense layer y = act(x W^T + b) on the tiled fp32 GEMM (b2n_linear_fwd / b2n_linear_bwd)."""
+
+    @staticmethod
+    @_fwd
+    def forward(ctx, x, w, b, act):
+        x, w = _c(x), _c(w)
+        n, out = x.shape[0], w.shape[0]
+        y = torch.empty(n, out, device=x.device, dtype=torch.float32)
+        call("b2n_linear_fwd", ptr(x), n, x.shape[1], x.shape[1], ptr(w), ptr(None if b is None else _c(b)), out, lib.ACT[act],
+             ptr(y), stream())
+        ctx.act = act
+        ctx.save_for_backward(x, w, y)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        n, out = y.shape
+        dz = torch.empty_like(y)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(out, device=x.device) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        call("b2n_linear_bwd", ptr(x), n, x.shape[1], x.shape[1], ptr(w), out, lib.ACT[ctx.act], ptr(y), ptr(_c(dy.float())),
+             ptr(dz), ptr(dx), x.shape[1], ptr(dw), ptr(db), stream())
+        return dx, dw, db, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], act: str = "none") -> Tensor:
+    return _LinearFn.apply(x, weight, bias, act)
+
+
 # ----------------------------------------------------------------------------------------
 # encodings
 # ----------------------------------------------------------------------------------------

@@ -92,6 +92,21 @@ def install(shim_third_party: bool = True, patch_get_weights: bool = True) -> Li
             if name not in sys.modules and not _importable(name):
                 sys.modules[name] = importlib.import_module(ours)
                 done.append(f"sys.modules[{name!r}]")
+        # gsplat (models/splatfacto.py:26-31 imports gsplat.rendering.rasterization and gsplat.strategy at import time)
+        if "gsplat" not in sys.modules and not _importable("gsplat"):
+            import types
+
+            shim = importlib.import_module("nerfstudio_b200.shims.gsplat")
+            pkg = types.ModuleType("gsplat")
+            pkg.__path__ = []
+            rendering = types.ModuleType("gsplat.rendering")
+            rendering.rasterization = shim.rasterization
+            strategy = types.ModuleType("gsplat.strategy")
+            strategy.DefaultStrategy, strategy.MCMCStrategy = shim.DefaultStrategy, shim.MCMCStrategy
+            pkg.rendering, pkg.strategy = rendering, strategy
+            for nm, mod in (("gsplat", pkg), ("gsplat.rendering", rendering), ("gsplat.strategy", strategy)):
+                sys.modules[nm] = mod
+                done.append(f"sys.modules[{nm!r}]")
     for ref_mod_name, attrs in _REPLACEMENTS.items():
         ref_mod = importlib.import_module(ref_mod_name)
         for attr, (our_mod_name, our_attr) in attrs.items():
@@ -178,6 +193,10 @@ def uninstall() -> None:
         mod = sys.modules.get(name)
         if mod is not None and getattr(mod, "__name__", "").startswith("nerfstudio_b200.shims"):
             del sys.modules[name]
+    rend = sys.modules.get("gsplat.rendering")
+    if rend is not None and getattr(getattr(rend, "rasterization", None), "__module__", "").startswith("nerfstudio_b200"):
+        for name in ("gsplat.strategy", "gsplat.rendering", "gsplat"):
+            sys.modules.pop(name, None)
 
 
 def install_fused_trainer(trainer, **engine_kwargs):

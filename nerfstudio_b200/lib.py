@@ -60,6 +60,8 @@ _SIGNATURES = {
     "b2n_mlp_tc_pack": [C.POINTER(B2nMlp), _P, _P],
     "b2n_mlp_tc_fwd_ws": [C.POINTER(B2nMlp), _P, _I64, _I64, _P, _P, _P, _P],
     "b2n_mlp_tc_bwd_ws": [C.POINTER(B2nMlp), C.POINTER(B2nMlpGrad), _P, _I64, _P, _P, _P, _I64, _P, _I64, _P, _P],
+    "b2n_linear_fwd": [_P, _I64, _I32, _I64, _P, _P, _I32, _I32, _P, _P],
+    "b2n_linear_bwd": [_P, _I64, _I32, _I64, _P, _I32, _I32, _P, _P, _P, _P, _I64, _P, _P, _P],
     "b2n_sh_fwd": [_P, _I64, _I32, _I32, _P, _P],
     "b2n_freq_fwd": [_P, _I64, _I32, _P, _I32, _I32, _P, _P],
     "b2n_freq_bwd": [_P, _P, _I64, _I32, _P, _I32, _I32, _P, _P],

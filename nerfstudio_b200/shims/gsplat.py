@@ -133,3 +133,34 @@ def rasterization(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tenso
     info = dict(means2d=torch.stack([m for m, _ in infos]), radii=torch.stack([r for _, r in infos]), width=width,
                 height=height, n_cameras=viewmats.shape[0], tile_size=16)
     return torch.stack(renders), torch.stack(alphas), info
+
+
+class _NoDensification:
+    """Stand-in for gsplat.strategy.{DefaultStrategy, MCMCStrategy}: splatfacto constructs one and calls its hooks every
+    step (models/splatfacto.py:294-330,583-586).  Densification / pruning is control plane (out of scope): the hooks
+    keep the call protocol and change nothing, so a splatfacto model trains with a fixed set of Gaussians."""
+
+    def __init__(self, *args, **kwargs) -> None:
+        self.absgrad = bool(kwargs.get("absgrad", False))
+        self.kwargs = kwargs
+
+    def check_sanity(self, params, optimizers) -> None:
+        return None
+
+    def initialize_state(self, *args, **kwargs) -> dict:
+        return {}
+
+    def step_pre_backward(self, params, optimizers, state, step, info) -> None:
+        if isinstance(info, dict) and "means2d" in info and info["means2d"].requires_grad:
+            info["means2d"].retain_grad()
+
+    def step_post_backward(self, *args, **kwargs) -> None:
+        return None
+
+
+class DefaultStrategy(_NoDensification):
+    pass
+
+
+class MCMCStrategy(_NoDensification):
+    pass

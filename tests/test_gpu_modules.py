@@ -111,6 +111,43 @@ def test_nerfacto_field_module(cuda, golden):
             assert_close(gr, g[f"{nm}_g_{k}"], REL, f"{nm} g_{k}")
 
 
+def test_wide_mlp_vanilla_nerf_size(cuda):
+    """a29 at the REAL vanilla-nerf size (fields/vanilla_nerf_field.py:84-107): 63 -> 8 x 256 (skip at layer 4) and the
+    128-wide colour branch run on the tiled fp32 GEMM layers of csrc/wide_mlp.cu (no library GEMM): outputs and every
+    weight / bias / input gradient against torch's own nn.Linear chain on the CPU (the reference's MLP.pytorch_fwd)."""
+    from torch import nn
+
+    from nerfstudio_b200.field_components.mlp import MLP
+
+    torch.manual_seed(21)
+    for in_dim, n_layers, width, out_dim, skips, oact in ((63, 8, 256, None, (4,), nn.ReLU()), (283, 2, 128, None, None, nn.ReLU()),
+                                                          (256, 1, 64, 3, None, nn.Sigmoid())):
+        m = MLP(in_dim=in_dim, num_layers=n_layers, layer_width=width, out_dim=out_dim, skip_connections=skips,
+                activation=nn.ReLU(), out_activation=oact, implementation="torch")
+        assert n_layers == 1 or not m._fused, "this configuration must exercise the wide path"
+        m._fused = False
+        x = torch.randn(3000 + 17, in_dim)
+        xr = x.clone().requires_grad_(True)
+        h = xr
+        for i, layer in enumerate(m.layers):  # field_components/mlp.py:160-179
+            if i in m._skip_connections:
+                h = torch.cat([xr, h], -1)
+            h = layer(h)
+            if i < len(m.layers) - 1:
+                h = torch.relu(h)
+        ref = oact(h)
+        dy = torch.randn_like(ref)
+        params = list(m.parameters())
+        g_ref = torch.autograd.grad(ref, [xr] + params, dy)
+        mc = m.cuda()
+        xc = x.cuda().requires_grad_(True)
+        out = mc(xc)
+        assert_close(out, ref, REL, f"wide mlp {in_dim}->{width}")
+        g = torch.autograd.grad(out, [xc] + list(mc.parameters()), dy.cuda())
+        for a, b in zip(g, g_ref):
+            assert_close(a, b, REL, f"wide mlp grad {tuple(b.shape)}")
+
+
 def test_nerfacto_field_analytic_normals(cuda, golden):
     """a20 `Field.forward(compute_normals=True)` / `get_normals`: the position gradient of the hash grid + base MLP
     (hashgrid_bwd dx, mlp_bwd dx) against the reference's autograd, contraction and aabb normalisation."""

@@ -131,6 +131,7 @@ def test_rasterization_full_size_properties(R):
     r2, _, _ = R.rasterization(means, quats, scales, opac, c2, view[None].cuda(), K[None].cuda(), W, H)
     r12, a12, _ = R.rasterization(means, quats, scales, opac, c1 + 2 * c2, view[None].cuda(), K[None].cuda(), W, H)
     assert torch.isfinite(r1).all() and float(a1.min()) >= 0 and float(a1.max()) <= 1.0
-    assert_close(r12, r1 + 2 * r2, 1e-5), assert torch.equal(a1, a12)
+    assert_close(r12, r1 + 2 * r2, 1e-5)
+    assert torch.equal(a1, a12)
     r1b, _, _ = R.rasterization(means, quats, scales, opac, c1, view[None].cuda(), K[None].cuda(), W, H)
     assert torch.equal(r1, r1b)

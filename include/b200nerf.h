@@ -321,6 +321,9 @@ int b2n_occgrid_fill(const float* origins, const float* directions, const float*
 /* exclusive scan of per-ray counts -> pack offsets int64 [n] and the total (device int64) — the step between the count and
  * the fill pass of the march / the pruning (replaces a framework cumsum). */
 int b2n_scan_counts(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* total, void* stream);
+/* same for large n (e.g. 1 M Gaussians): multi-CTA, scratch_sums int32 [ceil(n/1024)], scratch_offsets int64 [ceil(n/1024)] */
+int b2n_scan_counts_ws(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* total, int32_t* scratch_sums,
+                       int64_t* scratch_offsets, void* stream);
 /* packed sample midpoints x[i] = o[ray_i] + d[ray_i] * (ts_i + te_i)/2: what VolumetricSampler.get_sigma_fn evaluates the
  * density at (model_components/ray_samplers.py:406-430). */
 int b2n_packed_positions(const float* origins, const float* directions, const int64_t* ray_indices,

@@ -417,6 +417,69 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
   if (threadIdx.x == 0) *total = carry_s;
 }
 
+// Large inputs (1 M Gaussians' tile counts): three passes — per-block sums (1024 counts per CTA), a one-CTA scan of the
+// block sums, then every CTA re-scans its 1024 counts starting from its block offset.
+__global__ void __launch_bounds__(1024) scan_block_sums_kernel(const int32_t* __restrict__ counts, int64_t n,
+                                                               int32_t* __restrict__ block_sums) {
+  __shared__ int warp_tot[32];
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  int v = i < n ? counts[i] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int w = warp_tot[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = w;
+  }
+}
+__global__ void __launch_bounds__(1024) scan_apply_kernel(const int32_t* __restrict__ counts, int64_t n,
+                                                          const int64_t* __restrict__ block_offsets,
+                                                          int64_t* __restrict__ offsets) {
+  __shared__ long long warp_tot[32], warp_excl[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  const long long v = i < n ? (long long)counts[i] : 0;
+  long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const long long w = warp_tot[lane];
+    long long wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    warp_excl[lane] = wi - w;
+  }
+  __syncthreads();
+  if (i < n) offsets[i] = block_offsets[blockIdx.x] + warp_excl[warp] + incl - v;
+}
+
+extern "C" int b2n_scan_counts_ws(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* total, int32_t* scratch_sums,
+                                  int64_t* scratch_offsets, void* stream) {
+  B2N_REQUIRE(total != nullptr, "null pointer");
+  B2N_REQUIRE(n == 0 || (counts && offsets), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t blocks = div_up(n, 1024);
+  if (n <= 8192 || !scratch_sums || !scratch_offsets) {
+    scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n, offsets, total);
+    B2N_LAUNCH_CHECK();
+  }
+  scan_block_sums_kernel<<<(unsigned)blocks, 1024, 0, st>>>(counts, n, scratch_sums);
+  scan_counts_kernel<<<1, 1024, 0, st>>>(scratch_sums, blocks, scratch_offsets, total);
+  scan_apply_kernel<<<(unsigned)blocks, 1024, 0, st>>>(counts, n, scratch_offsets, offsets);
+  B2N_LAUNCH_CHECK();
+}
+
 extern "C" int b2n_scan_counts(const int32_t* counts, int64_t n, int64_t* offsets, int64_t* total, void* stream) {
   B2N_REQUIRE(total != nullptr, "null pointer");
   B2N_REQUIRE(n == 0 || (counts && offsets), "null pointer");

@@ -944,7 +944,14 @@ def scan_counts(counts: Tensor) -> Tuple[Tensor, int]:
     n = counts.shape[0]
     offsets = torch.empty(n, device=counts.device, dtype=torch.int64)
     total = torch.empty(1, device=counts.device, dtype=torch.int64)
-    call("b2n_scan_counts", ptr(counts, torch.int32), n, ptr(offsets, torch.int64), ptr(total, torch.int64), stream())
+    if n > 8192:
+        blocks = (n + 1023) // 1024
+        sums = torch.empty(blocks, device=counts.device, dtype=torch.int32)
+        offs = torch.empty(blocks, device=counts.device, dtype=torch.int64)
+        call("b2n_scan_counts_ws", ptr(counts, torch.int32), n, ptr(offsets, torch.int64), ptr(total, torch.int64),
+             ptr(sums, torch.int32), ptr(offs, torch.int64), stream())
+    else:
+        call("b2n_scan_counts", ptr(counts, torch.int32), n, ptr(offsets, torch.int64), ptr(total, torch.int64), stream())
     return offsets, int(total.item())
 
 

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "b2n_occgrid_count": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P],
     "b2n_occgrid_fill": [_P, _P, _P, _P, _P, _I32, _I32, _P, _F, _F, _F, _F, _P, _I64, _P, _P, _P, _P, _P],
     "b2n_scan_counts": [_P, _I64, _P, _P, _P],
+    "b2n_scan_counts_ws": [_P, _I64, _P, _P, _P, _P, _P],
     "b2n_packed_positions": [_P, _P, _P, _P, _P, _I64, _P, _P],
     "b2n_packed_prune_count": [_P, _P, _P, _I64, _F, _F, _P, _P, _P],
     "b2n_packed_prune_fill": [_P, _P, _P, _I64, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P],

@@ -500,7 +500,7 @@ def test_occgrid_march_full_size_warp_equals_serial(F):
 
 def test_scan_counts(F):
     torch.manual_seed(12)
-    for n in (1, 31, 1024, 1025, 4096, 5000):
+    for n in (1, 31, 1024, 1025, 4096, 5000, 8193, 1_000_003):
         c = torch.randint(0, 300, (n,), dtype=torch.int32)
         off, total = F.scan_counts(c.cuda())
         cs = torch.cumsum(c.long(), 0)

@@ -118,6 +118,15 @@ def rasterization(means: Tensor, quats: Tensor, scales: Tensor, opacities: Tenso
     if packed or sparse_grad:
         raise NotImplementedError("packed / sparse_grad are not implemented (splatfacto passes False)")
     with_depth = render_mode != "RGB"
+    if means.shape[0] == 0:  # nothing to draw (splatfacto's empty crop): zeros, as get_empty_outputs expects
+        C_ = viewmats.shape[0]
+        ch = {"RGB": 3, "D": 1, "ED": 1}.get(render_mode, 4)
+        z = means.new_zeros(C_, height, width, ch)
+        if backgrounds is not None and ch >= 3:
+            z = torch.cat([z[..., :3] + backgrounds[:, None, None, :], z[..., 3:]], -1)
+        return z, means.new_zeros(C_, height, width, 1), dict(means2d=means.new_zeros(C_, 0, 2), width=width, height=height,
+                                                               radii=torch.zeros(C_, 0, dtype=torch.int32, device=means.device),
+                                                               n_cameras=C_, tile_size=16)
     renders, alphas, infos = [], [], []
     for c in range(viewmats.shape[0]):
         out, alpha, means2d, radii = _Rasterize.apply(means, quats, scales, opacities, colors, viewmats[c], Ks[c], int(width),

@@ -52,7 +52,8 @@ def test_projection_and_binning_vs_oracle(R):
     rad, tt = torch.empty(N, device=dev, dtype=torch.int32), torch.empty(N, device=dev, dtype=torch.int32)
     rgb = torch.empty(N, 3, device=dev)
     vm, kk = host_floats(view.reshape(-1).tolist()), host_floats(K.reshape(-1).tolist())
-    call("b2n_gs_project_fwd", ptr(means.cuda()), ptr(quats.cuda()), ptr(scales.cuda()), ptr(colors.cuda()), 16, 3, N,
+    d_means, d_quats, d_scales, d_sh = means.cuda(), quats.cuda(), scales.cuda(), colors.cuda()  # keep alive across the call
+    call("b2n_gs_project_fwd", ptr(d_means), ptr(d_quats), ptr(d_scales), ptr(d_sh), 16, 3, N,
          C.cast(vm, C.c_void_p), C.cast(kk, C.c_void_p), W, H, 0.01, 1e10, 0.3, 0.0, ptr(m2), ptr(dep), ptr(con),
          ptr(rad, torch.int32), ptr(tt, torch.int32), ptr(rgb), stream())
     live = pr["radii"] > 0

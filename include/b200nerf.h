@@ -429,6 +429,22 @@ int b2n_mse_fwd_bwd(const float* pred, const float* gt, int64_t n, float gscale,
 /* out[0] += scale * sum(rows[0..n)) */
 int b2n_sum_rows(const float* rows, int64_t n, float scale, float* out, void* stream);
 
+/* ---- step glue: keeps the captured training step free of framework launches --------------------------------------
+ * b2n_step_begin: the step's stratified draws and accumulator zeroing in one launch.  uniforms[n] in [0,1) from
+ * Philox-4x32-10: element 4q+j = word j of philox(counter = (q, draw), key = seed) >> 8, times 2^-24;
+ * rng_state3 (device, 3 x uint64) = {seed, draw, 0}: `draw` is advanced by the kernel, so every replay of a captured
+ * graph gets a fresh stream (replaces torch.rand in model_components/ray_samplers.py:99-105, :335-340).
+ * zero0[n_zero0], zero1[n_zero1] are set to 0 (either may be NULL with n = 0). */
+int b2n_step_begin(float* uniforms, int64_t n_uniforms, uint64_t* rng_state3, float* zero0, int64_t n_zero0, float* zero1,
+                   int64_t n_zero1, void* stream);
+/* dst[i] += src[i] */
+int b2n_add_inplace(float* dst, const float* src, int64_t n, void* stream);
+/* out[0] = ((terms[0] + terms[1]) + ...) (+ extra[0] if not NULL): the Trainer's sum over the loss dict
+ * (engine/trainer.py:511). */
+int b2n_loss_total(const float* terms, int32_t n_terms, const float* extra, float* out, void* stream);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (a memset node when captured) */
+int b2n_zero_async(void* ptr, int64_t bytes, void* stream);
+
 /* ---- fused proposal density field (fields/density_fields.py:94-117) ---------------------------
  * ray sample -> unit cube -> hash grid (F=2, <= 8 levels) -> MLP in->16->1 (ReLU) -> avg_init * trunc_exp * selector,
  * ONE launch; the network is read from the device pointers in mlp_host (w[0] [16][in], b[0], w[1] [1][16], b[1]).

@@ -160,6 +160,7 @@ __device__ __forceinline__ float ldg1_early(const float* p) {
   return v;
 }
 
+static int g_tc_bwd_issuer = 1;  // backward: 1 = asynchronous MMA issue (mlp_tc_bwd2_kernel) for nets wider than 16, 2 = always, 0 = never
 #define TC_THREADS 512  // 16 warps: warps w, w+4, w+8, w+12 share TMEM quarter w&3 and split the tile's 64 columns
 #define TC_HALF 16     // columns per thread
 
@@ -939,6 +940,344 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd_kernel(const __grid_
   if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
+
+// mbarrier wait that cannot hang the GPU: a protocol error traps (the launch fails with an error) instead of spinning
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = tc::smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spin > (1u << 26)) asm volatile("trap;");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, dedicated MMA-issuer warp (default; b2n_tune("tc_bwd_issuer", 0) selects the kernel above)
+//
+// Phase profile of the kernel above (profiles/r02_tc_phase.log): 25 % of a tile is thread 0's MMA issue loop — the tensor
+// pipe's time — during which the other 15 warps sit at a CTA barrier, and the CUDA-core phases (input rows, Z store,
+// transposed staging, tcgen05.ld + activation gradient) never overlap it.  Here the 16 warps
+// never meet at a CTA barrier inside the tile loop: they signal 'operands staged' on an mbarrier (512 arrivals)
+// and wait for the tcgen05.commit of exactly the MMA group whose result or whose operand buffer they need next:
+//     worker, per layer:  [Z store] -> wait dW1(prev) -> [T half 0] -> arrive full -> wait dA -> tcgen05.ld dA
+//                         -> wait dW0 -> [T half 1] -> arrive full -> dz = act'(a) * dA
+//     issuer (lane 0 of warp 0, right after its own arrive):
+//                         wait full -> dA MMAs, commit(barA); dW(half 0) MMAs, commit(barW)
+//                         wait full -> dW(half 1) MMAs, commit(barW)
+// so the dW MMAs run under the workers' tcgen05.ld / activation / next layer's input rows and Z store.  Arithmetic and
+// operand layouts are those of the kernel above (dx, hidden-layer gradients bit-identical; dW up to atomics order).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_bwd2_kernel(const __grid_constant__ TcParams p,
+                                                                  const __grid_constant__ TcWeightsTma wt,
+                                                                  const float* __restrict__ x, int64_t x_stride,
+                                                                  const float* __restrict__ y,
+                                                                  const float* __restrict__ hidden,
+                                                                  const float* __restrict__ dy, int64_t n,
+                                                                  float* __restrict__ dx, int64_t dx_stride) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full, bar_a, bar_w;
+  __shared__ uint32_t tmem_slot;
+  uint8_t* Zh = smem;                                   // dZ tile, K-major [128][64]
+  uint8_t* Zl = Zh + TC_TILE_BYTES;
+  uint8_t* TZ = Zl + TC_TILE_BYTES;                     // stacked dZ^T: rows 0-63 hi, 64-127 lo; 64 point columns
+  uint8_t* TAh = TZ + TC_TZ_BYTES;                      // A^T hi (+ ones row)
+  uint8_t* TAl = TAh + TC_TA_BYTES;                     // A^T lo
+  uint8_t* Wr = TAl + TC_TA_BYTES;                      // W^T hi/lo per layer: K-major [K rows][N cols]
+  const int t = threadIdx.x, warp = t >> 5, quarter = warp & 3;
+  const int r = t & (TC_ROWS - 1), c0 = ((t >> 7) & 3) * TC_HALF;
+  const int L = p.n_layers;
+  __shared__ uint64_t bar_wt;
+
+  if (wt.rows > 0) {  // packed W^T image by TMA
+    if (t == 0) {
+      tc::mbar_init(&bar_wt, 1);
+      tma_issue_weights(wt, Wr, &bar_wt);
+    }
+  } else {
+  for (int l = 0; l < L; ++l) {
+    const int N = p.N[l], K = p.K[l], nr = p.nr[l], kr = p.kr[l];
+    // transposed (row = input index k, col = output index j), hi rows 0..K-1 and lo rows K..2K-1 stacked along the
+    // MMA's N: dA = [dZ_hi W_hi | dZ_hi W_lo] (N' = 2K) + dZ_lo W_hi (N' = K) in two streams
+    uint8_t* wst = Wr + p.w_off[l];
+    const uint32_t cs = (uint32_t)(2 * K) * 16u;
+#pragma unroll 4
+    for (int idx = t; idx < N * K; idx += TC_THREADS) {
+      const int j = idx / K, k = idx - j * K;
+      const float v = (j < nr && k < kr) ? __ldg(p.w[l] + (size_t)j * kr + k) : 0.f;
+      float h, lo;
+      tc::split_tf32(v, h, lo);
+      *reinterpret_cast<float*>(wst + tc::canon_off(k, j, cs)) = h;
+      *reinterpret_cast<float*>(wst + tc::canon_off(K + k, j, cs)) = lo;
+    }
+  }
+  }
+  if (t == 0) {
+    tc::mbar_init(&bar_full, TC_THREADS), tc::mbar_init(&bar_a, 1), tc::mbar_init(&bar_w, 1);
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (wt.rows > 0) mbar_wait_guard(&bar_wt, 0);  // W^T image has landed (TMA complete_tx)
+  const uint32_t tmem = tmem_slot;
+  uint32_t dw_started = 0;  // bit l: the layer's dW accumulator has been written once (issuer only)
+  const int DW_COL0 = 128, DW_COLS = 80;  // D (dA, two partial products) occupies columns 0..127
+  const bool xvec = quad_ok(x, x_stride);
+  const bool dxvec = dx != nullptr && quad_ok(dx, dx_stride);
+  const int wrow = 32 * quarter;  // first tile row of this warp
+  // input rows of layer l (x or the saved hidden activations) for this thread's (row, column slice): `issue_a` starts
+  // the loads one layer ahead (raw registers), `finish_a` turns them into row-owner values where they are consumed
+  auto a_is_quad = [&](int l) -> bool {  // warp-uniform
+    if (l == 0) return xvec;
+    return (p.kr[l] & 3) == 0 && quad_ok(hidden + p.hid_off[l - 1] * n, p.kr[l]);
+  };
+  auto issue_a = [&](int l, int64_t tile, int64_t row, bool live, float (&raw)[TC_HALF]) {
+    const int kr = p.kr[l];
+    if (c0 >= p.K[l]) {  // warp-uniform
+#pragma unroll
+      for (int c = 0; c < TC_HALF; ++c) raw[c] = 0.f;
+      return;
+    }
+    const float* src = (l == 0) ? x : hidden + p.hid_off[l - 1] * n;
+    const int64_t stride = (l == 0) ? x_stride : (int64_t)kr;
+    if (a_is_quad(l)) load_rows_quad_issue(src, stride, tile * TC_ROWS + wrow, n, c0, kr, raw);
+    else load_global_half(src + row * stride, live, false, c0, kr, p.K[l], raw);
+  };
+  auto finish_a = [&](int l, const float (&raw)[TC_HALF], float (&dst)[TC_HALF]) {
+    if (c0 < p.K[l] && a_is_quad(l)) {
+      load_rows_quad_finish(c0, p.kr[l], raw, dst);
+    } else {
+#pragma unroll
+      for (int c = 0; c < TC_HALF; ++c) dst[c] = raw[c];
+    }
+  };
+  const int64_t n_tiles = (n + TC_ROWS - 1) / TC_ROWS;
+  uint32_t ph_a = 0, ph_w = 0, ph_f = 0;  // parities of bar_a / bar_w (workers) and bar_full (issuer)
+  bool w_pending = false;                 // a dW group has been committed on bar_w and not yet waited for (uniform)
+  // MMA groups of (layer l, tile half ph), issued by lane 0 of warp 0 once all 512 threads have staged their operands
+  auto issue_group = [&](int l, int ph, bool need_da) {
+    const int N = p.N[l], K = p.K[l];
+    mbar_wait_guard(&bar_full, ph_f);
+    ph_f ^= 1;
+    tc::fence_after_sync();
+    if ((t & 31) == 0) {
+      if (ph == 0 && need_da) {  // dA = dZ W first: every thread's critical path waits for it
+        const uint32_t cs = (uint32_t)(2 * K) * 16u;
+        const uint32_t wst = tc::smem_u32(Wr + p.w_off[l]);
+        uint32_t acc2 = 0;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const uint32_t idx = tc::make_idesc_tf32(TC_ROWS, pass ? K : 2 * K, false, false);
+          uint64_t ad = tc::make_desc(tc::smem_u32(pass ? Zl : Zh), TC_CS_A, 128), bd = tc::make_desc(wst, cs, 128);
+#pragma unroll 2
+          for (int s = 0; s < N / 8; ++s) {
+            tc::mma_tf32(tmem, ad, bd, idx, acc2);
+            ad += (uint64_t)((2 * TC_CS_A) >> 4), bd += (uint64_t)((2 * cs) >> 4);
+            acc2 = 1;
+          }
+        }
+        tc::commit(&bar_a);
+      }
+      const uint32_t idesc_w = tc::make_idesc_tf32(TC_ROWS, K + 16, false, false);
+      const uint32_t dcol = tmem + (uint32_t)(DW_COL0 + DW_COLS * l);
+      uint32_t acc = (dw_started >> l) & 1u;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        uint64_t ad = tc::make_desc(tc::smem_u32(TZ), TC_CS_TZ, 128);
+        uint64_t bd = tc::make_desc(tc::smem_u32(pass ? TAl : TAh), TC_CS_TA, 128);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          tc::mma_tf32(dcol, ad, bd, idesc_w, acc);
+          ad += (uint64_t)((2 * TC_CS_TZ) >> 4), bd += (uint64_t)((2 * TC_CS_TA) >> 4);
+          acc = 1;
+        }
+      }
+      dw_started |= 1u << l;
+      tc::commit(&bar_w);
+    }
+    __syncwarp();
+  };
+  {
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t row = tile * TC_ROWS + r;
+      const bool live = row < n;
+      {  // pull the NEXT tile's rows into L2 (no registers)
+        const int64_t nrow = row + (int64_t)gridDim.x * TC_ROWS;
+        if (nrow < n) {
+          if (c0 == 0) {
+            tc::prefetch_l2(dy + nrow * p.nr[L - 1]);
+            tc::prefetch_l2(y + nrow * p.nr[L - 1]);
+          }
+          if (c0 < p.K[0]) tc::prefetch_l2(x + nrow * x_stride + c0);
+          for (int l = 1; l < L; ++l)
+            if (c0 < p.K[l]) tc::prefetch_l2(hidden + p.hid_off[l - 1] * n + nrow * p.kr[l] + c0);
+        }
+      }
+      float dz[TC_HALF], a[TC_HALF];
+      {  // dZ of the last layer = dy * act'(y)   (this thread's column slice)
+        const int nr = p.nr[L - 1];
+        if (c0 < nr && (nr & 3) == 0 && quad_ok(dy, nr) && quad_ok(y, nr)) {  // warp-uniform
+          float yv[TC_HALF];
+          load_rows_quad(dy, nr, tile * TC_ROWS + wrow, n, c0, nr, dz);
+          load_rows_quad(y, nr, tile * TC_ROWS + wrow, n, c0, nr, yv);
+          act_grad_slice(p.out_act, dz, yv);
+        } else {
+          float yv[TC_HALF];
+#pragma unroll
+          for (int c = 0; c < TC_HALF; ++c) {
+            const bool on = c0 + c < nr && live;
+            dz[c] = on ? __ldg(dy + row * nr + c0 + c) : 0.f;
+            yv[c] = on ? __ldg(y + row * nr + c0 + c) : 0.f;
+          }
+          act_grad_slice(p.out_act, dz, yv);
+        }
+      }
+      float a_next[TC_HALF];
+      issue_a(L - 1, tile, row, live, a_next);
+      for (int l = L - 1; l >= 0; --l) {
+        const int N = p.N[l], K = p.K[l];
+        finish_a(l, a_next, a);
+        if (l > 0) issue_a(l - 1, tile, row, live, a_next);
+        const bool need_da = (l > 0) || (dx != nullptr);
+        // Z is free: the dA MMAs of the previous layer (the only readers) completed before this thread's tcgen05.ld
+        if (need_da) store_half_hilo(Zh, Zl, r, c0, dz, N);
+        if (w_pending) {  // the transposed tiles are free once the previous dW(half 1) group has completed
+          mbar_wait_guard(&bar_w, ph_w);
+          ph_w ^= 1, w_pending = false;
+        }
+        auto stage_T = [&](int ph) {  // rows of tile half `ph`: dZ^T (hi/lo stacked), A^T (hi, lo), ones / padding rows
+          if ((r >> 6) == ph) {
+            const int pc = r & 63;  // point column inside the half
+#pragma unroll
+            for (int j = 0; j < TC_HALF; ++j) {
+              float h = 0.f, lo = 0.f;
+              if (c0 + j < N) tc::split_tf32(dz[j], h, lo);
+              *reinterpret_cast<float*>(TZ + tc::canon_off(c0 + j, pc, TC_CS_TZ)) = h;
+              *reinterpret_cast<float*>(TZ + tc::canon_off(64 + c0 + j, pc, TC_CS_TZ)) = lo;
+            }
+#pragma unroll
+            for (int k = 0; k < TC_HALF; ++k) {
+              if (c0 + k < K) {
+                float h, lo;
+                tc::split_tf32(a[k], h, lo);
+                *reinterpret_cast<float*>(TAh + tc::canon_off(c0 + k, pc, TC_CS_TA)) = h;
+                *reinterpret_cast<float*>(TAl + tc::canon_off(c0 + k, pc, TC_CS_TA)) = lo;
+              }
+            }
+            if (c0 == 0) {  // ones row (-> bias gradient) and zero padding rows K..K+15
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                *reinterpret_cast<float*>(TAh + tc::canon_off(K + k, pc, TC_CS_TA)) = (k == 0 && live) ? 1.f : 0.f;
+                *reinterpret_cast<float*>(TAl + tc::canon_off(K + k, pc, TC_CS_TA)) = 0.f;
+              }
+            }
+          }
+          tc::fence_smem_to_async();
+          tc::fence_before_sync();  // orders this thread's earlier TMEM reads before the issuer's next MMAs
+          tc::mbar_arrive(&bar_full);
+          if (warp == 0) issue_group(l, ph, need_da);
+        };
+        stage_T(0);
+        float da[TC_HALF];
+        if (need_da) {  // dA of this layer is issued first: ready long before the dW(half 0) group finishes
+          __syncwarp();
+          mbar_wait_guard(&bar_a, ph_a);
+          __syncwarp();
+          ph_a ^= 1;
+          tc::fence_after_sync();
+          float da2[TC_HALF];
+          load_half(tmem, quarter, 0, c0, K, da);
+          load_half(tmem, quarter, K, c0, K, da2);  // the dZ_hi W_lo partial product
+#pragma unroll
+          for (int c = 0; c < TC_HALF; ++c) da[c] += da2[c];
+        }
+        mbar_wait_guard(&bar_w, ph_w);  // dW(half 0) done: the transposed tiles may be rewritten
+        ph_w ^= 1;
+        stage_T(1);  // still THIS layer's dz and a
+        w_pending = true;
+        if (need_da) {  // runs under the dW(half 1) MMAs
+          if (l > 0) {
+#pragma unroll
+            for (int c = 0; c < TC_HALF; ++c) dz[c] = da[c];  // padded columns: zero weight rows give dA = 0
+            act_grad_slice(p.hidden_act, dz, a);
+          } else if (dxvec) {
+            if (c0 < p.in_dim) store_rows_quad(dx, dx_stride, tile * TC_ROWS + wrow, n, c0, p.in_dim, da);  // warp-uniform
+          } else if (live) {
+            float* dr = dx + row * dx_stride;
+#pragma unroll
+            for (int c = 0; c < TC_HALF; ++c)
+              if (c0 + c < p.in_dim) dr[c0 + c] = da[c];
+          }
+        }
+      }
+    }
+    if (w_pending) {  // every MMA of this CTA has completed before the accumulators are read
+      mbar_wait_guard(&bar_w, ph_w);
+      ph_w ^= 1;
+    }
+    tc::fence_after_sync();
+  }
+  // ---- flush dW / db: lanes 0-63 hold dZ_hi^T [A_hi + A_lo], lanes 64-127 the dZ_lo^T part
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  // The lo-part lanes hand their values to the hi-part lanes through shared memory (the dZ tile region is free now),
+  // and rows go out as 128-bit REDs where the gradient row is 16-byte aligned: 8x fewer L2 atomics than one atomicAdd
+  // per lane and element (148 CTAs all add into the same few KB).
+  float* scratch = reinterpret_cast<float*>(Zh);  // [4 column groups][64 rows][20 floats (16 + pad)]
+  for (int l = 0; l < L; ++l) {
+    if (p.dw[l] == nullptr && p.db[l] == nullptr) continue;
+    const int K = p.K[l], kr = p.kr[l], nr = p.nr[l];
+    const int j = r & 63;
+    const bool started = blockIdx.x < n_tiles;
+    const bool vec = p.dw[l] != nullptr && (kr & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dw[l]) & 15) == 0;
+    for (int base = 0; base < K + 16; base += 64) {  // uniform trip count: the loop body synchronises the CTA
+      const int cc = base + c0;
+      const bool active = cc < K + 16;  // warp-uniform
+      float v[16];
+      if (active) tc::ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(DW_COL0 + DW_COLS * l + cc), v);
+      float* sc = scratch + ((c0 >> 4) * 64 + j) * 20;
+      if (active && r >= 64) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(sc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      __syncthreads();
+      if (active && r < 64 && started && j < nr) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 o = *reinterpret_cast<const float4*>(sc + i);
+          const float g0 = v[i] + o.x, g1 = v[i + 1] + o.y, g2 = v[i + 2] + o.z, g3 = v[i + 3] + o.w;
+          const int k = cc + i;
+          if (vec && k + 4 <= kr) {
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.dw[l] + (size_t)j * kr + k),
+                         "f"(g0), "f"(g1), "f"(g2), "f"(g3)
+                         : "memory");
+          } else {
+            const float g[4] = {g0, g1, g2, g3};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (k + e < kr && p.dw[l]) atomicAdd(p.dw[l] + (size_t)j * kr + k + e, g[e]);
+              else if (k + e == K && p.db[l]) atomicAdd(p.db[l] + j, g[e]);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+
 // ------------------------------------------------------------------------------------------------
 static int tc_build(const B2nMlp* m, const B2nMlpGrad* g, TcParams& p, bool transposed) {
   memset(&p, 0, sizeof(p));
@@ -1061,6 +1400,10 @@ extern "C" int b2n_mlp_tc_pack(const B2nMlp* mlp_host, void* workspace, void* st
 
 static int g_tc_fwd_slots = 2;  // 2: warp-specialised two-slot kernel (default), 1: serial kernel
 int b2n_tune_mlp_tc(const char* key, int value) {
+  if (strcmp(key, "tc_bwd_issuer") == 0 && value >= 0 && value <= 2) {
+    g_tc_bwd_issuer = value;
+    return 1;
+  }
   if (strcmp(key, "tc_fwd_slots") == 0 && (value == 1 || value == 2)) {
     g_tc_fwd_slots = value;
     return 1;
@@ -1127,8 +1470,16 @@ extern "C" int b2n_mlp_tc_bwd_ws(const B2nMlp* mlp_host, const B2nMlpGrad* grad_
         make_weight_map(wt, static_cast<const uint8_t*>(workspace) + fwd_image_bytes(pf), bwd_image_bytes(p)) != 0)
       wt.rows = 0;
   }
-  cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = (int)min(div_up(n, TC_ROWS), (int64_t)b2n_sm_count());
+  int widest = 0;
+  for (int l = 0; l < p.n_layers; ++l) widest = max(widest, max(p.N[l], p.K[l]));
+  // measured (scripts/tc_bench.py): head 64-64-3 0.279 -> 0.259 ms, base 32-64-16 unchanged, a 10-16-1 net 5 % slower
+  if (g_tc_bwd_issuer == 2 || (g_tc_bwd_issuer == 1 && widest > 16)) {
+    cudaFuncSetAttribute(mlp_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    mlp_tc_bwd2_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, wt, x, x_stride, y, hidden, dy, n, dx, dx_stride);
+    B2N_LAUNCH_CHECK();
+  }
+  cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   mlp_tc_bwd_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(p, wt, x, x_stride, y, hidden, dy, n, dx, dx_stride);
   B2N_LAUNCH_CHECK();
 }

@@ -193,7 +193,12 @@ class NerfactoStep:
         self.emb_mean = torch.zeros(1, max(self.n_emb, 1), **f32)    # eval: mean appearance embedding (or zeros)
         self.rows = [torch.zeros(R, **f32) for _ in range(3)]
         self.losses = torch.zeros(5, **f32)  # rgb, interlevel, distortion, total, camera-optimiser regulariser
-        self.jitter = [torch.zeros(R, 1, **f32) for _ in range(3)]
+        self.jitter_all = torch.zeros(3, R, 1, **f32)  # stratified draws of the three sampling levels, one launch per step
+        self.jitter = list(self.jitter_all.unbind(0))
+        # Philox state {seed, draw counter, block tickets} on the device: every replay of the captured step draws afresh
+        rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+        seed = (torch.initial_seed() + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF  # ranks draw independent streams
+        self.rng_state = torch.tensor([seed, 0, 0], dtype=torch.int64, device=self.dev)
         self.step_count = 0
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._steps_since_update = 0
@@ -358,14 +363,13 @@ class NerfactoStep:
         R, S0, S1, S2 = self.R, *self.S
         cfg = self.cfg
         st = stream
-        self.optim.flat_grad.zero_()
-        self.losses.zero_()
-        if self.camopt is not None:
-            self.d_rays.zero_()
-        if self.fixed_jitter is None:
-            for j in self.jitter:
-                j.copy_(torch.rand(R, 1, device=self.dev))
-        else:  # tests: replay recorded stratified draws
+        g = self.optim.flat_grad
+        call("b2n_zero_async", ptr(g), g.numel() * g.element_size(), st())
+        draw = self.fixed_jitter is None
+        call("b2n_step_begin", ptr(self.jitter_all) if draw else NULL, 3 * R if draw else 0, ptr(self.rng_state, torch.int64),
+             ptr(self.losses), self.losses.numel(), ptr(self.d_rays) if self.camopt is not None else NULL,
+             self.d_rays.numel() if self.camopt is not None else 0, st())
+        if not draw:  # tests: replay recorded stratified draws
             for j, src in zip(self.jitter, self.fixed_jitter):
                 j.copy_(src)
         self._forward()
@@ -385,7 +389,7 @@ class NerfactoStep:
         # ---------------- backward: main field
         call("b2n_composite_bwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.d_rgb_out), NULL, NULL,
              R, S2, bg_mode, bg_ptr, ptr(self.d_rgb), ptr(self.d_w[2]), st())
-        self.d_w[2].add_(self.d_w_dist)
+        call("b2n_add_inplace", ptr(self.d_w[2]), ptr(self.d_w_dist), self.d_w[2].numel(), st())
         call("b2n_weights_bwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), ptr(self.d_w[2]), R, S2, ptr(self.d_dens[2]), st())
         call("b2n_density_act_bwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), ptr(self.d_dens[2]), N2, self.avg,
              ptr(self.d_hpre), 1, st())
@@ -407,7 +411,7 @@ class NerfactoStep:
             cc = self.camopt.config  # regulariser (camera_optimizers.py:155-162): value into losses[4], gradient into the poses
             call("b2n_pose_regularizer", ptr(self.cam_pose), self.cam_pose.shape[0], float(cc.trans_l2_penalty),
                  float(cc.rot_l2_penalty), 1.0, _off(self.losses, 4), ptr(self.cam_pose.grad), st())
-        self.losses[3:4].copy_(self.losses[0:3].sum(0, keepdim=True) + self.losses[4:5])
+        call("b2n_loss_total", ptr(self.losses), 3, _off(self.losses, 4), _off(self.losses, 3), st())
 
     def _body_props(self, update_props: bool) -> None:
         """backward of the proposal networks (only the interlevel loss reaches them)."""

@@ -122,6 +122,10 @@ _SIGNATURES = {
     "b2n_head_input_bwd": [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _P],
     "b2n_mse_fwd_bwd": [_P, _P, _I64, _F, _P, _P, _P],
     "b2n_sum_rows": [_P, _I64, _F, _P, _P],
+    "b2n_step_begin": [_P, _I64, _P, _P, _I64, _P, _I64, _P],
+    "b2n_add_inplace": [_P, _P, _I64, _P],
+    "b2n_loss_total": [_P, _I32, _P, _P, _P],
+    "b2n_zero_async": [_P, _I64, _P],
     "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P],
 }
 _RET = {"b2n_version": C.c_char_p, "b2n_last_error": C.c_char_p}

@@ -822,3 +822,23 @@ def camera_opt_apply(pose_adjustment: Tensor, camera_indices: Tensor, origins: T
 def camera_opt_regularizer(pose_adjustment: Tensor, trans_l2_penalty: float = 1e-2, rot_l2_penalty: float = 1e-3) -> Tensor:
     return (pose_adjustment[:, :3].norm(dim=-1).mean() * trans_l2_penalty
             + pose_adjustment[:, 3:].norm(dim=-1).mean() * rot_l2_penalty)
+
+
+def philox_uniform(n: int, seed: int, draw: int):
+    """Uniform [0,1) floats of b2n_step_begin (include/b200nerf.h): element 4q+j = word j of Philox-4x32-10 (Salmon et
+    al., SC'11, "Parallel random numbers: as easy as 1, 2, 3") with counter (q_lo, q_hi, draw_lo, draw_hi) and key
+    (seed_lo, seed_hi), top 24 bits scaled by 2^-24.  Restated from the paper; the reference draws with torch.rand
+    (ray_samplers.py:99-105), whose values are not part of the parity contract."""
+    import numpy as np
+
+    q = np.arange((n + 3) // 4, dtype=np.uint64)
+    c = [q & 0xFFFFFFFF, q >> np.uint64(32), np.full_like(q, draw & 0xFFFFFFFF), np.full_like(q, (draw >> 32) & 0xFFFFFFFF)]
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    for _ in range(10):
+        p0, p1 = m0 * c[0], m1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & 0xFFFFFFFF, p1 >> np.uint64(32), p1 & 0xFFFFFFFF
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    words = np.stack(c, axis=1).reshape(-1)[:n]
+    return ((words >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)).astype(np.float32)

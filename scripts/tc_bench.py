@@ -28,6 +28,12 @@ for name in which:
         return e0.elapsed_time(e1) / reps
     y, hid = F.mlp_tc_forward(spec, x, ws, bs, True, x_stride=stride)
     ys, hids = F.mlp_forward(spec, xs, ws, bs, True)
+    from nerfstudio_b200 import lib
+    image = F.mlp_tc_pack(spec, ws, bs)
+    for issuer in (0, 2):
+        lib.tune("tc_bwd_issuer", issuer)
+        print(name, "tc bwd (tma image) issuer=%d %.3f ms" % (issuer, t(lambda: F.mlp_tc_backward(spec, x, y, hid, dy, ws, bs, dws, dbs, True, workspace=image), reps=20)))
+    lib.tune("tc_bwd_issuer", 1)
     print(name, "tc fwd %.3f ms" % t(lambda: F.mlp_tc_forward(spec, x, ws, bs, True, x_stride=stride)),
           "simt fwd %.3f ms" % t(lambda: F.mlp_forward(spec, xs, ws, bs, True)),
           "tc bwd %.3f ms" % t(lambda: F.mlp_tc_backward(spec, x, y, hid, dy, ws, bs, dws, dbs, True)),

@@ -3,6 +3,7 @@
 Bars (north_star): bit-exact for integer / index outputs, <= 1e-4 relative (max-norm) for fp32 — most ops are
 held to a tighter 2e-5.  All calls go through nerfstudio_b200.functional -> ctypes -> libb200nerf.so.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -684,3 +685,37 @@ def test_other_spaced_samplers_golden(F, golden):
             sb, eb = F.spaced_sample(cu(g["nears"]), cu(g["fars"]), 24, kind, cu(jit) if jit is not None else None)
             assert torch.equal(sb.cpu(), g[f"{kind}_{mode}_sbins"].expand(64, -1)), (kind, mode)
             assert_close(eb, g[f"{kind}_{mode}_ebins"], tol, f"{kind} {mode}")
+
+
+def test_step_begin_philox_and_zeroing():
+    """b2n_step_begin: draws bit-equal to the Philox oracle for (seed, draw), the draw counter advances per launch (also
+    across replays of a captured graph), accumulators are zeroed."""
+    from nerfstudio_b200 import lib
+    from nerfstudio_b200.lib import call, ptr, stream
+
+    n = 3 * 4096 + 5
+    seed = 0x1234ABCD5678
+    state = torch.tensor([seed, 7, 0], dtype=torch.int64, device="cuda")
+    u = torch.empty(n, device="cuda")
+    z0, z1 = torch.ones(5, device="cuda"), torch.ones(2 * 4096 * 3, device="cuda")
+    call("b2n_step_begin", ptr(u), n, ptr(state, torch.int64), ptr(z0), z0.numel(), ptr(z1), z1.numel(), stream())
+    assert np.array_equal(u.cpu().numpy(), O.philox_uniform(n, seed, 7))
+    assert state.tolist() == [seed, 8, 0]
+    assert float(z0.abs().max()) == 0.0 and float(z1.abs().max()) == 0.0
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g):
+            call("b2n_step_begin", ptr(u), n, ptr(state, torch.int64), ptr(None), 0, ptr(None), 0, stream())
+    for k in range(3):
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(u.cpu().numpy(), O.philox_uniform(n, seed, 8 + k)), k
+    assert state.tolist() == [seed, 11, 0]
+    a, b = torch.randn(1000, device="cuda"), torch.randn(1000, device="cuda")
+    want = a + b
+    call("b2n_add_inplace", ptr(a), ptr(b), 1000, stream())
+    assert torch.equal(a, want)
+    t = torch.tensor([0.1, 0.2, 0.3, 0.0, 0.7], device="cuda")
+    call("b2n_loss_total", ptr(t), 3, ptr(t[4:]), ptr(t[3:]), stream())
+    assert float(t[3]) == float(((t[0] + t[1]) + t[2]) + t[4])

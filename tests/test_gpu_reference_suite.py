@@ -1,9 +1,6 @@
-"""NOT COLLECTED (file name does not match test_*.py): GPU mirrors of the reference's own component tests, written at
-the end of round 1 after the GPU budget was spent — to be run, fixed where our API differs, and moved into tests/ as
-`test_gpu_reference_suite.py` first thing in round 2.
-
-Each test restates one test of /root/reference/tests (cited), with tensors on the GPU and our mirrors of the classes.
-Run by hand:  python -m pytest tests/pending_round2/reference_component_suite.py -q -p no:cacheprovider
+"""GPU mirrors of the reference's own component tests (/root/reference/tests, each test cites the one it restates): the
+same constructions and assertions, tensors on the GPU, through our mirrors of the classes — what a reference user's own
+test-suite would exercise after switching packages.
 """
 import pytest
 import torch

@@ -42,6 +42,8 @@ def test_tcgen05_tf32_gemm_and_3xtf32_split(F):
         assert e3 < 5e-6, (N, K, e3)
 
 
+TC_BWD_ISSUER_DEFAULT = 1  # csrc/mlp_tc.cu g_tc_bwd_issuer
+
 CFGS = {
     "base": (32, [64, 16], "none"),
     "head": (63, [64, 64, 3], "sigmoid"),
@@ -169,3 +171,42 @@ def test_mlp_tc_tma_weight_image_bitwise(F, name):
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1] + outs[0][2], outs[1][1] + outs[1][2]):
         assert_close(a, b, 1e-5)
+
+
+@pytest.mark.parametrize("name", list(CFGS))
+@pytest.mark.parametrize("want_dx", [True, False])
+def test_backward_variants_agree(F, name, want_dx):
+    """The backward with the asynchronous MMA issue (tune tc_bwd_issuer = 1: mbarrier hand-offs instead of CTA barriers)
+    runs the same MMA sequence on the same operands as the serial kernel: dx bit-identical, dW/db to atomics-order
+    round-off.  Ragged batch with several tiles per CTA, with and without the TMA weight image."""
+    from nerfstudio_b200 import lib
+
+    in_dim, dims, out_act = CFGS[name]
+    torch.manual_seed(zlib.crc32(name.encode()) % 1000 + 2)
+    n = 128 * 148 * 3 + 41
+    spec = F.MlpSpec(in_dim, dims, out_act=out_act)
+    x = torch.randn(n, in_dim, device="cuda")
+    ws_, bs_, prev = [], [], in_dim
+    for o in dims:
+        ws_.append((torch.randn(o, prev, device="cuda") / prev ** 0.5).contiguous()), bs_.append(torch.randn(o, device="cuda") * 0.1)
+        prev = o
+    image = F.mlp_tc_pack(spec, ws_, bs_)
+    y, hidden = F.mlp_tc_forward(spec, x, ws_, bs_, True)
+    dy = torch.randn_like(y)
+    outs = {}
+    try:
+        for issuer in (0, 2):
+            assert lib.tune("tc_bwd_issuer", issuer)
+            for tag, wsp in (("scalar", None), ("tma", image)):
+                dws, dbs = [torch.zeros_like(w) for w in ws_], [torch.zeros_like(b) for b in bs_]
+                dx = F.mlp_tc_backward(spec, x, y, hidden, dy, ws_, bs_, dws, dbs, want_dx, workspace=wsp)
+                torch.cuda.synchronize()
+                outs[(issuer, tag)] = (dx, dws + dbs)
+    finally:
+        lib.tune("tc_bwd_issuer", TC_BWD_ISSUER_DEFAULT)
+    for tag in ("scalar", "tma"):
+        a, b = outs[(0, tag)], outs[(2, tag)]
+        if want_dx:
+            assert torch.equal(a[0], b[0]), tag
+        for u, v in zip(a[1], b[1]):
+            assert_close(u, v, 1e-5, tag)

@@ -3,7 +3,8 @@ bytes (dram__bytes_read.sum + dram__bytes_write.sum), L2 bytes (lts__t_sectors.s
 activity of the hash / MLP / Adam kernels, keyed exactly as bench.py names its C-ABI calls — plus a per-kernel table.
 
     ncu --set full --clock-control none --import-source on -k regex:'hashgrid|density_fused|mlp_tc|adam|live_compact' \
-        -c 16 -f -o gpurun_out/r02_full python bench.py --engine eager --steps 1 --warmup 3 --windows 1 --no-cpu-baseline --no-eval
+        --launch-skip 128 -c 32 -f -o gpurun_out/r02_full \
+        python bench.py --engine eager --steps 2 --warmup 3 --windows 1 --state-step 8 --no-cpu-baseline --no-eval   (scripts/gpu_final.sh)
     ncu -i gpurun_out/r02_full.ncu-rep --page raw --csv > gpurun_out/r02_full_raw.csv
     python scripts/ncu_traffic.py gpurun_out/r02_full_raw.csv profiles/ncu_traffic.json profiles/r02_ncu_summary.csv
 
@@ -24,6 +25,7 @@ ORDER = [  # (kernel-name fragment, [bench keys in launch order within a step])
     ("mlp_tc_fwd", [f"b2n_mlp_tc_fwd[n={R * 48},in=32,out=16]", f"b2n_mlp_tc_fwd[n={R * 48},in=63,out=3]"]),
     ("mlp_tc_bwd", [f"b2n_mlp_tc_bwd[n={R * 48},in=63,out=3]", f"b2n_mlp_tc_bwd[n={R * 48},in=32,out=16]"]),
     ("hashgrid_bwd", [f"b2n_hashgrid_bwd[n={R * 48}]"]),
+    ("hashgrid_dx", [f"b2n_hashgrid_dx[n={R * 48}]"]),
     ("density_fused_bwd", [f"b2n_density_field_bwd[n={R * 256}]", f"b2n_density_field_bwd[n={R * 96}]"]),
     ("adam", ["b2n_adam_step_dev"]),
 ]

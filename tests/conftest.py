@@ -61,4 +61,5 @@ def assert_grad_close(a, b, name="", rel=1e-4, sparse_switching=False):
     x, y = a.double().flatten(), b.double().flatten()
     cos = float((x @ y) / (x.norm() * y.norm()).clamp_min(1e-300))
     ratio = float(x.norm() / y.norm().clamp_min(1e-300))
-    assert cos > 0.999 and abs(ratio - 1) < 2e-2, f"{name}: cosine {cos:.6f}, norm ratio {ratio:.5f}"
+    # measured on B200 (scripts/composed_errors.py): cosine >= 0.999999, norm ratio within 5.1e-4, entries up to 1.6e-3
+    assert cos > 0.99999 and abs(ratio - 1) < 2e-3, f"{name}: cosine {cos:.7f}, norm ratio {ratio:.6f}"

@@ -37,18 +37,21 @@ def test_engine_step_equals_reference_losses_and_grads(cuda, golden):
     eng.optim.lr = 0.0  # keep the weights so that gradients can be read back unchanged
     losses = eng.step().cpu()
     assert_close(losses[0], g["loss_rgb"], 1e-4)
-    # a sum of a few clipped squares: the ~1e-5 sample shifts of two stacked inverse-CDF steps move it by ~5e-4
-    assert_close(losses[1], g["loss_interlevel"], 2e-3)
+    # a sum of a few clipped squares: the ~1e-5 sample shifts of two stacked inverse-CDF steps move it by 4.8e-4
+    # (measured, scripts/composed_errors.py); with the reference's samples fed in (staged test below) it meets 1e-4
+    assert_close(losses[1], g["loss_interlevel"], 1e-3)
     assert_close(losses[2], g["loss_distortion"], 1e-4)
     assert_close(losses[3], g["loss"], 1e-4)
     from test_gpu_modules import _named_params
 
     for k, p in _named_params(model).items():
         # switching gradients (see conftest.assert_grad_close): everything that only the interlevel loss reaches
-        # (proposal networks) and the hash tables; the MLP weights are compared entry-wise at 5e-3 — end to end they sit
-        # behind two stochastic-free but ill-conditioned resampling steps (a 1e-5 sample shift moves grid features by
-        # ~1e-3); the 1e-4 bar is enforced per operator on identical inputs in test_gpu_ops.py / test_gpu_tc.py
-        assert_grad_close(p.grad, g["g_" + k], "g_" + k, 5e-3, sparse_switching=k.startswith("p") or "table" in k)
+        # (proposal networks) and the hash tables; the MLP weights are compared entry-wise at 2.5e-3 (measured: up to
+        # 1.2e-3 on the base MLP's first layer, 1e-5 and below on the head) — end to end they sit behind two
+        # ill-conditioned resampling steps: the density networks agree with torch's to 1.6e-7, the inverse-CDF steps turn
+        # that into 7e-6 / 1.7e-5 sample shifts, and the x1000 test tables amplify those.  The 1e-4 bar is enforced
+        # entry-wise on identical inputs per operator (test_gpu_ops.py / test_gpu_tc.py) and composed in the staged test
+        assert_grad_close(p.grad, g["g_" + k], "g_" + k, 2.5e-3, sparse_switching=k.startswith("p") or "table" in k)
     assert_close(eng.rgb_out, g["train_rgb"], 1e-4)
     assert_close(eng.acc[:, None], g["train_acc"], 1e-4)
 

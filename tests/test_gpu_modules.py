@@ -258,7 +258,7 @@ def test_full_nerfacto_pipeline_train_and_eval(cuda, golden):
                 # level i weights are evaluated at level i-1's resampled positions: the 1e-7 cdf differences of
                 # two stacked inverse-CDF steps (and powf for the anneal) move samples by ~1e-5 in s-space, which the
                 # x1000 test tables amplify; per-level parity with identical inputs is pinned in test_gpu_ops.py
-                assert_close(out["weights_list"][i], g[f"{mode}_w{i}"], REL if i == 0 else 1e-3, f"w{i}")
+                assert_close(out["weights_list"][i], g[f"{mode}_w{i}"], (REL, 1e-4, 1e-3)[i], f"w{i}")  # measured 1.6e-7, 3.2e-5, 2.9e-4
         assert_close(out["rgb"], g[f"{mode}_rgb"], REL, mode + " rgb")
         assert_close(out["accumulation"], g[f"{mode}_acc"], REL, mode + " acc")
         assert_close(out["expected_depth"], g[f"{mode}_exp_depth"], REL, mode + " expected depth")
@@ -271,14 +271,14 @@ def test_full_nerfacto_pipeline_train_and_eval(cuda, golden):
             metrics = model.get_metrics_dict(out, batch)
             losses = model.get_loss_dict(out, batch, metrics)
             assert_close(losses["rgb_loss"], g["loss_rgb"], REL)
-            assert_close(losses["interlevel_loss"], g["loss_interlevel"], 2e-3)  # see test_gpu_engine.py
+            assert_close(losses["interlevel_loss"], g["loss_interlevel"], 1e-3)  # measured 4.8e-4, see test_gpu_engine.py
             assert_close(losses["distortion_loss"], g["loss_distortion"], REL)
             loss = sum(losses.values())
             assert_close(loss, g["loss"], REL)
             named = _named_params(model)
             grads = torch.autograd.grad(loss, list(named.values()))
             for k, gr in zip(named, grads):
-                assert_grad_close(gr, g["g_" + k], "g_" + k, 5e-3, sparse_switching=k.startswith("p") or "table" in k)
+                assert_grad_close(gr, g["g_" + k], "g_" + k, 2.5e-3, sparse_switching=k.startswith("p") or "table" in k)
 
 
 def test_nerfacto_pipeline_staged_levels(cuda, golden):

@@ -39,7 +39,9 @@ def test_pdf_sampler(cuda):
     rb = _bundle()
     coarse = UniformSampler(num_samples=15)(rb)
     weights = torch.ones(10, 15, 1, device="cuda")
-    rs = PDFSampler(15)(rb, coarse, weights, 15)
+    rs = PDFSampler(15)(rb, coarse, weights, 15)  # include_original (default): 16 old + 16 new edges -> 31 samples
+    assert rs.frustums.get_positions().shape[-2] == 31
+    rs = PDFSampler(15, include_original=False)(rb, coarse, weights, 15)
     assert rs.frustums.get_positions().shape[-2] == 15
 
 

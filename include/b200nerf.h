@@ -445,6 +445,35 @@ int b2n_loss_total(const float* terms, int32_t n_terms, const float* extra, floa
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (a memset node when captured) */
 int b2n_zero_async(void* ptr, int64_t bytes, void* stream);
 
+/* ---- the per-ray middle of the nerfacto training step in one launch (SURVEY 8 a21-a24 composed) ---------------------
+ * One warp per ray: density activation (nerfacto_field.py:226-232) + RaySamples.get_weights (cameras/rays.py:129-152),
+ * RGB / accumulation / expected + median depth renderers (model_components/renderers.py:71-119,292-385), the MSE gradient
+ * (models/nerfacto.py:372), the interlevel loss against both proposal levels and the distortion loss
+ * (model_components/losses.py:53-155), then the backward of compositing, get_weights (all three levels) and the density
+ * activation.  Same arithmetic as the separate operators above (bit-identical gradients).
+ * Inputs: sbins/ebins_main [R, S+1] (spacing / euclidean edges), base_out [R*S, base_stride] (column 0 = density
+ * pre-activation), selector [R*S], rgb [R*S,3], gt [R,3]; per proposal level l (arrays of 2 HOST pointers to device
+ * buffers): sbins [R,Sl+1], ebins [R,Sl+1], weights [R,Sl], density [R,Sl].  d_prop_weights2 == NULL: proposals frozen
+ * (no proposal gradients are produced).  gscales: mse 1, interlevel mult/(R*S), distortion mult/R.
+ * Outputs: density, weights [R,S]; rgb_out [R,3]; accumulation, depth_expected, depth_median [R]; d_rgb [R*S,3];
+ * d_weights, d_weights_distortion [R,S]; d_density_pre [R*S]; d_prop_weights2[l], d_prop_density2[l] [R,Sl];
+ * loss_rows4 = {interlevel 0, interlevel 1, distortion, squared rgb error} per ray [R] each. */
+int b2n_nerfacto_ray_tail(int64_t n_rays, int32_t s_main, int32_t s_prop0, int32_t s_prop1, const float* sbins_main,
+                          const float* ebins_main, const float* base_out, int32_t base_stride, const uint8_t* selector,
+                          float avg_init, const float* rgb, const float* gt, int32_t bg_mode, const float* bg_host3,
+                          float mse_gscale, float interlevel_gscale, float distortion_gscale,
+                          const float* const* prop_sbins2, const float* const* prop_ebins2,
+                          const float* const* prop_weights2, const float* const* prop_density2,
+                          float* const* d_prop_weights2, float* const* d_prop_density2, float* density, float* weights,
+                          float* rgb_out, float* accumulation, float* depth_expected, float* depth_median, float* d_rgb,
+                          float* d_weights, float* d_weights_distortion, float* d_density_pre, float* const* loss_rows4,
+                          void* stream);
+/* losses5[0] = rgb_scale * sum(rows4[3]), [1] = interlevel_scale * (sum(rows4[0]) + sum(rows4[1])),
+ * [2] = distortion_scale * sum(rows4[2]), [3] = ((l0 + l1) + l2) + losses5[4] (engine/trainer.py:511); fixed reduction
+ * order (deterministic).  losses5[4] (the camera-optimiser regulariser) is read, not written. */
+int b2n_loss_finalize(const float* const* loss_rows4, int64_t n_rays, float interlevel_scale, float distortion_scale,
+                      float rgb_scale, float* losses5, void* stream);
+
 /* ---- fused proposal density field (fields/density_fields.py:94-117) ---------------------------
  * ray sample -> unit cube -> hash grid (F=2, <= 8 levels) -> MLP in->16->1 (ReLU) -> avg_init * trunc_exp * selector,
  * ONE launch; the network is read from the device pointers in mlp_host (w[0] [16][in], b[0], w[1] [1][16], b[1]).

@@ -20,7 +20,7 @@ LIB = os.path.join(PKG, "libb200nerf.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
 
 SOURCES = ["runtime.cu", "hashgrid.cu", "mlp.cu", "encodings.cu", "sampling.cu", "render.cu", "raygen.cu",
-           "packed.cu", "adam.cu", "fuse.cu", "tc_test.cu", "mlp_tc.cu", "density_fused.cu", "splat.cu", "wide_mlp.cu", "step_glue.cu"]
+           "packed.cu", "adam.cu", "fuse.cu", "tc_test.cu", "mlp_tc.cu", "density_fused.cu", "splat.cu", "wide_mlp.cu", "step_glue.cu", "ray_tail.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v" if os.environ.get("B2N_PTXAS_V") else "-O3"] + os.environ.get("B2N_NVCC_EXTRA", "").split()
 

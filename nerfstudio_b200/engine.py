@@ -58,7 +58,7 @@ class NerfactoStep:
                  lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
                  always_update_proposals: bool = False, mlp_backend: str = "auto",
                  fused_proposals: bool = True, eval_mode: bool = False, camera_lr: float = 1e-3,
-                 camera_lr_schedule: Optional[Callable[[int], float]] = None) -> None:
+                 camera_lr_schedule: Optional[Callable[[int], float]] = None, fused_tail: bool = True) -> None:
         cfg = model.config
         if cfg.implementation != "torch":
             raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
@@ -191,7 +191,10 @@ class NerfactoStep:
         self.acc, self.depth_exp, self.depth_med = torch.zeros(R, **f32), torch.zeros(R, **f32), torch.zeros(R, **f32)
         self.prop_depth = [torch.zeros(R, **f32) for _ in range(2)]  # median depth of the proposal levels (eval outputs)
         self.emb_mean = torch.zeros(1, max(self.n_emb, 1), **f32)    # eval: mean appearance embedding (or zeros)
-        self.rows = [torch.zeros(R, **f32) for _ in range(3)]
+        self.rows = [torch.zeros(R, **f32) for _ in range(4)]  # per-ray loss terms: interlevel 0/1, distortion, rgb
+        # the per-ray middle of the step (weights, renderers, losses, their backward) in one launch (csrc/ray_tail.cu);
+        # False = one operator per launch (the A/B reference of tests/test_gpu_engine.py)
+        self.fused_tail = fused_tail and not eval_mode
         self.losses = torch.zeros(5, **f32)  # rgb, interlevel, distortion, total, camera-optimiser regulariser
         self.jitter_all = torch.zeros(3, R, 1, **f32)  # stratified draws of the three sampling levels, one launch per step
         self.jitter = list(self.jitter_all.unbind(0))
@@ -270,8 +273,9 @@ class NerfactoStep:
         R, S = self.R, self.S[lvl]
         N = R * S
         eb = self.eb[lvl]
-        call("b2n_weights_bwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), ptr(self.d_w[lvl]), R, S,
-             ptr(self.d_dens[lvl]), stream())
+        if not self.fused_tail:  # (the fused tail has already turned d_w[lvl] into d_dens[lvl])
+            call("b2n_weights_bwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), ptr(self.d_w[lvl]), R, S,
+                 ptr(self.d_dens[lvl]), stream())
         if self.fused_props:
             self.density_field_bwd_launch(lvl)
             return
@@ -338,7 +342,9 @@ class NerfactoStep:
         mb, gb = self.base.structs()
         self._mlp_fwd(mb, self.enc[2], self.enc[2].shape[1], N2, self.h[2], self.hid[2], self.base.spec)
         bw = self.h[2].shape[1]
-        call("b2n_density_act_fwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), N2, self.avg, ptr(self.dens[2]), st())
+        tail = self.fused_tail and not ev  # density activation, weights and renderers run inside b2n_nerfacto_ray_tail
+        if not tail:
+            call("b2n_density_act_fwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), N2, self.avg, ptr(self.dens[2]), st())
         call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), st())
         if self.emb is None:
             emb_ptr, emb_mode = NULL, 0
@@ -353,10 +359,11 @@ class NerfactoStep:
         for i, (w, b) in enumerate(zip(self.head_w, self.head_b)):
             gh.dw[i], gh.db[i] = ptr(w.grad).value, ptr(b.grad).value
         self._mlp_fwd(mh, self.hin, self.hin_stride, N2, self.rgb, self.hid_head, self.head_spec)
-        call("b2n_weights_fwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), R, S2, ptr(self.w[2]), st())
         bg_mode, bg_ptr, _keep = F._bg_args(self.bg)
-        call("b2n_composite_fwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2, bg_mode, bg_ptr,
-             1 if ev else 0, ptr(self.rgb_out), ptr(self.acc), ptr(self.depth_exp), ptr(self.depth_med), NULL, st())
+        if not tail:
+            call("b2n_weights_fwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), R, S2, ptr(self.w[2]), st())
+            call("b2n_composite_fwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2, bg_mode, bg_ptr,
+                 1 if ev else 0, ptr(self.rgb_out), ptr(self.acc), ptr(self.depth_exp), ptr(self.depth_med), NULL, st())
         self._fw = (mb, gb, mh, gh, bw, bg_mode, bg_ptr, _keep)
 
     def _body(self, update_props: bool) -> None:
@@ -376,23 +383,21 @@ class NerfactoStep:
         mb, gb, mh, gh, bw, bg_mode, bg_ptr, _keep = self._fw
         N2 = R * S2
         eb2 = self.eb[2]
-        # ---------------- losses (+ their gradients)
-        call("b2n_mse_fwd_bwd", ptr(self.rgb_out), ptr(self.gt), 3 * R, 1.0, ptr(self.losses), ptr(self.d_rgb_out), st())
         il = cfg.interlevel_loss_mult / float(R * S2)
-        for lvl in (0, 1):
-            call("b2n_interlevel_fwd_bwd", ptr(self.sb[2]), ptr(self.w[2]), ptr(self.sb[lvl]), ptr(self.w[lvl]), R, S2,
-                 self.S[lvl], il, ptr(self.rows[lvl]), ptr(self.d_w[lvl]) if update_props else NULL, st())
-            call("b2n_sum_rows", ptr(self.rows[lvl]), R, il, _off(self.losses, 1), st())
         dm = cfg.distortion_loss_mult / float(R)
-        call("b2n_distortion_fwd_bwd", ptr(self.sb[2]), ptr(self.w[2]), R, S2, dm, ptr(self.rows[2]), ptr(self.d_w_dist), st())
-        call("b2n_sum_rows", ptr(self.rows[2]), R, dm, _off(self.losses, 2), st())
-        # ---------------- backward: main field
-        call("b2n_composite_bwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.d_rgb_out), NULL, NULL,
-             R, S2, bg_mode, bg_ptr, ptr(self.d_rgb), ptr(self.d_w[2]), st())
-        call("b2n_add_inplace", ptr(self.d_w[2]), ptr(self.d_w_dist), self.d_w[2].numel(), st())
-        call("b2n_weights_bwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), ptr(self.d_w[2]), R, S2, ptr(self.d_dens[2]), st())
-        call("b2n_density_act_bwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), ptr(self.d_dens[2]), N2, self.avg,
-             ptr(self.d_hpre), 1, st())
+        if self.fused_tail:
+            # ---------------- weights, renderers, losses and their backward down to the density pre-activation: one launch
+            arr = lambda ts: (C.c_void_p * len(ts))(*[ptr(t).value for t in ts])
+            self._tail_keep = (arr(self.sb[:2]), arr(self.eb[:2]), arr(self.w[:2]), arr(self.dens[:2]), arr(self.d_w[:2]),
+                               arr(self.d_dens[:2]), arr(self.rows))
+            a_sb, a_eb, a_w, a_dens, a_dw, a_ddens, a_rows = self._tail_keep
+            call("b2n_nerfacto_ray_tail", R, S2, S0, S1, ptr(self.sb[2]), ptr(eb2), ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8),
+                 self.avg, ptr(self.rgb), ptr(self.gt), bg_mode, bg_ptr, 1.0, il, dm, a_sb, a_eb, a_w, a_dens,
+                 a_dw if update_props else NULL, a_ddens if update_props else NULL, ptr(self.dens[2]), ptr(self.w[2]),
+                 ptr(self.rgb_out), ptr(self.acc), ptr(self.depth_exp), ptr(self.depth_med), ptr(self.d_rgb), ptr(self.d_w[2]),
+                 ptr(self.d_w_dist), ptr(self.d_hpre), a_rows, st())
+        else:
+            self._tail_unfused(update_props, il, dm)
         self._mlp_bwd(mh, gh, self.hin, self.hin_stride, self.rgb, self.hid_head, self.d_rgb, N2, self.d_hin, self.hin_stride,
                       self.head_spec)
         call("b2n_head_input_bwd", ptr(self.d_hin), self.hin_stride, self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre), ptr(self.cams, torch.int64),
@@ -411,7 +416,33 @@ class NerfactoStep:
             cc = self.camopt.config  # regulariser (camera_optimizers.py:155-162): value into losses[4], gradient into the poses
             call("b2n_pose_regularizer", ptr(self.cam_pose), self.cam_pose.shape[0], float(cc.trans_l2_penalty),
                  float(cc.rot_l2_penalty), 1.0, _off(self.losses, 4), ptr(self.cam_pose.grad), st())
-        call("b2n_loss_total", ptr(self.losses), 3, _off(self.losses, 4), _off(self.losses, 3), st())
+        if self.fused_tail:
+            call("b2n_loss_finalize", self._tail_keep[6], R, il, dm, 1.0 / float(3 * R), ptr(self.losses), st())
+        else:
+            call("b2n_loss_total", ptr(self.losses), 3, _off(self.losses, 4), _off(self.losses, 3), st())
+
+    def _tail_unfused(self, update_props: bool, il: float, dm: float) -> None:
+        """The per-ray middle of the step, one operator per launch (what b2n_nerfacto_ray_tail fuses)."""
+        R, S0, S1, S2 = self.R, *self.S
+        st = stream
+        mb, gb, mh, gh, bw, bg_mode, bg_ptr, _keep = self._fw
+        N2 = R * S2
+        eb2 = self.eb[2]
+        # ---------------- losses (+ their gradients)
+        call("b2n_mse_fwd_bwd", ptr(self.rgb_out), ptr(self.gt), 3 * R, 1.0, ptr(self.losses), ptr(self.d_rgb_out), st())
+        for lvl in (0, 1):
+            call("b2n_interlevel_fwd_bwd", ptr(self.sb[2]), ptr(self.w[2]), ptr(self.sb[lvl]), ptr(self.w[lvl]), R, S2,
+                 self.S[lvl], il, ptr(self.rows[lvl]), ptr(self.d_w[lvl]) if update_props else NULL, st())
+            call("b2n_sum_rows", ptr(self.rows[lvl]), R, il, _off(self.losses, 1), st())
+        call("b2n_distortion_fwd_bwd", ptr(self.sb[2]), ptr(self.w[2]), R, S2, dm, ptr(self.rows[2]), ptr(self.d_w_dist), st())
+        call("b2n_sum_rows", ptr(self.rows[2]), R, dm, _off(self.losses, 2), st())
+        # ---------------- backward: main field
+        call("b2n_composite_bwd", ptr(self.rgb), ptr(self.w[2]), ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.d_rgb_out), NULL, NULL,
+             R, S2, bg_mode, bg_ptr, ptr(self.d_rgb), ptr(self.d_w[2]), st())
+        call("b2n_add_inplace", ptr(self.d_w[2]), ptr(self.d_w_dist), self.d_w[2].numel(), st())
+        call("b2n_weights_bwd", ptr(eb2), _off(eb2, 1), S2 + 1, ptr(self.dens[2]), ptr(self.d_w[2]), R, S2, ptr(self.d_dens[2]), st())
+        call("b2n_density_act_bwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), ptr(self.d_dens[2]), N2, self.avg,
+             ptr(self.d_hpre), 1, st())
 
     def _body_props(self, update_props: bool) -> None:
         """backward of the proposal networks (only the interlevel loss reaches them)."""

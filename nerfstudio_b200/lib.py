@@ -122,6 +122,9 @@ _SIGNATURES = {
     "b2n_head_input_bwd": [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _P],
     "b2n_mse_fwd_bwd": [_P, _P, _I64, _F, _P, _P, _P],
     "b2n_sum_rows": [_P, _I64, _F, _P, _P],
+    "b2n_nerfacto_ray_tail": [_I64, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _F, _P, _P, _I32, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P,
+                              _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "b2n_loss_finalize": [_P, _I64, _F, _F, _F, _P, _P],
     "b2n_step_begin": [_P, _I64, _P, _P, _I64, _P, _I64, _P],
     "b2n_add_inplace": [_P, _P, _I64, _P],
     "b2n_loss_total": [_P, _I32, _P, _P, _P],

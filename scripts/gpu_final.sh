@@ -20,5 +20,6 @@ if [ "${FULL_NCU:-1}" = "1" ]; then
       python bench.py --engine eager --steps 2 --warmup 3 --windows 1 --state-step 8 --no-cpu-baseline --no-eval \
       > gpurun_out/${TAG}_bench_under_ncu_full.log 2>&1; echo "ncu full rc=$?"
   ncu -i gpurun_out/${TAG}_full.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_raw.csv 2>/dev/null
+  rm -f gpurun_out/${TAG}_full.ncu-rep   # ~80 MB: gpurun only merges gpurun_out/ back when it is below 64 MiB
 fi
 ls -la gpurun_out | tail -12

@@ -17,11 +17,11 @@ def cuda():
         pytest.skip("no CUDA device")
 
 
-def _mk(g, use_graph, always=True):
+def _mk(g, use_graph, always=True, **kw):
     from nerfstudio_b200.engine import NerfactoStep
 
     model = _pipeline_model(g).train()
-    eng = NerfactoStep(model, n_rays=g["origins"].shape[0], use_graph=use_graph, always_update_proposals=always)
+    eng = NerfactoStep(model, n_rays=g["origins"].shape[0], use_graph=use_graph, always_update_proposals=always, **kw)
     eng.set_batch(g["origins"].cuda(), g["directions"].cuda(), g["train_cams"].cuda(), g["gt"].cuda())
     eng.fixed_jitter = [g["train_rand0"].cuda(), g["train_rand1"].cuda(), g["train_rand2"].cuda()]
     return model, eng
@@ -211,6 +211,32 @@ def test_graph_replay_equals_eager(cuda, golden):
             # a +-lr move of that entry: compare in relative L2, where those isolated entries do not dominate
             rel = float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
             assert rel < 1e-4, (k, rel)
+
+
+def test_fused_ray_tail_equals_operator_chain(cuda, golden):
+    """b2n_nerfacto_ray_tail (weights, renderers, losses and their backward for all three levels in one launch) runs the
+    per-ray bodies of the separate operators: every deterministic product is bit-identical to the 15-launch chain, the
+    loss scalars (different reduction order) agree to 1e-6, the parameter gradients (float atomics downstream) to 1e-5."""
+    g = golden("nerfacto_pipeline")
+    outs = []
+    for fused in (False, True):
+        model, eng = _mk(g, use_graph=False, fused_tail=fused)
+        assert eng.fused_tail == fused
+        eng.optim.lr = 0.0
+        losses = eng.step().clone()
+        torch.cuda.synchronize()
+        outs.append((eng, losses))
+    (a, la), (b, lb) = outs
+    for name in ("rgb_out", "acc", "depth_exp", "depth_med", "d_rgb", "d_hpre", "d_w_dist"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    for lvl in range(3):
+        assert torch.equal(a.w[lvl], b.w[lvl]) and torch.equal(a.dens[lvl], b.dens[lvl]), lvl
+        assert torch.equal(a.d_w[lvl], b.d_w[lvl]), lvl
+        assert torch.equal(a.rows[lvl], b.rows[lvl]), lvl
+    for lvl in range(2):
+        assert torch.equal(a.d_dens[lvl], b.d_dens[lvl]), lvl
+    assert_close(lb, la, 1e-6, "losses")
+    assert_close(b.optim.flat_grad, a.optim.flat_grad, 1e-5, "flat gradient")
 
 
 def test_engine_trains(cuda, golden):

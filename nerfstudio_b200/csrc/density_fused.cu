@@ -206,12 +206,21 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
   float* denc = dyn_smem + SC * CSW;             // [DF_THREADS][DW]
   __shared__ __align__(16) float ws[DF_NET_FLOATS];
   __shared__ float red2[DF_H + 1];
-  stage_net(net, ws);
   const int t = threadIdx.x;
   // `live` (optional): live[0] = number of samples with a non-zero gradient, live[1..] = their indices (compacted by
   // live_compact_kernel, order preserved inside 4096-sample blocks) — the kernel then only visits those
   const int64_t n = live ? (int64_t)live[0] : rg.n_rays * rg.n_samples;
-  const int64_t n_tiles = (n + DF_THREADS * DF_CH - 1) / (DF_THREADS * DF_CH);
+  // Samples per thread and round: DF_CH when there is work for every CTA; with few live samples (the grid was sized on
+  // the host for ALL samples) fewer, so that the live ones spread over as many CTAs as possible — 16 k live samples in
+  // tiles of 1024 would keep 16 of 444 CTAs busy for four latency-bound rounds each.
+  int ch = DF_CH;
+  if (live) {
+    const int64_t per = (n + (int64_t)gridDim.x * DF_THREADS - 1) / ((int64_t)gridDim.x * DF_THREADS);
+    ch = (int)min((int64_t)DF_CH, max((int64_t)1, per));
+  }
+  const int64_t n_tiles = (n + DF_THREADS * ch - 1) / (DF_THREADS * ch);
+  if ((int64_t)blockIdx.x >= n_tiles) return;  // CTA-uniform: nothing to do, nothing to flush
+  stage_net(net, ws);
   // weight-gradient owners (one register accumulator each, kept across all tiles of the CTA):
   //   t in [0, H*IN) owns dW1[j][c], the next H threads own db1[j]; dW2 / db2 are accumulated per thread
   const int oj = t / IN, oc = t - oj * IN;
@@ -226,10 +235,15 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
   float* my_denc = denc + t * DW;
 
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t i0 = (tile * DF_THREADS + t) * DF_CH;
+    const int64_t i0 = (tile * DF_THREADS + t) * ch;
     float xs[DF_CH][3];
 #pragma unroll
     for (int s = 0; s < DF_CH; ++s) {
+      if (s >= ch) {  // CTA-uniform
+#pragma unroll
+        for (int c = 0; c < IN; ++c) my_denc[s * IN + c] = 0.f;
+        continue;
+      }
       const int64_t slot = i0 + s;
       const bool in = slot < n;
       const int64_t i = !in ? 0 : (live ? (int64_t)live[1 + slot] : slot);

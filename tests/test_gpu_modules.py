@@ -576,7 +576,8 @@ def test_fused_density_field_equals_unfused_and_golden(cuda, golden):
         for n_, a, b in zip(names, gf, gu):
             assert_close(a, b, 2e-5, f"{nm} fused-vs-unfused {n_}")
         # sparse gradients (what the interlevel loss produces): live-sample compaction == visiting every sample
-        for frac in (0.0, 0.004, 0.12):
+        # (the kernel picks 1..4 samples per thread and round from the live count: 0.12 -> 1, 0.3 -> 2, 0.6 -> 3, 1.0 -> 4)
+        for frac in (0.0, 0.004, 0.12, 0.3, 0.6, 1.0):
             dy = torch.randn_like(fused) * (torch.rand_like(fused) < frac)
             outs = []
             for compact in (True, False):

@@ -177,7 +177,8 @@ int b2n_positions_fwd(const float* origins, const float* directions, const float
                       const float* aabb_host6, float* x_out, uint8_t* sel_out, void* stream);
 
 /* backward of the ray form: dx [R*S,3] (gradient w.r.t. x_out) -> d_origins [R,3], d_directions [R,3] (overwritten, or
- * added to when accumulate != 0; either may be NULL), through the selector, the normalisation and the L-inf contraction's Jacobian.  Carries the photometric
+ * added to when accumulate != 0 — 2 = with atomics, for callers that run another producer of the same gradients
+ * concurrently; either may be NULL), through the selector, the normalisation and the L-inf contraction's Jacobian.  Carries the photometric
  * gradient to CameraOptimizer's pose corrections (cameras/camera_optimizers.py:148-153). */
 int b2n_positions_bwd(const float* origins, const float* directions, const float* starts, const float* ends,
                       int64_t bin_stride, int64_t n_rays, int32_t n_samples, int32_t contraction,

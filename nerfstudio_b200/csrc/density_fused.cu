@@ -61,6 +61,7 @@ struct RayGeom {
   int64_t bin_stride;
   int64_t n_rays;
   int n_samples;
+  int sm_count;  // SMs of the device (work distribution of the compacted backward)
 };
 
 template <int L>
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
                                                                        const __grid_constant__ RayGeom rg,
                                                                        const float* __restrict__ table,
                                                                        const float* __restrict__ d_density,
-                                                                       const int32_t* __restrict__ live,
+                                                                       const int32_t* __restrict__ live, int live_policy,
                                                                        float* __restrict__ dtable, float* __restrict__ dw1,
                                                                        float* __restrict__ db1, float* __restrict__ dw2,
                                                                        float* __restrict__ db2, float* __restrict__ d_origins,
@@ -214,9 +215,12 @@ __global__ void __launch_bounds__(DF_THREADS, 2) density_fused_bwd_kernel(const 
   // the host for ALL samples) fewer, so that the live ones spread over as many CTAs as possible — 16 k live samples in
   // tiles of 1024 would keep 16 of 444 CTAs busy for four latency-bound rounds each.
   int ch = DF_CH;
-  if (live) {
+  if (live && live_policy == 1) {         // spread as widely as the launched grid allows
     const int64_t per = (n + (int64_t)gridDim.x * DF_THREADS - 1) / ((int64_t)gridDim.x * DF_THREADS);
     ch = (int)min((int64_t)DF_CH, max((int64_t)1, per));
+  } else if (live && live_policy >= 2) {  // the most samples per thread (run-length merged scatter) that still leaves
+    const int64_t ctas = min((int64_t)gridDim.x, (int64_t)(live_policy - 1) * rg.sm_count);  // >= (policy-1) CTAs per SM
+    ch = (int)min((int64_t)DF_CH, max((int64_t)1, n / (ctas * DF_THREADS)));
   }
   const int64_t n_tiles = (n + DF_THREADS * ch - 1) / (DF_THREADS * ch);
   if ((int64_t)blockIdx.x >= n_tiles) return;  // CTA-uniform: nothing to do, nothing to flush
@@ -412,6 +416,17 @@ static int check_shape(const B2nGrid* g, const B2nMlp* m) {
   return 0;
 }
 
+// compacted backward: samples per thread and round from the live count (b2n_tune "df_live_policy"): 0 = always DF_CH,
+// 1 = spread over the whole launched grid, k >= 2 = the largest count that still leaves (k-1) CTAs per SM busy
+static int g_live_policy = 2;
+int b2n_tune_density_fused(const char* key, int value) {
+  if (strcmp(key, "df_live_policy") == 0 && value >= 0 && value <= 4) {
+    g_live_policy = value;
+    return 1;
+  }
+  return 0;
+}
+
 template <int L, int MODE>
 static void launch_fused_bwd(unsigned grid, cudaStream_t st, const GridParams& gp, const PosParams& pp, const DensityNet& net,
                              const RayGeom& rg, const float* table, const float* d_density, const int32_t* live,
@@ -421,12 +436,13 @@ static void launch_fused_bwd(unsigned grid, cudaStream_t st, const GridParams& g
   if (d_origins != nullptr || d_directions != nullptr) {
     auto kernel = density_fused_bwd_kernel<L, MODE, true>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, dtable, dw1, db1, dw2, db2, d_origins,
-                                           d_directions);
+    kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, g_live_policy, dtable, dw1, db1, dw2, db2,
+                                           d_origins, d_directions);
   } else {
     auto kernel = density_fused_bwd_kernel<L, MODE, false>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, dtable, dw1, db1, dw2, db2, nullptr, nullptr);
+    kernel<<<grid, DF_THREADS, smem, st>>>(gp, pp, net, rg, table, d_density, live, g_live_policy, dtable, dw1, db1, dw2, db2, nullptr,
+                                           nullptr);
   }
 }
 
@@ -461,7 +477,7 @@ extern "C" int b2n_density_field_fwd(const B2nGrid* grid_host, const B2nMlp* mlp
   PosParams pp;
   fill_pos_params(pp, contraction, aabb_host6);
   DensityNet net{mlp_host->w[0], mlp_host->b[0], mlp_host->w[1], mlp_host->b[1], avg_init, mlp_host->in_dim};
-  RayGeom rg{origins, directions, starts, ends, bin_stride, n_rays, directions ? n_samples : 1};
+  RayGeom rg{origins, directions, starts, ends, bin_stride, n_rays, directions ? n_samples : 1, b2n_sm_count()};
   const int64_t n = rg.n_rays * rg.n_samples;
   const unsigned grid = (unsigned)div_up(n, DF_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
@@ -486,7 +502,7 @@ extern "C" int b2n_density_field_bwd_rays(const B2nGrid* grid_host, const B2nMlp
   PosParams pp;
   fill_pos_params(pp, contraction, aabb_host6);
   DensityNet net{mlp_host->w[0], mlp_host->b[0], mlp_host->w[1], mlp_host->b[1], avg_init, mlp_host->in_dim};
-  RayGeom rg{origins, directions, starts, ends, bin_stride, n_rays, directions ? n_samples : 1};
+  RayGeom rg{origins, directions, starts, ends, bin_stride, n_rays, directions ? n_samples : 1, b2n_sm_count()};
   const int64_t n = rg.n_rays * rg.n_samples;
   const int64_t tiles = div_up(n, (int64_t)DF_THREADS * DF_CH);
   const unsigned grid = (unsigned)min(tiles, (int64_t)b2n_sm_count() * 3);

@@ -277,8 +277,13 @@ __global__ void __launch_bounds__(128) positions_bwd_kernel(const __grid_constan
   for (int a = 0; a < 3; ++a) {
     go[a] = warp_sum(go[a]), gd[a] = warp_sum(gd[a]);
     if (lane == 0) {  // this warp is the only writer of ray r in this launch
-      if (d_origins) d_origins[3 * r + a] = accumulate ? d_origins[3 * r + a] + go[a] : go[a];
-      if (d_directions) d_directions[3 * r + a] = accumulate ? d_directions[3 * r + a] + gd[a] : gd[a];
+      if (accumulate == 2) {  // ... but another kernel may be adding to the same rays concurrently (forked streams)
+        if (d_origins) atomicAdd(d_origins + 3 * r + a, go[a]);
+        if (d_directions) atomicAdd(d_directions + 3 * r + a, gd[a]);
+      } else {
+        if (d_origins) d_origins[3 * r + a] = accumulate ? d_origins[3 * r + a] + go[a] : go[a];
+        if (d_directions) d_directions[3 * r + a] = accumulate ? d_directions[3 * r + a] + gd[a] : gd[a];
+      }
     }
   }
 }

@@ -47,10 +47,11 @@ extern "C" int b2n_device_info(int32_t* out4_host) {
 
 int b2n_tune_hashgrid(const char* key, int value);
 int b2n_tune_mlp_tc(const char* key, int value);
+int b2n_tune_density_fused(const char* key, int value);
 int b2n_tune_packed(const char* key, int value);
 
 // runtime tuning knobs (kernel launch geometry); returns 1 if the key was recognised
 extern "C" int b2n_tune(const char* key, int value) {
   if (!key) return 0;
-  return b2n_tune_hashgrid(key, value) || b2n_tune_mlp_tc(key, value) || b2n_tune_packed(key, value);
+  return b2n_tune_hashgrid(key, value) || b2n_tune_mlp_tc(key, value) || b2n_tune_packed(key, value) || b2n_tune_density_fused(key, value);
 }

@@ -58,7 +58,8 @@ class NerfactoStep:
                  lr_schedule: Optional[Callable[[int], float]] = None, allreduce=None, use_graph: bool = True,
                  always_update_proposals: bool = False, mlp_backend: str = "auto",
                  fused_proposals: bool = True, eval_mode: bool = False, camera_lr: float = 1e-3,
-                 camera_lr_schedule: Optional[Callable[[int], float]] = None, fused_tail: bool = True) -> None:
+                 camera_lr_schedule: Optional[Callable[[int], float]] = None, fused_tail: bool = True,
+                 concurrent_backward: bool = True) -> None:
         cfg = model.config
         if cfg.implementation != "torch":
             raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
@@ -195,6 +196,16 @@ class NerfactoStep:
         # the per-ray middle of the step (weights, renderers, losses, their backward) in one launch (csrc/ray_tail.cu);
         # False = one operator per launch (the A/B reference of tests/test_gpu_engine.py)
         self.fused_tail = fused_tail and not eval_mode
+        # Independent pieces of the backward on forked streams (joined before the pose backward / Adam; inside the captured
+        # graph they become parallel branches): the proposal fields' backward only needs the ray tail's d_density, and the
+        # main grid's position gradient (gather) is independent of its table scatter (atomics).  In the sparse-gradient
+        # regime the proposal backward is a few latency-bound rounds on a fraction of the SMs — it hides completely.
+        # Not used when collectives run between the pieces of the step (the field all-reduce overlaps the proposal backward).
+        self.concurrent = concurrent_backward and not eval_mode
+        self._side = [torch.cuda.Stream(), torch.cuda.Stream()] if self.concurrent else []
+        self._fork = False
+        self._joins = []
+        self._prologue_join = None
         self.losses = torch.zeros(5, **f32)  # rgb, interlevel, distortion, total, camera-optimiser regulariser
         self.jitter_all = torch.zeros(3, R, 1, **f32)  # stratified draws of the three sampling levels, one launch per step
         self.jitter = list(self.jitter_all.unbind(0))
@@ -310,8 +321,13 @@ class NerfactoStep:
         R, S0, S1, S2 = self.R, *self.S
         st = stream
         ev = self.eval_mode
-        if self.tma_weights:
+        prologue = self._prologue_join  # training step with forked streams: packing (and grad zeroing) already in flight
+        self._prologue_join = None
+        if self.tma_weights and prologue is None:
             self._pack_weights()
+        if prologue is not None and not self.fused_props:  # unfused proposal networks read their packed images right away
+            torch.cuda.current_stream().wait_event(prologue)
+            prologue = None
         if self.camopt is not None:  # CameraOptimizer.apply_to_raybundle (camera_optimizers.py:148-153)
             call("b2n_pose_apply_fwd", ptr(self.cam_pose), ptr(self.cams, torch.int64), ptr(self.cam_frozen, torch.uint8),
                  ptr(self.origins_in), ptr(self.directions_in), R, ptr(self.origins), ptr(self.directions), st())
@@ -333,6 +349,8 @@ class NerfactoStep:
                 call("b2n_composite_fwd", NULL, ptr(self.w[lvl]), ptr(eb), _off(eb, 1), self.S[lvl] + 1, R, self.S[lvl],
                      lib.BG_NONE, NULL, 0, NULL, NULL, NULL, ptr(self.prop_depth[lvl]), NULL, st())
         # ---------------- forward: main field
+        if prologue is not None:
+            torch.cuda.current_stream().wait_event(prologue)
         N2 = R * S2
         eb2 = self.eb[2]
         box = lib.host_floats(self.aabb)
@@ -371,7 +389,16 @@ class NerfactoStep:
         cfg = self.cfg
         st = stream
         g = self.optim.flat_grad
-        call("b2n_zero_async", ptr(g), g.numel() * g.element_size(), st())
+
+        def prologue() -> None:  # nothing before the main-field forward needs the packed MLP weights or the gradient buffer
+            call("b2n_zero_async", ptr(g), g.numel() * g.element_size(), stream())
+            if self.tma_weights:
+                self._pack_weights()
+
+        if self._fork:
+            self._prologue_join = self._forked(1, prologue)
+        else:
+            call("b2n_zero_async", ptr(g), g.numel() * g.element_size(), st())
         draw = self.fixed_jitter is None
         call("b2n_step_begin", ptr(self.jitter_all) if draw else NULL, 3 * R if draw else 0, ptr(self.rng_state, torch.int64),
              ptr(self.losses), self.losses.numel(), ptr(self.d_rays) if self.camopt is not None else NULL,
@@ -398,21 +425,32 @@ class NerfactoStep:
                  ptr(self.d_w_dist), ptr(self.d_hpre), a_rows, st())
         else:
             self._tail_unfused(update_props, il, dm)
+        self._joins = []
+        if self._fork and update_props and self.fused_tail:
+            # proposal backward: its inputs (d_density of both levels) are complete -> parallel branch
+            self._joins.append(self._forked(0, lambda: [self._density_net_bwd(lvl, self.props[lvl], None) for lvl in (0, 1)]))
         self._mlp_bwd(mh, gh, self.hin, self.hin_stride, self.rgb, self.hid_head, self.d_rgb, N2, self.d_hin, self.hin_stride,
                       self.head_spec)
         call("b2n_head_input_bwd", ptr(self.d_hin), self.hin_stride, self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre), ptr(self.cams, torch.int64),
              R, S2, ptr(self.d_h[2]), bw, ptr(self.emb.grad) if self.emb is not None else NULL, st())
         self._mlp_bwd(mb, gb, self.enc[2], self.enc[2].shape[1], self.h[2], self.hid[2], self.d_h[2], N2, self.d_enc[2],
                       self.d_enc[2].shape[1], self.base.spec)
-        call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
-             ptr(self.base.table.grad), NULL, st())
-        if self.camopt is not None:
+        def main_dx() -> None:
             # main level: d enc -> d x (gather-only kernel) -> contraction Jacobian -> the ray's d origin / d direction
             box = lib.host_floats(self.aabb)
             call("b2n_hashgrid_dx", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
-                 ptr(self.d_x2), st())
+                 ptr(self.d_x2), stream())
             call("b2n_positions_bwd", ptr(self.origins), ptr(self.directions), ptr(eb2), _off(eb2, 1), S2 + 1, R, S2,
-                 int(self.contraction), C.cast(box, C.c_void_p), ptr(self.d_x2), 1, ptr(self.d_rays[0]), ptr(self.d_rays[1]), st())
+                 int(self.contraction), C.cast(box, C.c_void_p), ptr(self.d_x2), 2 if self._fork else 1, ptr(self.d_rays[0]),
+                 ptr(self.d_rays[1]), stream())
+
+        if self.camopt is not None and self._fork:
+            self._joins.append(self._forked(1, main_dx))  # gather-bound, next to the atomics-bound scatter below
+        call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
+             ptr(self.base.table.grad), NULL, st())
+        if self.camopt is not None:
+            if not self._fork:
+                main_dx()
             cc = self.camopt.config  # regulariser (camera_optimizers.py:155-162): value into losses[4], gradient into the poses
             call("b2n_pose_regularizer", ptr(self.cam_pose), self.cam_pose.shape[0], float(cc.trans_l2_penalty),
                  float(cc.rot_l2_penalty), 1.0, _off(self.losses, 4), ptr(self.cam_pose.grad), st())
@@ -444,9 +482,25 @@ class NerfactoStep:
         call("b2n_density_act_bwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), ptr(self.d_dens[2]), N2, self.avg,
              ptr(self.d_hpre), 1, st())
 
+    def _forked(self, k: int, fn) -> torch.cuda.Event:
+        """Run fn() on side stream k after everything issued so far on the current stream; returns the event to join on."""
+        cur, side = torch.cuda.current_stream(), self._side[k]
+        start = torch.cuda.Event()
+        start.record(cur)
+        side.wait_event(start)
+        with torch.cuda.stream(side):
+            fn()
+            done = torch.cuda.Event()
+            done.record(side)
+        return done
+
     def _body_props(self, update_props: bool) -> None:
         """backward of the proposal networks (only the interlevel loss reaches them)."""
-        if update_props:
+        forked_props = self._fork and update_props and self.fused_tail
+        for ev in self._joins:  # branches forked in _body
+            torch.cuda.current_stream().wait_event(ev)
+        self._joins = []
+        if update_props and not forked_props:
             for lvl in (0, 1):
                 self._density_net_bwd(lvl, self.props[lvl], None)
         if self.camopt is not None:  # all three levels have added their d origin / d direction: on to the poses
@@ -530,6 +584,7 @@ class NerfactoStep:
         self._hyper_events[slot] = ev
         update = self._update_due(t)
         overlap = self.allreduce is not None and world > 1
+        self._fork = self.concurrent and not overlap
         if self.use_graph and update not in self._graphs:
             self._capture(update, split=overlap)
         if self.use_graph and not overlap:
@@ -578,6 +633,7 @@ class NerfactoStep:
     def _capture(self, update: bool, split: bool) -> None:
         """Warm the kernels up on a side stream (loads modules, sizes smem attributes), then capture: three graphs
         (forward + main backward | proposal backward | Adam) when collectives run between them, else one."""
+        self._fork = self.concurrent and not split
         saved = [t.clone() for t in (self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq)]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

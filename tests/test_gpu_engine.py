@@ -92,8 +92,10 @@ def test_engine_camera_optimizer_pose_gradients(cuda, golden):
     model = _pipeline_model(g, camera_optimizer="SO3xR3").train()
     with torch.no_grad():
         model.camera_optimizer.pose_adjustment.copy_(g["pose"].cuda())
-    for use_graph in (False, True):
-        eng = NerfactoStep(model, n_rays=g["origins"].shape[0], use_graph=use_graph, always_update_proposals=True)
+    # (the proposal backward and the main grid's position gradient run as forked branches; also checked serialised)
+    for use_graph, concurrent in ((False, True), (True, True), (True, False)):
+        eng = NerfactoStep(model, n_rays=g["origins"].shape[0], use_graph=use_graph, always_update_proposals=True,
+                           concurrent_backward=concurrent)
         assert eng.camopt is not None and eng.optim.segment_of("camera_opt") is not None
         assert eng.grad_split == eng.optim.segment_of("camera_opt")[0]  # [field | camera_opt | proposals]
         eng.set_batch(g["origins"].cuda(), g["directions"].cuda(), g["cams"].cuda(), g["gt"].cuda())

@@ -334,7 +334,7 @@ def run_b200(args) -> None:
 
         fused = FusedTrainStep(model, None, RAYS_PER_GPU, allreduce=allreduce, use_graph=(args.engine == "graph"),
                                always_update_proposals=args.force_proposal_update, mlp_backend=args.mlp,
-                               fused_proposals=not args.unfused_proposals)
+                               fused_proposals=not args.unfused_proposals, sharded_update=not args.no_sharded_update)
         engine = trainer = fused.engine
         fused.datamanager = HostRayQueue(engine, host)
     D.broadcast_parameters(trainer.optim.flat)
@@ -553,7 +553,10 @@ def run_b200(args) -> None:
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch_rays": world * RAYS_PER_GPU,
-                   "parallelism": f"ray-batch data parallel x{world}, one flat-gradient allreduce/step" if world > 1 else "single GPU",
+                   "parallelism": (f"ray-batch data parallel x{world}: " + ("field gradients reduce-scattered, Adam on 1/N of the table, "
+                                   "parameters all-gathered under the next step's proposal sampling; camera + proposal "
+                                   "gradients all-reduced" if not args.no_sharded_update and args.engine != "autograd" else
+                                   "flat-gradient all-reduce in two overlapped segments")) if world > 1 else "single GPU",
                    "precision": ("fp32 tables; MLPs on tcgen05 tensor cores, 3xTF32 split, fp32 accumulate in TMEM (1e-4 parity mode)"
                                  if (engine is not None and engine.tc) else "fp32 tables, fp32 SIMT MLPs (1e-4 parity mode)"), "optimizer": "fused Adam over one flat buffer", "engine": args.engine,
                    "proposal_update": "every step" if args.force_proposal_update else "reference schedule",
@@ -818,6 +821,9 @@ def main() -> None:
     ap.add_argument("--state-step", type=int, default=STATE_STEP,
                     help="optimisation step at which the timed windows start (profiling runs under ncu use a small value)")
     ap.add_argument("--no-eval", action="store_true", help="skip the full-image eval-render measurement")
+    ap.add_argument("--no-sharded-update", action="store_true",
+                    help="N > 1: all-reduce the whole gradient buffer and run Adam replicated (instead of reduce-scatter -> "
+                         "Adam on 1/N of the hash table -> all-gather overlapped with the next step's proposal sampling)")
     ap.add_argument("--mlp", default="auto", choices=["auto", "tc", "simt"],
                     help="tiny-MLP kernels of the graph/eager engine: tcgen05 3xTF32 (tc) or fp32 SIMT")
     ap.add_argument("--unfused-proposals", action="store_true", help="proposal networks as separate grid/MLP launches")

@@ -45,6 +45,44 @@ class FlatGradAllReduce:
             return None
         return dist.all_reduce(segment, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
+    # ---- sharded update of a large segment (the 67 MB hash table): reduce-scatter -> every rank runs Adam on its 1/W slice
+    # -> all-gather of the updated parameters.  Same bytes on the wire as the all-reduce it replaces, but the second half
+    # moves AFTER the optimiser and overlaps the next step's proposal sampling, and Adam touches 1/W of the segment.
+    def shard_chunk(self, n: int) -> int:
+        """Elements per rank (multiple of 4: 16-byte aligned slices) for a segment of n elements; the tail
+        n - world * chunk (< 4 * world elements) is left to the caller's all-reduce."""
+        return (n // self.world) // 4 * 4
+
+    def start_reduce_scatter(self, segment: torch.Tensor):
+        """Sum `segment` (numel = world * chunk) over ranks; afterwards rank r's slice [r*chunk, (r+1)*chunk) holds the
+        sums (the other slices are unspecified).  In place, asynchronous."""
+        if self.world <= 1:
+            return None
+        chunk = segment.numel() // self.world
+        assert chunk * self.world == segment.numel()
+        rank = dist.get_rank(self.group)
+        mine = segment[rank * chunk: (rank + 1) * chunk]
+        if dist.get_backend(self.group) == "gloo":  # CPU tests: gloo has no reduce-scatter
+            return dist.all_reduce(segment, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return dist.reduce_scatter_tensor(mine, segment, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def start_all_gather(self, segment: torch.Tensor):
+        """Every rank contributes its slice [r*chunk, (r+1)*chunk) of `segment`; afterwards all of `segment` is identical
+        on every rank.  In place, asynchronous."""
+        if self.world <= 1:
+            return None
+        chunk = segment.numel() // self.world
+        assert chunk * self.world == segment.numel()
+        rank = dist.get_rank(self.group)
+        mine = segment[rank * chunk: (rank + 1) * chunk]
+        if dist.get_backend(self.group) == "gloo":  # in-place all_gather_into_tensor is NCCL-only
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine.clone(), group=self.group)
+            for r, p_ in enumerate(parts):
+                segment[r * chunk: (r + 1) * chunk].copy_(p_)
+            return None
+        return dist.all_gather_into_tensor(segment, mine, group=self.group, async_op=True)
+
     @staticmethod
     def finish(*handles) -> None:
         """Make the current stream wait for the collectives started with `start`."""

@@ -59,7 +59,7 @@ class NerfactoStep:
                  always_update_proposals: bool = False, mlp_backend: str = "auto",
                  fused_proposals: bool = True, eval_mode: bool = False, camera_lr: float = 1e-3,
                  camera_lr_schedule: Optional[Callable[[int], float]] = None, fused_tail: bool = True,
-                 concurrent_backward: bool = True) -> None:
+                 concurrent_backward: bool = True, sharded_update: bool = True) -> None:
         cfg = model.config
         if cfg.implementation != "torch":
             raise NotImplementedError("the captured step is built on the torch-mode (parity) networks")
@@ -200,12 +200,18 @@ class NerfactoStep:
         # graph they become parallel branches): the proposal fields' backward only needs the ray tail's d_density, and the
         # main grid's position gradient (gather) is independent of its table scatter (atomics).  In the sparse-gradient
         # regime the proposal backward is a few latency-bound rounds on a fraction of the SMs — it hides completely.
-        # Not used when collectives run between the pieces of the step (the field all-reduce overlaps the proposal backward).
+        # (i) is not used when collectives run between the pieces of the step (the field all-reduce overlaps the proposal
+        # backward there); the other branches are joined inside the first piece.
         self.concurrent = concurrent_backward and not eval_mode
         self._side = [torch.cuda.Stream(), torch.cuda.Stream()] if self.concurrent else []
-        self._fork = False
+        self._fork = False        # grad zeroing / weight packing / position-gradient branches (joined inside _body)
+        self._fork_props = False  # proposal backward as a branch (joined in _body_props; single-process step only)
         self._joins = []
         self._prologue_join = None
+        self._pack_late = False   # sharded update: the weight images are packed after the parameter all-gather has landed
+        self._h_ag = None         # pending all-gather of the field parameters (sharded update)
+        self.sharded_update = sharded_update
+        self._shard = None        # (chunk, my_begin, my_end, tail_begin) of the field segment while the sharded path is active
         self.losses = torch.zeros(5, **f32)  # rgb, interlevel, distortion, total, camera-optimiser regulariser
         self.jitter_all = torch.zeros(3, R, 1, **f32)  # stratified draws of the three sampling levels, one launch per step
         self.jitter = list(self.jitter_all.unbind(0))
@@ -318,16 +324,20 @@ class NerfactoStep:
         Training: stratified samplers, per-camera appearance embedding.  Eval: deterministic samplers
         (ray_samplers.py:326-330), the mean embedding (or zeros), eval-mode compositing (renderers.py:225-231) and the
         proposal levels' median depths (models/nerfacto.py:346-347)."""
+        self._forward_props()
+        self._forward_main()
+
+    def _forward_props(self) -> None:
+        """Pose correction and the proposal sampling of both levels (reads only the proposal networks and the poses)."""
         R, S0, S1, S2 = self.R, *self.S
         st = stream
         ev = self.eval_mode
         prologue = self._prologue_join  # training step with forked streams: packing (and grad zeroing) already in flight
-        self._prologue_join = None
-        if self.tma_weights and prologue is None:
+        if self.tma_weights and prologue is None and not self._pack_late:
             self._pack_weights()
         if prologue is not None and not self.fused_props:  # unfused proposal networks read their packed images right away
             torch.cuda.current_stream().wait_event(prologue)
-            prologue = None
+            self._prologue_join = None
         if self.camopt is not None:  # CameraOptimizer.apply_to_raybundle (camera_optimizers.py:148-153)
             call("b2n_pose_apply_fwd", ptr(self.cam_pose), ptr(self.cams, torch.int64), ptr(self.cam_frozen, torch.uint8),
                  ptr(self.origins_in), ptr(self.directions_in), R, ptr(self.origins), ptr(self.directions), st())
@@ -348,9 +358,18 @@ class NerfactoStep:
                 eb = self.eb[lvl]
                 call("b2n_composite_fwd", NULL, ptr(self.w[lvl]), ptr(eb), _off(eb, 1), self.S[lvl] + 1, R, self.S[lvl],
                      lib.BG_NONE, NULL, 0, NULL, NULL, NULL, ptr(self.prop_depth[lvl]), NULL, st())
-        # ---------------- forward: main field
-        if prologue is not None:
-            torch.cuda.current_stream().wait_event(prologue)
+
+    def _forward_main(self) -> None:
+        """Main field on the final samples: positions, hash grid, base MLP, colour head (+ weights and renderers unless the
+        fused ray tail does them)."""
+        R, S0, S1, S2 = self.R, *self.S
+        st = stream
+        ev = self.eval_mode
+        if self._prologue_join is not None:
+            torch.cuda.current_stream().wait_event(self._prologue_join)
+            self._prologue_join = None
+        if self.tma_weights and self._pack_late:
+            self._pack_weights()
         N2 = R * S2
         eb2 = self.eb[2]
         box = lib.host_floats(self.aabb)
@@ -385,14 +404,19 @@ class NerfactoStep:
         self._fw = (mb, gb, mh, gh, bw, bg_mode, bg_ptr, _keep)
 
     def _body(self, update_props: bool) -> None:
-        R, S0, S1, S2 = self.R, *self.S
-        cfg = self.cfg
+        self._body_a(update_props)
+        self._body_b(update_props)
+
+    def _body_a(self, update_props: bool) -> None:
+        """Step prologue (draws, zeroing) and the proposal sampling: touches no field parameter."""
+        R = self.R
         st = stream
         g = self.optim.flat_grad
+        late = self._pack_late
 
         def prologue() -> None:  # nothing before the main-field forward needs the packed MLP weights or the gradient buffer
             call("b2n_zero_async", ptr(g), g.numel() * g.element_size(), stream())
-            if self.tma_weights:
+            if self.tma_weights and not late:
                 self._pack_weights()
 
         if self._fork:
@@ -406,7 +430,17 @@ class NerfactoStep:
         if not draw:  # tests: replay recorded stratified draws
             for j, src in zip(self.jitter, self.fixed_jitter):
                 j.copy_(src)
-        self._forward()
+        self._forward_props()
+        if late and self._prologue_join is not None:  # this piece is captured on its own: join its branch here
+            torch.cuda.current_stream().wait_event(self._prologue_join)
+            self._prologue_join = None
+
+    def _body_b(self, update_props: bool) -> None:
+        """Main-field forward, the per-ray middle, the main backward."""
+        R, S0, S1, S2 = self.R, *self.S
+        cfg = self.cfg
+        st = stream
+        self._forward_main()
         mb, gb, mh, gh, bw, bg_mode, bg_ptr, _keep = self._fw
         N2 = R * S2
         eb2 = self.eb[2]
@@ -426,7 +460,7 @@ class NerfactoStep:
         else:
             self._tail_unfused(update_props, il, dm)
         self._joins = []
-        if self._fork and update_props and self.fused_tail:
+        if self._fork_props and update_props and self.fused_tail:
             # proposal backward: its inputs (d_density of both levels) are complete -> parallel branch
             self._joins.append(self._forked(0, lambda: [self._density_net_bwd(lvl, self.props[lvl], None) for lvl in (0, 1)]))
         self._mlp_bwd(mh, gh, self.hin, self.hin_stride, self.rgb, self.hid_head, self.d_rgb, N2, self.d_hin, self.hin_stride,
@@ -444,8 +478,9 @@ class NerfactoStep:
                  int(self.contraction), C.cast(box, C.c_void_p), ptr(self.d_x2), 2 if self._fork else 1, ptr(self.d_rays[0]),
                  ptr(self.d_rays[1]), stream())
 
+        dx_join = None
         if self.camopt is not None and self._fork:
-            self._joins.append(self._forked(1, main_dx))  # gather-bound, next to the atomics-bound scatter below
+            dx_join = self._forked(1, main_dx)  # gather-bound, next to the atomics-bound scatter below
         call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
              ptr(self.base.table.grad), NULL, st())
         if self.camopt is not None:
@@ -458,6 +493,8 @@ class NerfactoStep:
             call("b2n_loss_finalize", self._tail_keep[6], R, il, dm, 1.0 / float(3 * R), ptr(self.losses), st())
         else:
             call("b2n_loss_total", ptr(self.losses), 3, _off(self.losses, 4), _off(self.losses, 3), st())
+        if dx_join is not None:
+            torch.cuda.current_stream().wait_event(dx_join)
 
     def _tail_unfused(self, update_props: bool, il: float, dm: float) -> None:
         """The per-ray middle of the step, one operator per launch (what b2n_nerfacto_ray_tail fuses)."""
@@ -496,7 +533,7 @@ class NerfactoStep:
 
     def _body_props(self, update_props: bool) -> None:
         """backward of the proposal networks (only the interlevel loss reaches them)."""
-        forked_props = self._fork and update_props and self.fused_tail
+        forked_props = self._fork_props and update_props and self.fused_tail
         for ev in self._joins:  # branches forked in _body
             torch.cuda.current_stream().wait_event(ev)
         self._joins = []
@@ -521,6 +558,21 @@ class NerfactoStep:
                 runs[-1][1] = b
             else:
                 runs.append([a, b, slot])
+        if self._shard is not None:
+            # sharded update: of the field segment [0, grad_split) this rank steps its own slice (whose gradient sums the
+            # reduce-scatter left here) and the short tail that went through the all-reduce; the all-gather that follows
+            # brings the other ranks' slices of the updated parameters
+            chunk, m0, m1, tail = self._shard
+            split_runs = []
+            for a, b, slot in runs:
+                if b <= self.grad_split:
+                    for lo, hi in ((max(a, m0), min(b, m1)), (max(a, tail), b)):
+                        if hi > lo:
+                            split_runs.append([lo, hi, slot])
+                else:
+                    assert a >= self.grad_split
+                    split_runs.append([a, b, slot])
+            runs = split_runs
         for a, b, slot in runs:
             call("b2n_adam_step_dev", _off(o.flat, a), _off(o.flat_grad, a), _off(o.exp_avg, a), _off(o.exp_avg_sq, a),
                  b - a, _off(self.hyper, slot), float(o.betas[0]), float(o.betas[1]), float(o.eps), stream())
@@ -584,7 +636,12 @@ class NerfactoStep:
         self._hyper_events[slot] = ev
         update = self._update_due(t)
         overlap = self.allreduce is not None and world > 1
-        self._fork = self.concurrent and not overlap
+        self._fork, self._fork_props = self.concurrent, self.concurrent and not overlap
+        shard = (overlap and self.sharded_update and self.grad_split is not None and self.fused_tail
+                 and hasattr(self.allreduce, "start_reduce_scatter") and self.allreduce.shard_chunk(self.grad_split) > 0)
+        if shard:
+            return self._step_sharded(update, world)
+        self.flush()
         if self.use_graph and update not in self._graphs:
             self._capture(update, split=overlap)
         if self.use_graph and not overlap:
@@ -618,6 +675,81 @@ class NerfactoStep:
         run(2)
         return self._finish_step(update)
 
+    def flush(self) -> None:
+        """Make the current stream wait for a pending parameter all-gather (sharded update): call before anything other
+        than step() reads the field parameters (evaluation, checkpoints)."""
+        if self._h_ag is not None:
+            self._h_ag.wait()
+            self._h_ag = None
+
+    def _step_sharded(self, update: bool, world: int) -> Tensor:
+        """One process per GPU, the field segment (the 67 MB hash table) updated in shards:
+            [draws + proposal sampling]            | all-gather of the field parameters of the PREVIOUS step still landing
+            wait all-gather -> [main forward + ray tail + main backward]
+            reduce-scatter(field gradients)        | [proposal + pose backward]
+            all-reduce(field tail + camera + proposal gradients)
+            [Adam: own field slice, field tail, camera, proposals] -> all-gather(field parameters), asynchronous.
+        Same wire bytes as one all-reduce of the buffer, but only the reduce-scatter half sits between backward and Adam,
+        the other half overlaps the next step's proposal sampling, and Adam touches 1/world of the table."""
+        o, ar = self.optim, self.allreduce
+        rank = torch.distributed.get_rank(ar.group)
+        chunk = ar.shard_chunk(self.grad_split)
+        self._shard = (chunk, rank * chunk, (rank + 1) * chunk, world * chunk)
+        key = ("shard", update)
+        if self.use_graph and key not in self._graphs:
+            self._capture_sharded(update)
+
+        def run(i: int) -> None:
+            if self.use_graph:
+                g = self._graphs[key][i]
+                if g is not None:
+                    g.replay()
+            else:
+                self._pack_late = True
+                (self._body_a, self._body_b, self._body_props, self._adam)[i](update)
+                self._pack_late = False
+
+        run(0)
+        self.flush()  # the field parameters of the previous step are complete before the main forward reads them
+        run(1)
+        h_rs = ar.start_reduce_scatter(o.flat_grad[: world * chunk])
+        run(2)
+        end = o.flat_grad.numel() if update else (self._cam_seg[1] if self._cam_seg is not None and
+                                                   self._cam_seg[0] == self.grad_split else self.grad_split)
+        h_rest = ar.start(o.flat_grad[world * chunk: end]) if end > world * chunk else None
+        ar.finish(h_rs, h_rest)
+        run(3)
+        self._h_ag = ar.start_all_gather(o.flat[: world * chunk])
+        self._shard = None
+        return self._finish_step(update)
+
+    def _capture_sharded(self, update: bool) -> None:
+        """Four graphs: [prologue + proposal sampling] [main forward .. main backward] [proposal + pose backward] [Adam]."""
+        self._fork, self._fork_props, self._pack_late = self.concurrent, False, True
+        saved = [t.clone() for t in (self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq)]
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._body_a(update), self._body_b(update), self._body_props(update), self._adam(update)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for dst, src in zip((self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq), saved):
+            dst.copy_(src)  # the warm-up pass must not count as an optimisation step
+        g_a, g_b, g_props, g_adam = (torch.cuda.CUDAGraph() for _ in range(4))
+        with torch.cuda.graph(g_a):
+            self._body_a(update)
+        with torch.cuda.graph(g_b, pool=g_a.pool()):
+            self._body_b(update)
+        if update or self.camopt is not None:
+            with torch.cuda.graph(g_props, pool=g_a.pool()):
+                self._body_props(update)
+        else:
+            g_props = None
+        with torch.cuda.graph(g_adam, pool=g_a.pool()):
+            self._adam(update)
+        self._pack_late = False
+        self._graphs[("shard", update)] = (g_a, g_b, g_props, g_adam)
+
     def _finish_step(self, update: bool) -> Tensor:
         if update:
             self._steps_since_update = 0
@@ -633,7 +765,7 @@ class NerfactoStep:
     def _capture(self, update: bool, split: bool) -> None:
         """Warm the kernels up on a side stream (loads modules, sizes smem attributes), then capture: three graphs
         (forward + main backward | proposal backward | Adam) when collectives run between them, else one."""
-        self._fork = self.concurrent and not split
+        self._fork, self._fork_props = self.concurrent, self.concurrent and not split
         saved = [t.clone() for t in (self.optim.flat, self.optim.exp_avg, self.optim.exp_avg_sq)]
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

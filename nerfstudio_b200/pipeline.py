@@ -88,6 +88,11 @@ class FusedTrainStep:
         metrics_dict = {"distortion": losses[2] / c.distortion_loss_mult if c.distortion_loss_mult else losses[2]}
         return model_outputs, loss_dict, metrics_dict
 
+    def flush(self) -> None:
+        """Multi-GPU sharded update: wait for the in-flight parameter all-gather before anything but the next training
+        step reads the model (evaluation, checkpoints)."""
+        self.engine.flush()
+
     # ---- engine/trainer.py:486-530 ----
     def train_iteration(self, step: int):
         _, loss_dict, metrics_dict = self.get_train_loss_dict(step)

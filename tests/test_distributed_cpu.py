@@ -75,6 +75,45 @@ def test_segmented_async_allreduce_world2():
     assert out[0] == expect and out[1] == expect
 
 
+def _worker_sharded(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from nerfstudio_b200 import distributed as D
+
+    D.init_from_env("gloo")
+    ar = D.FlatGradAllReduce()
+    n_field, n_all = 21, 30                  # field segment [0, 21), late segments [21, 30) as engine.grad_split = 21
+    chunk = ar.shard_chunk(n_field)          # (21 // 2) // 4 * 4 = 8 -> slices [0,8) [8,16), tail [16, 21)
+    params = torch.zeros(n_all)
+    grad = torch.arange(float(n_all)) * (rank + 1)
+    h_rs = ar.start_reduce_scatter(grad[: world * chunk])
+    h_rest = ar.start(grad[world * chunk:])  # field tail + camera + proposal gradients
+    ar.finish(h_rs, h_rest)
+    # "Adam" (p -= g) on what this rank owns: its slice, the field tail, the late segments
+    lo, hi = rank * chunk, (rank + 1) * chunk
+    params[lo:hi] -= grad[lo:hi]
+    params[world * chunk:] -= grad[world * chunk:]
+    h_ag = ar.start_all_gather(params[: world * chunk])
+    ar.finish(h_ag)
+    out[rank] = (chunk, params.tolist())
+    dist.destroy_process_group()
+
+
+def test_sharded_update_world2():
+    """engine.NerfactoStep._step_sharded's exchange: reduce-scatter of the field gradients, all-reduce of the rest, every
+    rank updates its slice, all-gather of the parameters — replicas end up with the all-reduce result."""
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_sharded, args=(2, port, out), nprocs=2, join=True)
+    expect = [-3.0 * i for i in range(30)]
+    for rank in (0, 1):
+        chunk, params = out[rank]
+        assert chunk == 8
+        assert params == expect, (rank, params)
+
+
 def test_single_process_allreduce_is_identity():
     sys.path.insert(0, ROOT)
     from nerfstudio_b200.distributed import FlatGradAllReduce

@@ -209,6 +209,15 @@ int b2n_pdf_sample(const float* bins, const float* weights, const float* u_base,
                    int32_t n_out, float anneal, const float* anneal_dev, float histogram_padding, float eps,
                    int32_t spacing,
                    float* new_sbins, float* new_ebins, float* cdf_out, int64_t* inds_out, void* stream);
+/* RaySamples.get_weights of the level being resampled (cameras/rays.py:129-152; euclidean edges `ebins`, density [R,n_in]
+ * -> weights [R,n_in], written) followed by b2n_pdf_sample on those weights (histogram over the spacing-domain edges
+ * `sbins`), one launch: the inner loop of ProposalNetworkSampler.generate_ray_samples
+ * (model_components/ray_samplers.py:568-604).  Same arithmetic as b2n_weights_fwd + b2n_pdf_sample. */
+int b2n_weights_pdf_sample(const float* sbins, const float* ebins, const float* density, const float* u_base,
+                           const float* jitter, int32_t jitter_per_bin, const float* nears, const float* fars,
+                           int64_t n_rays, int32_t n_in, int32_t n_out, float anneal, const float* anneal_dev,
+                           float histogram_padding, float eps, int32_t spacing, float* weights, float* new_sbins,
+                           float* new_ebins, void* stream);
 
 /* parity pin of the PDF sampler's normaliser: out[r] = sum(x[r, 0..n_cols)) accumulated in the order of torch's CPU
  * `sum` kernel (8-lane vectors x 4 interleaved rows x 4 cascade levels; model_components/ray_samplers.py:306 calls it),

@@ -8,6 +8,7 @@
 // One warp owns one ray; cdf and bin edges live in shared memory; the scan is a warp-shuffle scan over
 // per-lane contiguous chunks.
 #include "common.cuh"
+#include "render_rays.cuh"
 
 __device__ __forceinline__ float spacing_fn(int kind, float x) {
   switch (kind) {
@@ -68,16 +69,24 @@ extern "C" int b2n_spaced_sample(const float* nears, const float* fars, const fl
 #define PDF_WARPS 4
 
 __global__ void __launch_bounds__(PDF_WARPS * 32) pdf_sample_kernel(
-    const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ u_base,
+    const float* __restrict__ bins, const float* weights, const float* __restrict__ u_base,
     const float* __restrict__ jitter, int jitter_per_bin, const float* __restrict__ nears,
     const float* __restrict__ fars, int64_t n_rays, int S, int n_out, float anneal_host,
     const float* __restrict__ anneal_dev, float pad_hist, float eps,
     int spacing, float* __restrict__ new_sbins, float* __restrict__ new_ebins, float* __restrict__ cdf_out,
-    int64_t* __restrict__ inds_out) {
+    int64_t* __restrict__ inds_out, const float* __restrict__ ebins_in, const float* __restrict__ density,
+    float* weights_out) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * PDF_WARPS + warp;
   if (r >= n_rays) return;
+  if (density != nullptr) {
+    // fused RaySamples.get_weights (cameras/rays.py:129-152) of the level being resampled: same per-ray body as
+    // b2n_weights_fwd; the histogram below then reads what this warp just wrote
+    weights_fwd_ray<true>(ebins_in + r * (S + 1), ebins_in + r * (S + 1) + 1, density + r * S, S, weights_out + r * S, lane);
+    __syncwarp();
+    weights = weights_out;
+  }
   float* cdf = sm + (size_t)warp * 2 * (S + 1);
   float* eb = cdf + (S + 1);
   const int nb = n_out;  // number of new bin edges = num_samples + 1
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) pdf_sample_kernel(
 
   // pass 1: padded weights into smem (eb reused as scratch for w); their sum in torch's CPU summation order
   for (int i = i0; i < i1; ++i) {
-    float w = __ldg(wrow + i);
+    float w = density != nullptr ? wrow[i] : __ldg(wrow + i);
     if (anneal != 1.f) w = powf(w, anneal);
     eb[i] = add_rn(w, pad_hist);
   }
@@ -156,7 +165,25 @@ extern "C" int b2n_pdf_sample(const float* bins, const float* weights, const flo
   pdf_sample_kernel<<<(unsigned)div_up(n_rays, PDF_WARPS), PDF_WARPS * 32, smem, (cudaStream_t)stream>>>(
       bins, weights, u_base, jitter, jitter_per_bin, nears, fars, n_rays, n_in, n_out, anneal, anneal_dev,
       histogram_padding, eps,
-      spacing, new_sbins, new_ebins, cdf_out, inds_out);
+      spacing, new_sbins, new_ebins, cdf_out, inds_out, nullptr, nullptr, nullptr);
+  B2N_LAUNCH_CHECK();
+}
+
+// get_weights of the level being resampled + the PDF resampling in one launch (the proposal sampler's inner loop:
+// model_components/ray_samplers.py:568-604 calls field density -> get_weights -> PDFSampler per level)
+extern "C" int b2n_weights_pdf_sample(const float* sbins, const float* ebins, const float* density, const float* u_base,
+                                      const float* jitter, int32_t jitter_per_bin, const float* nears, const float* fars,
+                                      int64_t n_rays, int32_t n_in, int32_t n_out, float anneal, const float* anneal_dev,
+                                      float histogram_padding, float eps, int32_t spacing, float* weights, float* new_sbins,
+                                      float* new_ebins, void* stream) {
+  if (n_rays == 0) return B2N_OK;
+  B2N_REQUIRE(sbins && ebins && density && weights && u_base && nears && fars && new_sbins, "null pointer");
+  B2N_REQUIRE(n_in >= 1 && n_in <= 4096 && n_out >= 1, "sample counts out of range");
+  const size_t smem = sizeof(float) * PDF_WARPS * 2 * (n_in + 1);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(pdf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pdf_sample_kernel<<<(unsigned)div_up(n_rays, PDF_WARPS), PDF_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      sbins, weights, u_base, jitter, jitter_per_bin, nears, fars, n_rays, n_in, n_out, anneal, anneal_dev,
+      histogram_padding, eps, spacing, new_sbins, new_ebins, nullptr, nullptr, ebins, density, weights);
   B2N_LAUNCH_CHECK();
 }
 

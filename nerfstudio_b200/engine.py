@@ -264,7 +264,7 @@ class NerfactoStep:
         else:
             call("b2n_mlp_bwd", C.byref(m), C.byref(g), ptr(x), ptr(y), ptr(hidden), ptr(dy), n, ptr(dx), stream())
 
-    def _density_net_fwd(self, lvl: int, net: _Net) -> None:
+    def _density_net_fwd(self, lvl: int, net: _Net, weights: bool = True) -> None:
         R, S = self.R, self.S[lvl]
         N = R * S
         eb = self.eb[lvl]
@@ -274,7 +274,8 @@ class NerfactoStep:
             call("b2n_density_field_fwd", C.byref(net.grid.c), C.byref(m), ptr(net.table), ptr(self.origins),
                  ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S, int(self.contraction), C.cast(box, C.c_void_p),
                  self.avg, ptr(self.dens[lvl]), stream())
-            call("b2n_weights_fwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), R, S, ptr(self.w[lvl]), stream())
+            if weights:
+                call("b2n_weights_fwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), R, S, ptr(self.w[lvl]), stream())
             return
         call("b2n_positions_fwd", ptr(self.origins), ptr(self.directions), ptr(eb), _off(eb, 1), S + 1, R, S,
              int(self.contraction), C.cast(box, C.c_void_p), ptr(self.x[lvl]), ptr(self.sel[lvl], torch.uint8), stream())
@@ -283,7 +284,8 @@ class NerfactoStep:
         self._mlp_fwd(m, self.enc[lvl], self.enc[lvl].shape[1], N, self.h[lvl], self.hid[lvl], net.spec)
         call("b2n_density_act_fwd", ptr(self.h[lvl]), self.h[lvl].shape[1], ptr(self.sel[lvl], torch.uint8), N, self.avg,
              ptr(self.dens[lvl]), stream())
-        call("b2n_weights_fwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), R, S, ptr(self.w[lvl]), stream())
+        if weights:
+            call("b2n_weights_fwd", ptr(eb), _off(eb, 1), S + 1, ptr(self.dens[lvl]), R, S, ptr(self.w[lvl]), stream())
 
     def _density_net_bwd(self, lvl: int, net: _Net, d_hpre: Optional[Tensor]) -> None:
         """weights -> density -> pre-activation -> MLP -> encoding -> table, for a proposal level."""
@@ -347,11 +349,12 @@ class NerfactoStep:
         if self.fixed_bins is not None:
             self.sb[0].copy_(self.fixed_bins[0][0]), self.eb[0].copy_(self.fixed_bins[0][1])
         for lvl in (0, 1):
-            self._density_net_fwd(lvl, self.props[lvl])
-            call("b2n_pdf_sample", ptr(self.sb[lvl]), ptr(self.w[lvl]), ptr(self.u_base[lvl]),
+            # density of the level's samples, then get_weights + PDF resampling in one launch
+            self._density_net_fwd(lvl, self.props[lvl], weights=False)
+            call("b2n_weights_pdf_sample", ptr(self.sb[lvl]), ptr(self.eb[lvl]), ptr(self.dens[lvl]), ptr(self.u_base[lvl]),
                  NULL if ev else ptr(self.jitter[lvl + 1]), 0,
                  ptr(self.nears), ptr(self.fars), R, self.S[lvl], self.S[lvl + 1] + 1, 1.0, _off(self.hyper, 3), 0.01, 1e-5,
-                 lib.SPACING[self.spacing], ptr(self.sb[lvl + 1]), ptr(self.eb[lvl + 1]), NULL, NULL, st())
+                 lib.SPACING[self.spacing], ptr(self.w[lvl]), ptr(self.sb[lvl + 1]), ptr(self.eb[lvl + 1]), st())
             if self.fixed_bins is not None:  # staged parity tests: every level sees the reference's recorded samples
                 self.sb[lvl + 1].copy_(self.fixed_bins[lvl + 1][0]), self.eb[lvl + 1].copy_(self.fixed_bins[lvl + 1][1])
             if ev:

@@ -125,6 +125,7 @@ _SIGNATURES = {
     "b2n_nerfacto_ray_tail": [_I64, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _F, _P, _P, _I32, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P,
                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "b2n_loss_finalize": [_P, _I64, _F, _F, _F, _P, _P],
+    "b2n_weights_pdf_sample": [_P, _P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _I32, _F, _P, _F, _F, _I32, _P, _P, _P, _P],
     "b2n_step_begin": [_P, _I64, _P, _P, _I64, _P, _I64, _P],
     "b2n_add_inplace": [_P, _P, _I64, _P],
     "b2n_loss_total": [_P, _I32, _P, _P, _P],

@@ -11,6 +11,11 @@ Semantics follow tiny-cuda-nn's published behaviour: HashGrid 
 tiny-cuda-nn's sources are not available in this environment: numerical parity with it is UNPINNED (the oracle
 for this mode is oracle/nerf_oracle.py:tcnn_hash_encode).  Unlike tcnn we keep fp32 tables and outputs (the
 reference casts tcnn's fp16 outputs to fp32 immediately: nerfacto_field.py:230).
+
+Parameter LAYOUT is not tiny-cuda-nn's either: the flat `params` holds the exact (out, in) weight matrices back to back,
+without tcnn's padding of input/output widths to multiples of 16, so `params.numel()` differs and checkpoints written by
+genuine tiny-cuda-nn modules do not load into these (nor the other way round): `load_state_dict` reports the size
+mismatch.  Checkpoints of the torch-mode modules (`implementation="torch"`) are interchangeable with the reference's.
 """
 from __future__ import annotations
 

@@ -207,6 +207,7 @@ class NerfactoStep:
         self._fork = False        # grad zeroing / weight packing / position-gradient branches (joined inside _body)
         self._fork_props = False  # proposal backward as a branch (joined in _body_props; single-process step only)
         self._joins = []
+        self._props_stepped = False  # the proposal group was already stepped inside the forked branch of this step
         self._prologue_join = None
         self._pack_late = False   # sharded update: the weight images are packed after the parameter all-gather has landed
         self._h_ag = None         # pending all-gather of the field parameters (sharded update)
@@ -465,7 +466,13 @@ class NerfactoStep:
         self._joins = []
         if self._fork_props and update_props and self.fused_tail:
             # proposal backward: its inputs (d_density of both levels) are complete -> parallel branch
-            self._joins.append(self._forked(0, lambda: [self._density_net_bwd(lvl, self.props[lvl], None) for lvl in (0, 1)]))
+            def prop_branch() -> None:
+                for lvl in (0, 1):
+                    self._density_net_bwd(lvl, self.props[lvl], None)
+                self._adam(update_props, only_props=True)  # their gradients are complete: step them here, off the main chain
+                self._props_stepped = True
+
+            self._joins.append(self._forked(0, prop_branch))
         self._mlp_bwd(mh, gh, self.hin, self.hin_stride, self.rgb, self.hid_head, self.d_rgb, N2, self.d_hin, self.hin_stride,
                       self.head_spec)
         call("b2n_head_input_bwd", ptr(self.d_hin), self.hin_stride, self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre), ptr(self.cams, torch.int64),
@@ -547,14 +554,21 @@ class NerfactoStep:
             call("b2n_pose_apply_bwd", ptr(self.cam_pose), ptr(self.cams, torch.int64), ptr(self.cam_frozen, torch.uint8),
                  ptr(self.directions_in), ptr(self.d_rays[0]), ptr(self.d_rays[1]), self.R, ptr(self.cam_pose.grad), stream())
 
-    def _adam(self, update: bool = True) -> None:
+    def _adam(self, update: bool = True, only_props: bool = False) -> None:
         """Fused Adam over the flat buffer.  Frozen proposal networks are NOT stepped (reference: their grads are None
-        and engine/optimizers.py:155 skips the group), and when they are, they use their own bias-correction count."""
+        and engine/optimizers.py:155 skips the group), and when they are, they use their own bias-correction count.
+        `only_props`: just the proposal group (stepped at the end of the forked proposal branch, beside the main backward);
+        the regular call then leaves that group out."""
         o = self.optim
         runs = []
+        props_done = False
+        if not only_props:
+            props_done, self._props_stepped = self._props_stepped, False
         for name, a, b in o.segments:
             is_prop = name == "proposal_networks"
-            if is_prop and not update:
+            if is_prop and (not update or props_done):
+                continue
+            if only_props and not is_prop:
                 continue
             slot = 8 if name == "camera_opt" else (4 if (is_prop and not self.always_update) else 0)
             if runs and runs[-1][1] == a and runs[-1][2] == slot:

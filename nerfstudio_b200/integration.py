@@ -221,4 +221,14 @@ def install_fused_trainer(trainer, **engine_kwargs):
     trainer._b200_original_train_iteration = trainer.train_iteration
     trainer.train_iteration = fused.train_iteration
     pipeline.get_train_loss_dict = fused.get_train_loss_dict
+    # multi-GPU sharded update: the parameter all-gather of the last step may still be in flight when the trainer turns to
+    # evaluation or checkpointing (engine/trainer.py:532-580, 435-480) — make those wait for it
+    for name in ("eval_iteration", "save_checkpoint"):
+        orig = getattr(trainer, name, None)
+        if callable(orig):
+            def flushed(*a, _orig=orig, **k):
+                fused.flush()
+                return _orig(*a, **k)
+
+            setattr(trainer, name, flushed)
     return fused

@@ -433,6 +433,16 @@ int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int
 int b2n_head_input_bwd(const float* d_in, int32_t in_stride, int32_t n_sh, int32_t geo, int32_t n_emb, const float* d_dens_pre,
                        const int64_t* cam, int64_t n_rays, int32_t n_samples, float* d_base_out, int32_t base_w,
                        float* d_emb, void* stream);
+/* The same two operators restricted to a part of the columns, so that a caller can run the part that does not depend on
+ * the field off its critical path: forward part 1 = the 4-column groups that do not read base_out (SH + embedding columns:
+ * per-ray constants), 2 = the groups that do (geo features), 0 = all; needs 16-byte aligned rows.  Backward part 1 =
+ * d_base_out only, 2 = the embedding-row accumulation only (d_base_out may be NULL), 0 = both. */
+int b2n_head_input_fwd_part(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
+                            const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
+                            int32_t n_samples, float* out, int32_t out_stride, int32_t part, void* stream);
+int b2n_head_input_bwd_part(const float* d_in, int32_t in_stride, int32_t n_sh, int32_t geo, int32_t n_emb,
+                            const float* d_dens_pre, const int64_t* cam, int64_t n_rays, int32_t n_samples,
+                            float* d_base_out, int32_t base_w, float* d_emb, int32_t part, void* stream);
 /* loss_out[0] += mean((pred-gt)^2); d_pred = gscale * 2 (pred-gt)/n  (either output may be NULL) */
 int b2n_mse_fwd_bwd(const float* pred, const float* gt, int64_t n, float gscale, float* loss_out, float* d_pred,
                     void* stream);

@@ -21,11 +21,16 @@ __device__ __forceinline__ float head_input_elem(const float* __restrict__ sh, i
 __global__ void head_input_fwd_vec_kernel(const float* __restrict__ sh, int n_sh, const float* __restrict__ base_out,
                                           int base_w, int geo, const float* __restrict__ emb,
                                           const int64_t* __restrict__ cam, int n_emb, int emb_mode, int64_t n_rays, int S,
-                                          float* __restrict__ out, int out_stride) {
-  const int width = n_sh + geo + n_emb, groups = (width + 3) >> 2;
+                                          float* __restrict__ out, int out_stride, int part) {
+  // part 0: every 4-column group; 1: the groups that do not read base_out (SH and embedding columns: per-ray constants,
+  // available before the field runs); 2: the groups that do (geo features)
+  const int width = n_sh + geo + n_emb, all_groups = (width + 3) >> 2;
+  const int dyn0 = n_sh >> 2, dyn1 = min(all_groups, (n_sh + geo + 3) >> 2);
+  const int groups = part == 0 ? all_groups : part == 2 ? dyn1 - dyn0 : all_groups - (dyn1 - dyn0);
   const uint32_t total = (uint32_t)(n_rays * S) * (uint32_t)groups;  // host guarantees < 2^31
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const uint32_t n = idx / (uint32_t)groups, q = idx - n * (uint32_t)groups, r = n / (uint32_t)S;
+    const uint32_t n = idx / (uint32_t)groups, qi = idx - n * (uint32_t)groups, r = n / (uint32_t)S;
+    const uint32_t q = part == 0 ? qi : part == 2 ? qi + dyn0 : ((int)qi < dyn0 ? qi : qi + (dyn1 - dyn0));
     const int64_t cam_row = (emb_mode == 1 && (int)(4 * q + 3) >= n_sh + geo) ? __ldg(cam + r) : 0;
     float4 v;
     v.x = head_input_elem(sh, n_sh, base_out, base_w, geo, emb, cam_row, n_emb, emb_mode, n, r, 4 * q);
@@ -55,10 +60,10 @@ __global__ void head_input_fwd_kernel(const float* __restrict__ sh, int n_sh, co
 __global__ void head_input_bwd_kernel(const float* __restrict__ d_in, int in_stride, int n_sh, int geo, int n_emb,
                                       const float* __restrict__ d_dens_pre, const int64_t* __restrict__ cam,
                                       int64_t n_rays, int S, float* __restrict__ d_base_out, int base_w,
-                                      float* __restrict__ d_emb) {
+                                      float* __restrict__ d_emb, int part) {
   const int width = in_stride;
-  // part 1: one thread per (sample, base column)
-  const int64_t total1 = n_rays * S * base_w;
+  // part 1: one thread per (sample, base column)          (launch part: 0 = both, 1 = this one, 2 = the embedding rows)
+  const int64_t total1 = part == 2 ? 0 : n_rays * S * base_w;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = gtid; idx < total1; idx += gsz) {
     const int64_t n = idx / base_w;
@@ -69,7 +74,7 @@ __global__ void head_input_bwd_kernel(const float* __restrict__ d_in, int in_str
     d_base_out[idx] = v;
   }
   // part 2: one thread per (ray, embedding column): reduce over the ray's samples, one atomic per ray
-  if (d_emb != nullptr && n_emb > 0) {
+  if (d_emb != nullptr && n_emb > 0 && part != 1) {
     const int64_t total2 = n_rays * n_emb;
     for (int64_t idx = gtid; idx < total2; idx += gsz) {
       const int64_t r = idx / n_emb;
@@ -82,11 +87,12 @@ __global__ void head_input_bwd_kernel(const float* __restrict__ d_in, int in_str
   }
 }
 
-extern "C" int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
-                                  const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
-                                  int32_t n_samples, float* out, int32_t out_stride, void* stream) {
+extern "C" int b2n_head_input_fwd_part(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
+                                       const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
+                                       int32_t n_samples, float* out, int32_t out_stride, int32_t part, void* stream) {
   if (n_rays == 0) return B2N_OK;
   B2N_REQUIRE(sh && base_out && out, "null pointer");
+  B2N_REQUIRE(part >= 0 && part <= 2, "part");
   B2N_REQUIRE(n_emb == 0 || emb_mode == 0 || emb, "embedding table missing");
   B2N_REQUIRE(emb_mode != 1 || cam, "camera indices missing");
   B2N_REQUIRE(1 + geo <= base_w, "geo features exceed base width");
@@ -97,9 +103,10 @@ extern "C" int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* ba
   if ((out_stride & 3) == 0 && ((uintptr_t)out & 15) == 0 && 4 * groups <= out_stride && total_vec < (1ll << 31)) {
     const unsigned grid = (unsigned)min(div_up(total_vec, 256), (int64_t)b2n_sm_count() * 16);
     head_input_fwd_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sh, n_sh, base_out, base_w, geo, emb, cam, n_emb,
-                                                                      emb_mode, n_rays, n_samples, out, out_stride);
+                                                                      emb_mode, n_rays, n_samples, out, out_stride, part);
     B2N_LAUNCH_CHECK();
   }
+  B2N_UNSUPPORTED(part != 0, "head input in parts needs 16-byte aligned rows (out_stride % 4 == 0)");
   const int64_t total = n_rays * n_samples * width;
   const unsigned grid = (unsigned)min(div_up(total, 256), (int64_t)b2n_sm_count() * 32);
   head_input_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sh, n_sh, base_out, base_w, geo, emb, cam, n_emb,
@@ -107,19 +114,34 @@ extern "C" int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* ba
   B2N_LAUNCH_CHECK();
 }
 
-extern "C" int b2n_head_input_bwd(const float* d_in, int32_t in_stride, int32_t n_sh, int32_t geo, int32_t n_emb,
-                                  const float* d_dens_pre,
-                                  const int64_t* cam, int64_t n_rays, int32_t n_samples, float* d_base_out,
-                                  int32_t base_w, float* d_emb, void* stream) {
+extern "C" int b2n_head_input_fwd(const float* sh, int32_t n_sh, const float* base_out, int32_t base_w, int32_t geo,
+                                  const float* emb, const int64_t* cam, int32_t n_emb, int32_t emb_mode, int64_t n_rays,
+                                  int32_t n_samples, float* out, int32_t out_stride, void* stream) {
+  return b2n_head_input_fwd_part(sh, n_sh, base_out, base_w, geo, emb, cam, n_emb, emb_mode, n_rays, n_samples, out, out_stride, 0,
+                                 stream);
+}
+
+extern "C" int b2n_head_input_bwd_part(const float* d_in, int32_t in_stride, int32_t n_sh, int32_t geo, int32_t n_emb,
+                                       const float* d_dens_pre, const int64_t* cam, int64_t n_rays, int32_t n_samples,
+                                       float* d_base_out, int32_t base_w, float* d_emb, int32_t part, void* stream) {
   if (n_rays == 0) return B2N_OK;
-  B2N_REQUIRE(d_in && d_base_out, "null pointer");
+  B2N_REQUIRE(d_in && (d_base_out || part == 2), "null pointer");
+  B2N_REQUIRE(part >= 0 && part <= 2, "part");
   B2N_REQUIRE(d_emb == nullptr || cam, "camera indices missing");
   B2N_REQUIRE(in_stride >= n_sh + geo + n_emb, "in_stride too small");
-  const int64_t total = n_rays * n_samples * base_w;
+  const int64_t total = part == 2 ? n_rays * n_emb : n_rays * n_samples * base_w;
+  if (total == 0) return B2N_OK;
   const unsigned grid = (unsigned)min(div_up(total, 256), (int64_t)b2n_sm_count() * 32);
   head_input_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, in_stride, n_sh, geo, n_emb, d_dens_pre, cam, n_rays,
-                                                                n_samples, d_base_out, base_w, d_emb);
+                                                                n_samples, d_base_out, base_w, d_emb, part);
   B2N_LAUNCH_CHECK();
+}
+
+extern "C" int b2n_head_input_bwd(const float* d_in, int32_t in_stride, int32_t n_sh, int32_t geo, int32_t n_emb,
+                                  const float* d_dens_pre, const int64_t* cam, int64_t n_rays, int32_t n_samples,
+                                  float* d_base_out, int32_t base_w, float* d_emb, void* stream) {
+  return b2n_head_input_bwd_part(d_in, in_stride, n_sh, geo, n_emb, d_dens_pre, cam, n_rays, n_samples, d_base_out, base_w, d_emb,
+                                 0, stream);
 }
 
 // loss_out[0] += mean((pred - gt)^2) * 1 ; d_pred = gscale * 2 (pred - gt) / n     (nn.MSELoss, models/nerfacto.py:372)

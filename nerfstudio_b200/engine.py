@@ -208,6 +208,7 @@ class NerfactoStep:
         self._fork_props = False  # proposal backward as a branch (joined in _body_props; single-process step only)
         self._joins = []
         self._props_stepped = False  # the proposal group was already stepped inside the forked branch of this step
+        self._head_static_join = None
         self._prologue_join = None
         self._pack_late = False   # sharded update: the weight images are packed after the parameter all-gather has landed
         self._h_ag = None         # pending all-gather of the field parameters (sharded update)
@@ -344,6 +345,16 @@ class NerfactoStep:
         if self.camopt is not None:  # CameraOptimizer.apply_to_raybundle (camera_optimizers.py:148-153)
             call("b2n_pose_apply_fwd", ptr(self.cam_pose), ptr(self.cams, torch.int64), ptr(self.cam_frozen, torch.uint8),
                  ptr(self.origins_in), ptr(self.directions_in), R, ptr(self.origins), ptr(self.directions), st())
+        self._head_static_join = None
+        if self._fork and not ev and not self._pack_late and self.hin_stride % 4 == 0:
+            # SH of the (pose-corrected) directions and the per-ray constant columns of the colour head's input do not depend
+            # on the field: a branch beside the proposal sampling (not in the sharded multi-GPU step, where the embedding
+            # table is still being all-gathered at this point)
+            def head_static() -> None:
+                call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), stream())
+                self._head_input(1)
+
+            self._head_static_join = self._forked(0, head_static)
         # ---------------- forward: proposal sampling
         call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), NULL if ev else ptr(self.jitter[0]), 0, R, S0,
              lib.SPACING[self.spacing], ptr(self.sb[0]), ptr(self.eb[0]), st())
@@ -362,6 +373,19 @@ class NerfactoStep:
                 eb = self.eb[lvl]
                 call("b2n_composite_fwd", NULL, ptr(self.w[lvl]), ptr(eb), _off(eb, 1), self.S[lvl] + 1, R, self.S[lvl],
                      lib.BG_NONE, NULL, 0, NULL, NULL, NULL, ptr(self.prop_depth[lvl]), NULL, st())
+
+    def _head_input(self, part: int) -> None:
+        """Colour-head input rows [SH | geo features | appearance embedding] (nerfacto_field.py:234-310); part 1 = the
+        columns that are constant along a ray, 2 = the geo features, 0 = all."""
+        R, S2, ev = self.R, self.S[2], self.eval_mode
+        if self.emb is None:
+            emb_ptr, emb_mode = NULL, 0
+        elif ev:  # nerfacto_field.py:250-261: mean embedding (pre-averaged into emb_mean by the caller) or zeros
+            emb_ptr, emb_mode = (ptr(self.emb_mean), 2) if self.model.field.use_average_appearance_embedding else (NULL, 0)
+        else:
+            emb_ptr, emb_mode = ptr(self.emb), 1
+        call("b2n_head_input_fwd_part", ptr(self.sh), self.n_sh, ptr(self.h[2]), self.h[2].shape[1], self.geo, emb_ptr,
+             ptr(self.cams, torch.int64), self.n_emb, emb_mode, R, S2, ptr(self.hin), self.hin_stride, part, stream())
 
     def _forward_main(self) -> None:
         """Main field on the final samples: positions, hash grid, base MLP, colour head (+ weights and renderers unless the
@@ -386,15 +410,13 @@ class NerfactoStep:
         tail = self.fused_tail and not ev  # density activation, weights and renderers run inside b2n_nerfacto_ray_tail
         if not tail:
             call("b2n_density_act_fwd", ptr(self.h[2]), bw, ptr(self.sel[2], torch.uint8), N2, self.avg, ptr(self.dens[2]), st())
-        call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), st())
-        if self.emb is None:
-            emb_ptr, emb_mode = NULL, 0
-        elif ev:  # nerfacto_field.py:250-261: mean embedding (pre-averaged into emb_mean by the caller) or zeros
-            emb_ptr, emb_mode = (ptr(self.emb_mean), 2) if self.model.field.use_average_appearance_embedding else (NULL, 0)
+        if self._head_static_join is not None:  # SH + embedding columns of the head input were written by a forked branch
+            torch.cuda.current_stream().wait_event(self._head_static_join)
+            self._head_static_join = None
+            self._head_input(2)
         else:
-            emb_ptr, emb_mode = ptr(self.emb), 1
-        call("b2n_head_input_fwd", ptr(self.sh), self.n_sh, ptr(self.h[2]), bw, self.geo, emb_ptr, ptr(self.cams, torch.int64),
-             self.n_emb, emb_mode, R, S2, ptr(self.hin), self.hin_stride, st())
+            call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), st())
+            self._head_input(0)
         mh = self.head_spec.struct(self.head_w, self.head_b)
         gh = B2nMlpGrad()
         for i, (w, b) in enumerate(zip(self.head_w, self.head_b)):
@@ -475,8 +497,18 @@ class NerfactoStep:
             self._joins.append(self._forked(0, prop_branch))
         self._mlp_bwd(mh, gh, self.hin, self.hin_stride, self.rgb, self.hid_head, self.d_rgb, N2, self.d_hin, self.hin_stride,
                       self.head_spec)
-        call("b2n_head_input_bwd", ptr(self.d_hin), self.hin_stride, self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre), ptr(self.cams, torch.int64),
-             R, S2, ptr(self.d_h[2]), bw, ptr(self.emb.grad) if self.emb is not None else NULL, st())
+        emb_grad = ptr(self.emb.grad) if self.emb is not None else NULL
+
+        def head_in_bwd(part: int) -> None:
+            call("b2n_head_input_bwd_part", ptr(self.d_hin), self.hin_stride, self.n_sh, self.geo, self.n_emb, ptr(self.d_hpre),
+                 ptr(self.cams, torch.int64), R, S2, ptr(self.d_h[2]), bw, emb_grad, part, stream())
+
+        emb_join = None
+        if self._fork and self.emb is not None:
+            head_in_bwd(1)                                        # d(base output): the base MLP's backward waits for it
+            emb_join = self._forked(1, lambda: head_in_bwd(2))    # embedding-row gradients: beside the base backward
+        else:
+            head_in_bwd(0)
         self._mlp_bwd(mb, gb, self.enc[2], self.enc[2].shape[1], self.h[2], self.hid[2], self.d_h[2], N2, self.d_enc[2],
                       self.d_enc[2].shape[1], self.base.spec)
         def main_dx() -> None:
@@ -503,8 +535,9 @@ class NerfactoStep:
             call("b2n_loss_finalize", self._tail_keep[6], R, il, dm, 1.0 / float(3 * R), ptr(self.losses), st())
         else:
             call("b2n_loss_total", ptr(self.losses), 3, _off(self.losses, 4), _off(self.losses, 3), st())
-        if dx_join is not None:
-            torch.cuda.current_stream().wait_event(dx_join)
+        for ev_ in (dx_join, emb_join):
+            if ev_ is not None:
+                torch.cuda.current_stream().wait_event(ev_)
 
     def _tail_unfused(self, update_props: bool, il: float, dm: float) -> None:
         """The per-ray middle of the step, one operator per launch (what b2n_nerfacto_ray_tail fuses)."""

@@ -120,6 +120,8 @@ _SIGNATURES = {
     "b2n_adam_step_dev": [_P, _P, _P, _P, _I64, _P, C.c_double, C.c_double, C.c_double, _P],
     "b2n_head_input_fwd": [_P, _I32, _P, _I32, _I32, _P, _P, _I32, _I32, _I64, _I32, _P, _I32, _P],
     "b2n_head_input_bwd": [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _P],
+    "b2n_head_input_fwd_part": [_P, _I32, _P, _I32, _I32, _P, _P, _I32, _I32, _I64, _I32, _P, _I32, _I32, _P],
+    "b2n_head_input_bwd_part": [_P, _I32, _I32, _I32, _I32, _P, _P, _I64, _I32, _P, _I32, _P, _I32, _P],
     "b2n_mse_fwd_bwd": [_P, _P, _I64, _F, _P, _P, _P],
     "b2n_sum_rows": [_P, _I64, _F, _P, _P],
     "b2n_nerfacto_ray_tail": [_I64, _I32, _I32, _I32, _P, _P, _P, _I32, _P, _F, _P, _P, _I32, _P, _F, _F, _F, _P, _P, _P, _P, _P, _P,

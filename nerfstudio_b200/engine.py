@@ -346,15 +346,11 @@ class NerfactoStep:
             call("b2n_pose_apply_fwd", ptr(self.cam_pose), ptr(self.cams, torch.int64), ptr(self.cam_frozen, torch.uint8),
                  ptr(self.origins_in), ptr(self.directions_in), R, ptr(self.origins), ptr(self.directions), st())
         self._head_static_join = None
-        if self._fork and not ev and not self._pack_late and self.hin_stride % 4 == 0:
+        if not self._pack_late:
             # SH of the (pose-corrected) directions and the per-ray constant columns of the colour head's input do not depend
-            # on the field: a branch beside the proposal sampling (not in the sharded multi-GPU step, where the embedding
-            # table is still being all-gathered at this point)
-            def head_static() -> None:
-                call("b2n_sh_fwd", ptr(self.directions), R, 4, 1, ptr(self.sh), stream())
-                self._head_input(1)
-
-            self._head_static_join = self._forked(0, head_static)
+            # on the field: a branch beside the proposal sampling (in the sharded multi-GPU step the embedding table is still
+            # being all-gathered at this point: the branch starts at the head of _forward_main instead)
+            self._fork_head_static()
         # ---------------- forward: proposal sampling
         call("b2n_spaced_sample", ptr(self.nears), ptr(self.fars), ptr(self.lin0), NULL if ev else ptr(self.jitter[0]), 0, R, S0,
              lib.SPACING[self.spacing], ptr(self.sb[0]), ptr(self.eb[0]), st())
@@ -373,6 +369,16 @@ class NerfactoStep:
                 eb = self.eb[lvl]
                 call("b2n_composite_fwd", NULL, ptr(self.w[lvl]), ptr(eb), _off(eb, 1), self.S[lvl] + 1, R, self.S[lvl],
                      lib.BG_NONE, NULL, 0, NULL, NULL, NULL, ptr(self.prop_depth[lvl]), NULL, st())
+
+    def _fork_head_static(self) -> None:
+        if self._head_static_join is not None or not self._fork or self.eval_mode or self.hin_stride % 4 != 0:
+            return
+
+        def head_static() -> None:
+            call("b2n_sh_fwd", ptr(self.directions), self.R, 4, 1, ptr(self.sh), stream())
+            self._head_input(1)
+
+        self._head_static_join = self._forked(0, head_static)
 
     def _head_input(self, part: int) -> None:
         """Colour-head input rows [SH | geo features | appearance embedding] (nerfacto_field.py:234-310); part 1 = the
@@ -398,6 +404,7 @@ class NerfactoStep:
             self._prologue_join = None
         if self.tma_weights and self._pack_late:
             self._pack_weights()
+        self._fork_head_static()  # (no-op when the branch is already running)
         N2 = R * S2
         eb2 = self.eb[2]
         box = lib.host_floats(self.aabb)

@@ -719,3 +719,64 @@ def test_step_begin_philox_and_zeroing():
     t = torch.tensor([0.1, 0.2, 0.3, 0.0, 0.7], device="cuda")
     call("b2n_loss_total", ptr(t), 3, ptr(t[4:]), ptr(t[3:]), stream())
     assert float(t[3]) == float(((t[0] + t[1]) + t[2]) + t[4])
+
+
+def test_fused_weights_pdf_sample_equals_the_two_operators():
+    """b2n_weights_pdf_sample = b2n_weights_fwd followed by b2n_pdf_sample, bit for bit (weights and new edges), with the
+    anneal exponent on and off, ragged sample counts."""
+    from nerfstudio_b200.functional import _linspace
+    from nerfstudio_b200.lib import SPACING, call, ptr, stream
+
+    torch.manual_seed(3)
+    for R, S, nb, anneal in ((513, 256, 97, 0.7), (257, 96, 49, 1.0), (64, 37, 20, 0.35)):
+        sb = torch.sort(torch.rand(R, S + 1, device="cuda"), dim=-1).values
+        near, far = torch.full((R,), 0.05, device="cuda"), torch.full((R,), 1000.0, device="cuda")
+        eb = 1.0 / (1.0 / near[:, None] * (1 - sb) + 1.0 / far[:, None] * sb)
+        eb = torch.sort(eb, dim=-1).values.contiguous()
+        dens = torch.rand(R, S, device="cuda") * 5 * (torch.rand(R, S, device="cuda") > 0.4)
+        jit = torch.rand(R, 1, device="cuda")
+        u_base = _linspace(0.0, 1.0 - (1.0 / nb), nb, sb.device)
+        w0 = torch.empty(R, S, device="cuda")
+        call("b2n_weights_fwd", ptr(eb), ptr(eb.view(-1)[1:]), S + 1, ptr(dens), R, S, ptr(w0), stream())  # ends = starts + 1 element
+        ns0, ne0 = torch.empty(R, nb, device="cuda"), torch.empty(R, nb, device="cuda")
+        call("b2n_pdf_sample", ptr(sb), ptr(w0), ptr(u_base), ptr(jit), 0, ptr(near), ptr(far), R, S, nb, float(anneal), ptr(None),
+             0.01, 1e-5, SPACING["piecewise"], ptr(ns0), ptr(ne0), ptr(None), ptr(None), stream())
+        w1, ns1, ne1 = torch.empty_like(w0), torch.empty_like(ns0), torch.empty_like(ne0)
+        call("b2n_weights_pdf_sample", ptr(sb), ptr(eb), ptr(dens), ptr(u_base), ptr(jit), 0, ptr(near), ptr(far), R, S, nb,
+             float(anneal), ptr(None), 0.01, 1e-5, SPACING["piecewise"], ptr(w1), ptr(ns1), ptr(ne1), stream())
+        assert torch.equal(w0, w1) and torch.equal(ns0, ns1) and torch.equal(ne0, ne1), (R, S)
+
+
+def test_head_input_parts_compose():
+    """b2n_head_input_fwd_part: the static (SH + embedding) and the geo column groups together write exactly what the whole
+    operator writes; backward parts 1 + 2 produce what part 0 produces."""
+    from nerfstudio_b200.lib import call, ptr, stream
+
+    torch.manual_seed(5)
+    R, S, n_sh, geo, n_emb, bw, stride = 129, 48, 16, 15, 32, 16, 64
+    sh, base = torch.randn(R, n_sh, device="cuda"), torch.randn(R * S, bw, device="cuda")
+    emb, cam = torch.randn(7, n_emb, device="cuda"), torch.randint(0, 7, (R,), device="cuda")
+    outs = []
+    for parts in ((0,), (1, 2), (2, 1)):
+        out = torch.full((R * S, stride), float("nan"), device="cuda")
+        for part in parts:
+            call("b2n_head_input_fwd_part", ptr(sh), n_sh, ptr(base), bw, geo, ptr(emb), ptr(cam, torch.int64), n_emb, 1, R, S,
+                 ptr(out), stride, part, stream())
+        outs.append(out)
+    assert not torch.isnan(outs[0]).any()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = torch.cat([sh[:, None, :].expand(R, S, n_sh).reshape(R * S, n_sh), base[:, 1:1 + geo], emb[cam][:, None, :].expand(R, S, n_emb)
+                     .reshape(R * S, n_emb), torch.zeros(R * S, 1, device="cuda")], dim=1)
+    assert torch.equal(outs[0], ref)
+    d_in, d_pre = torch.randn(R * S, stride, device="cuda"), torch.randn(R * S, device="cuda")
+    res = []
+    for parts in ((0,), (1, 2)):
+        d_base, d_emb = torch.full((R * S, bw), float("nan"), device="cuda"), torch.zeros_like(emb)
+        for part in parts:
+            call("b2n_head_input_bwd_part", ptr(d_in), stride, n_sh, geo, n_emb, ptr(d_pre), ptr(cam, torch.int64), R, S, ptr(d_base), bw,
+                 ptr(d_emb), part, stream())
+        res.append((d_base, d_emb))
+    assert torch.equal(res[0][0], res[1][0])
+    assert_close(res[1][1], res[0][1], 1e-5, "embedding-row gradients")  # float atomics across rays of one camera
+    want = torch.zeros_like(emb).index_add_(0, cam, d_in[:, n_sh + geo: n_sh + geo + n_emb].reshape(R, S, n_emb).sum(1))
+    assert_close(res[0][1], want, 1e-4, "embedding-row gradients vs torch")

@@ -516,7 +516,7 @@ def run_b200(args) -> None:
         name, (c, t) = max(prof.items(), key=lambda kv: kv[1][1])
         ms_avg = t / c
         share = t / n_prof / ms_prof
-        if name.startswith("b2n_mlp_tc"):
+        if name.startswith("b2n_mlp_tc") and "n=" in name and "in=" in name:  # (b2n_mlp_tc_pack carries no shape)
             tpeak, tsrc = sustained_tensor_peak()
             n_rows = int(name.split("n=")[1].split(",")[0])
             key = (int(name.split("in=")[1].split(",")[0]), int(name.split("out=")[1].split("]")[0]))

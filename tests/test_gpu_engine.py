@@ -241,6 +241,25 @@ def test_fused_ray_tail_equals_operator_chain(cuda, golden):
     assert_close(b.optim.flat_grad, a.optim.flat_grad, 1e-5, "flat gradient")
 
 
+def test_branches_do_not_change_the_update(cuda, golden):
+    """The captured step with its parallel branches (proposal backward + its Adam, position gradient, early Adam of the fine
+    table levels, static head-input columns, ...) against the same step issued as one chain: same losses and, after three
+    optimisation steps, the same parameters (up to float-atomics order)."""
+    g = golden("nerfacto_pipeline")
+    m_c, chain = _mk(g, use_graph=True, concurrent_backward=False)
+    m_b, branched = _mk(g, use_graph=True, concurrent_backward=True)
+    assert branched.concurrent and not chain.concurrent
+    for it in range(3):
+        lc, lb = chain.step().clone(), branched.step().clone()
+        torch.cuda.synchronize()
+        assert_close(lb, lc, 1e-5, f"losses step {it}")
+    for (k, a), (_, b) in zip(m_b.state_dict().items(), m_c.state_dict().items()):
+        if a.dtype.is_floating_point and a.numel() > 1:
+            rel = float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+            assert rel < 1e-4, (k, rel)
+    assert float(branched.optim.exp_avg.abs().sum()) > 0
+
+
 def test_engine_trains(cuda, golden):
     """Sanity of the optimisation loop under graph replay with fresh random jitter: the loss goes down."""
     g = golden("nerfacto_pipeline")

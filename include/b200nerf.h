@@ -103,12 +103,6 @@ int b2n_hashgrid_fwd(const B2nGrid* grid_host, const float* x, const float* tabl
 /* dtable [rows,F] is ACCUMULATED into (caller zeroes);  dx [N,3] optional (NULL = skip) is overwritten. */
 int b2n_hashgrid_bwd(const B2nGrid* grid_host, const float* x, const float* table, const float* dy, int64_t n,
                      float* dtable, float* dx, void* stream);
-/* The table scatter of levels [level_begin, level_end) only (same kernel, no dx): a caller can consume the finished rows
- * of some levels — e.g. run their optimiser step — while the other levels are still being scattered.  Level l owns the
- * table rows [b2n_grid_level_rows(grid, l), b2n_grid_level_rows(grid, l + 1)); returns -1 on a bad argument. */
-int b2n_hashgrid_bwd_levels(const B2nGrid* grid_host, const float* x, const float* dy, int64_t n, float* dtable,
-                            int32_t level_begin, int32_t level_end, void* stream);
-int64_t b2n_grid_level_rows(const B2nGrid* grid_host, int32_t level);
 
 /* position gradient only: dx [N,3] = d<dy, y>/dx (overwritten), no table scatter — for callers that get dtable from the
  * run-length scatter of b2n_hashgrid_bwd(dx = NULL) and need d x as well (camera optimiser: positions_bwd -> poses). */

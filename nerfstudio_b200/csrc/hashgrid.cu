@@ -287,11 +287,11 @@ template <int F, int MODE, int CH>
 __global__ void __launch_bounds__(256) hashgrid_bwd_runs_kernel(const __grid_constant__ GridParams gp,
                                                                 const float* __restrict__ x,
                                                                 const float* __restrict__ dy, int64_t n,
-                                                                float* __restrict__ dtable, int level0) {
+                                                                float* __restrict__ dtable) {
   const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i0 = chunk * CH;
   if (i0 >= n) return;
-  const int l = level0 + blockIdx.y;
+  const int l = blockIdx.y;
   const int LF = gp.n_levels * F;
   uint32_t rows[8];
   float acc[8][F];
@@ -363,14 +363,12 @@ static void launch_fwd(const GridParams& gp, const float* x, const float* table,
 }
 
 template <int F, int CH>
-static void launch_bwd_runs(const GridParams& gp, const float* x, const float* dy, int64_t n, float* dtable, cudaStream_t st,
-                            int level0 = 0, int level1 = -1) {
-  if (level1 < 0) level1 = gp.n_levels;
-  dim3 grid((unsigned)div_up(div_up(n, CH), 256), (unsigned)(level1 - level0));
+static void launch_bwd_runs(const GridParams& gp, const float* x, const float* dy, int64_t n, float* dtable, cudaStream_t st) {
+  dim3 grid((unsigned)div_up(div_up(n, CH), 256), (unsigned)gp.n_levels);
   if (gp.mode == B2N_GRID_TORCH)
-    hashgrid_bwd_runs_kernel<F, B2N_GRID_TORCH, CH><<<grid, 256, 0, st>>>(gp, x, dy, n, dtable, level0);
+    hashgrid_bwd_runs_kernel<F, B2N_GRID_TORCH, CH><<<grid, 256, 0, st>>>(gp, x, dy, n, dtable);
   else
-    hashgrid_bwd_runs_kernel<F, B2N_GRID_TCNN, CH><<<grid, 256, 0, st>>>(gp, x, dy, n, dtable, level0);
+    hashgrid_bwd_runs_kernel<F, B2N_GRID_TCNN, CH><<<grid, 256, 0, st>>>(gp, x, dy, n, dtable);
 }
 
 template <int F, bool DX>
@@ -435,43 +433,6 @@ extern "C" int b2n_hashgrid_bwd(const B2nGrid* grid_host, const float* x, const 
   }
 #undef B2N_BWD_CASE
   B2N_LAUNCH_CHECK();
-}
-
-// The table scatter of levels [level_begin, level_end) only: lets a caller start consuming the finished rows of some levels
-// (e.g. their optimiser step) while the other levels are still being scattered.  Rows of level l are
-// [row_offset(l), row_offset(l+1)) of the table (b2n_grid_level_rows).
-extern "C" int b2n_hashgrid_bwd_levels(const B2nGrid* grid_host, const float* x, const float* dy, int64_t n, float* dtable,
-                                       int32_t level_begin, int32_t level_end, void* stream) {
-  if (n == 0) return B2N_OK;
-  B2N_REQUIRE(grid_host && x && dy && dtable, "null pointer");
-  GridParams gp;
-  B2N_REQUIRE(fill_params(grid_host, gp) == 0, "bad grid description");
-  B2N_REQUIRE(0 <= level_begin && level_begin < level_end && level_end <= gp.n_levels, "level range");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int ch = g_bwd_chunk >= 16 ? 16 : g_bwd_chunk >= 8 ? 8 : 4;
-#define B2N_BWDL_CASE(F)                                                                              \
-  case F:                                                                                             \
-    if (ch == 16) launch_bwd_runs<F, 16>(gp, x, dy, n, dtable, st, level_begin, level_end);           \
-    else if (ch == 8) launch_bwd_runs<F, 8>(gp, x, dy, n, dtable, st, level_begin, level_end);        \
-    else launch_bwd_runs<F, 4>(gp, x, dy, n, dtable, st, level_begin, level_end);                     \
-    break;
-  switch (grid_host->n_features) {
-    B2N_BWDL_CASE(1)
-    B2N_BWDL_CASE(2)
-    B2N_BWDL_CASE(4)
-    B2N_BWDL_CASE(8)
-    default: B2N_UNSUPPORTED(true, "n_features must be 1, 2, 4 or 8");
-  }
-#undef B2N_BWDL_CASE
-  B2N_LAUNCH_CHECK();
-}
-
-// first table row of level `level` (level == n_levels: total rows)
-extern "C" int64_t b2n_grid_level_rows(const B2nGrid* grid_host, int32_t level) {
-  GridParams gp;
-  if (!grid_host || fill_params(grid_host, gp) != 0 || level < 0 || level > gp.n_levels) return -1;
-  if (level == gp.n_levels) return (int64_t)gp.offset[gp.n_levels - 1] + gp.size[gp.n_levels - 1];
-  return (int64_t)gp.offset[level];
 }
 
 extern "C" int b2n_hashgrid_dx(const B2nGrid* grid_host, const float* x, const float* table, const float* dy, int64_t n,

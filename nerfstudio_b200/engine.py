@@ -203,14 +203,12 @@ class NerfactoStep:
         # (i) is not used when collectives run between the pieces of the step (the field all-reduce overlaps the proposal
         # backward there); the other branches are joined inside the first piece.
         self.concurrent = concurrent_backward and not eval_mode
-        self._side = [torch.cuda.Stream() for _ in range(3)] if self.concurrent else []
+        self._side = [torch.cuda.Stream(), torch.cuda.Stream()] if self.concurrent else []
         self._fork = False        # grad zeroing / weight packing / position-gradient branches (joined inside _body)
         self._fork_props = False  # proposal backward as a branch (joined in _body_props; single-process step only)
         self._joins = []
         self._props_stepped = False  # the proposal group was already stepped inside the forked branch of this step
         self._head_static_join = None
-        self._adam_done = []       # [begin, end) ranges of the flat buffer already stepped inside this step's graph
-        self._adam_early_join = None
         self._prologue_join = None
         self._pack_late = False   # sharded update: the weight images are packed after the parameter all-gather has landed
         self._h_ag = None         # pending all-gather of the field parameters (sharded update)
@@ -532,31 +530,8 @@ class NerfactoStep:
         dx_join = None
         if self.camopt is not None and self._fork:
             dx_join = self._forked(1, main_dx)  # gather-bound, next to the atomics-bound scatter below
-        grid_c = self.base.grid.c
-        L = int(grid_c.n_levels)
-        if self._fork_props and L >= 2:
-            # Scatter the fine half of the levels first and step their table rows (Adam: HBM streaming) on a branch while
-            # the coarse half is still being scattered (L2 atomics): different resources, and the optimiser of 8 M
-            # parameters leaves the critical path.  Single-process step only (the sharded step runs Adam after a collective).
-            o, mid = self.optim, L // 2
-            rows = lambda lvl: int(lib.load().b2n_grid_level_rows(C.byref(grid_c), lvl))
-            F_ = int(grid_c.n_features)
-            base_off = (self.base.table.data_ptr() - o.flat.data_ptr()) // 4
-            a, b = base_off + rows(mid) * F_, base_off + rows(L) * F_
-            call("b2n_hashgrid_bwd_levels", C.byref(grid_c), ptr(self.x[2]), ptr(self.d_enc[2]), N2, ptr(self.base.table.grad),
-                 mid, L, st())
-
-            def adam_fine() -> None:
-                call("b2n_adam_step_dev", _off(o.flat, a), _off(o.flat_grad, a), _off(o.exp_avg, a), _off(o.exp_avg_sq, a),
-                     b - a, _off(self.hyper, 0), float(o.betas[0]), float(o.betas[1]), float(o.eps), stream())
-
-            self._adam_early_join = self._forked(2, adam_fine)
-            self._adam_done.append((a, b))
-            call("b2n_hashgrid_bwd_levels", C.byref(grid_c), ptr(self.x[2]), ptr(self.d_enc[2]), N2, ptr(self.base.table.grad),
-                 0, mid, st())
-        else:
-            call("b2n_hashgrid_bwd", C.byref(grid_c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
-                 ptr(self.base.table.grad), NULL, st())
+        call("b2n_hashgrid_bwd", C.byref(self.base.grid.c), ptr(self.x[2]), ptr(self.base.table), ptr(self.d_enc[2]), N2,
+             ptr(self.base.table.grad), NULL, st())
         if self.camopt is not None:
             if not self._fork:
                 main_dx()
@@ -640,18 +615,6 @@ class NerfactoStep:
                 runs[-1][1] = b
             else:
                 runs.append([a, b, slot])
-        if not only_props:
-            if self._adam_early_join is not None:
-                torch.cuda.current_stream().wait_event(self._adam_early_join)
-                self._adam_early_join = None
-            for d0, d1 in self._adam_done:  # ranges already stepped on a branch of this step
-                cut = []
-                for a, b, slot in runs:
-                    for lo, hi in ((a, min(b, d0)), (max(a, d1), b)):
-                        if hi > lo:
-                            cut.append([lo, hi, slot])
-                runs = cut
-            self._adam_done = []
         if self._shard is not None:
             # sharded update: of the field segment [0, grad_split) this rank steps its own slice (whose gradient sums the
             # reduce-scatter left here) and the short tail that went through the all-reduce; the all-gather that follows

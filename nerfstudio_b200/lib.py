@@ -128,7 +128,6 @@ _SIGNATURES = {
                               _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "b2n_loss_finalize": [_P, _I64, _F, _F, _F, _P, _P],
     "b2n_weights_pdf_sample": [_P, _P, _P, _P, _P, _I32, _P, _P, _I64, _I32, _I32, _F, _P, _F, _F, _I32, _P, _P, _P, _P],
-    "b2n_hashgrid_bwd_levels": [_P, _P, _P, _I64, _P, _I32, _I32, _P],
     "b2n_step_begin": [_P, _I64, _P, _P, _I64, _P, _I64, _P],
     "b2n_add_inplace": [_P, _P, _I64, _P],
     "b2n_loss_total": [_P, _I32, _P, _P, _P],
@@ -136,8 +135,7 @@ _SIGNATURES = {
     "b2n_adam_step": [_P, _P, _P, _P, _I64, _I32, C.c_double, C.c_double, C.c_double, C.c_double, _F, _P],
 }
 _RET = {"b2n_version": C.c_char_p, "b2n_last_error": C.c_char_p}
-_RET_ARGS = {"b2n_mlp_tc_workspace_bytes": ([C.POINTER(B2nMlp)], C.c_int64),
-             "b2n_grid_level_rows": ([_P, _I32], C.c_int64)}
+_RET_ARGS = {"b2n_mlp_tc_workspace_bytes": ([C.POINTER(B2nMlp)], C.c_int64)}
 
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_RET) + list(_RET_ARGS))
 

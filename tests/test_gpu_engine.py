@@ -242,8 +242,8 @@ def test_fused_ray_tail_equals_operator_chain(cuda, golden):
 
 
 def test_branches_do_not_change_the_update(cuda, golden):
-    """The captured step with its parallel branches (proposal backward + its Adam, position gradient, early Adam of the fine
-    table levels, static head-input columns, ...) against the same step issued as one chain: same losses and, after three
+    """The captured step with its parallel branches (proposal backward + its Adam, position gradient, static head-input
+    columns, embedding-row gradients, ...) against the same step issued as one chain: same losses and, after three
     optimisation steps, the same parameters (up to float-atomics order)."""
     g = golden("nerfacto_pipeline")
     m_c, chain = _mk(g, use_graph=True, concurrent_backward=False)

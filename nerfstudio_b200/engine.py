@@ -8,8 +8,17 @@ a CUDA graph and replays it: one graph launch per optimisation step, no tracing 
 allocation.  Parameters stay the model's own nn.Parameters (views into one flat buffer), so state_dicts and
 evaluation through the module API are unaffected.
 
-Per-step scalars that change (Adam bias corrections, proposal-weight anneal exponent, lr schedule) live in a tiny
-device buffer refreshed with one 16-byte copy before each replay.
+Per-step scalars that change (Adam bias corrections of the three parameter groups, proposal-weight anneal exponent, lr
+schedules) live in a tiny device buffer refreshed with one small copy before each replay; the stratified draws come from a
+Philox state kept on the device.
+
+Shape of the captured step:
+  * single process — ONE graph whose independent pieces are parallel branches (forked streams during capture): the
+    proposal fields' backward + their Adam, the main grid's position gradient, the gradient memset + TMA weight packing,
+    the per-ray-constant columns of the colour head's input, the embedding-row gradients;
+  * one process per GPU — four graph pieces with the collectives between them: the field segment's gradients are
+    reduce-scattered, every rank runs Adam on its 1/N slice, the parameter all-gather lands under the next step's proposal
+    sampling (`sharded_update=False`: two all-reduces over the flat buffer, replicated Adam).
 """
 from __future__ import annotations
 

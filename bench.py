@@ -462,6 +462,7 @@ def run_b200(args) -> None:
         cams = Cameras(c2w, torch.tensor([1200.0], device=dev), torch.tensor([1200.0], device=dev),
                        torch.tensor([Ww / 2], device=dev), torch.tensor([Hh / 2], device=dev),
                        width=torch.tensor([Ww], device=dev), height=torch.tensor([Hh], device=dev))
+        engine.flush()  # multi-GPU sharded update: the last step's parameter all-gather must have landed before the model is read
         model.eval()
         ren = NerfactoRender(model, chunk_rays=1 << 15, mlp_backend=args.mlp)
         ren.render_camera(cams, 0, shard=world > 1)  # warm-up + graph capture
